@@ -1,0 +1,170 @@
+"""Synthetic convex-hull pair workloads.
+
+Everything is unit length scale because every tolerance in the reference is absolute
+(GCLIB_GJKEPA.f90:106,123,140,157,199,203,1172,...).  Hull store layout (the one the C ABI takes):
+hull h is the Fortran ``p(n,3)`` column-major block ``[x(n) | y(n) | z(n)]`` starting at double
+index ``3*hull_off[h]``; ``hull_off`` has ``n_hulls+1`` entries in vertex units.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class PairBatch:
+    verts: np.ndarray      # float64, packed hull blocks
+    hull_off: np.ndarray   # int64, n_hulls+1 (vertex units)
+    pair_a: np.ndarray     # int32, n_pairs
+    pair_b: np.ndarray     # int32, n_pairs
+    name: str = ""
+
+    @property
+    def n_pairs(self) -> int:
+        return int(self.pair_a.shape[0])
+
+    @property
+    def n_hulls(self) -> int:
+        return int(self.hull_off.shape[0] - 1)
+
+    def hull(self, h: int) -> np.ndarray:
+        """(n,3) array of hull h's vertices."""
+        o0, o1 = int(self.hull_off[h]), int(self.hull_off[h + 1])
+        n = o1 - o0
+        return self.verts[3 * o0:3 * o1].reshape(3, n).T.copy()
+
+    def algorithmic_bytes_per_pair(self, out_bytes: int) -> float:
+        """24*(nA+nB) vertex bytes + 8 index bytes + outputs."""
+        n = np.diff(self.hull_off)
+        return float(np.mean(24.0 * (n[self.pair_a] + n[self.pair_b])) + 8 + out_bytes)
+
+
+def _quat_rot(rng: np.random.Generator, m: int) -> np.ndarray:
+    q = rng.standard_normal((m, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    r = np.empty((m, 3, 3))
+    r[:, 0, 0] = 1 - 2 * (y * y + z * z); r[:, 0, 1] = 2 * (x * y - z * w); r[:, 0, 2] = 2 * (x * z + y * w)
+    r[:, 1, 0] = 2 * (x * y + z * w); r[:, 1, 1] = 1 - 2 * (x * x + z * z); r[:, 1, 2] = 2 * (y * z - x * w)
+    r[:, 2, 0] = 2 * (x * z - y * w); r[:, 2, 1] = 2 * (y * z + x * w); r[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return r
+
+
+def _box8_local(rng, m):
+    he = rng.uniform(0.25, 1.0, size=(m, 3))
+    # vertex order: x sign fastest, then y, then z
+    sx = np.array([-1, 1, -1, 1, -1, 1, -1, 1.0])
+    sy = np.array([-1, -1, 1, 1, -1, -1, 1, 1.0])
+    sz = np.array([-1, -1, -1, -1, 1, 1, 1, 1.0])
+    s = np.stack([sx, sy, sz], axis=1)             # (8,3)
+    return s[None, :, :] * he[:, None, :]          # (m,8,3)
+
+
+def _hull_local(rng, m, n):
+    d = rng.standard_normal((m, n, 3))
+    d /= np.linalg.norm(d, axis=2, keepdims=True)
+    ax = rng.uniform(0.5, 1.0, size=(m, 1, 3))
+    return d * ax                                   # ellipsoid surface: every point is extreme
+
+
+def _pack_uniform(pts: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """pts (H,n,3) -> packed blocks, hull_off."""
+    h, n, _ = pts.shape
+    verts = np.ascontiguousarray(pts.transpose(0, 2, 1)).reshape(-1)     # per hull [x|y|z]
+    hull_off = np.arange(h + 1, dtype=np.int64) * n
+    return verts, hull_off
+
+
+def make_pairs(kind: str, n_pairs: int, sigma: float, seed: int = 12345, n_vert: int = 8) -> PairBatch:
+    """Per-pair hulls: pair i = (hull 2i, hull 2i+1); body B translated by N(0, sigma^2)^3."""
+    rng = np.random.default_rng(seed)
+    m = 2 * n_pairs
+    if kind == "box8":
+        loc = _box8_local(rng, m)
+    elif kind == "hull":
+        loc = _hull_local(rng, m, n_vert)
+    else:
+        raise ValueError(kind)
+    rot = _quat_rot(rng, m)
+    pts = np.einsum("mij,mvj->mvi", rot, loc)
+    off = rng.standard_normal((n_pairs, 3)) * sigma
+    pts[1::2] += off[:, None, :]
+    verts, hull_off = _pack_uniform(pts)
+    pa = np.arange(0, m, 2, dtype=np.int32)
+    pb = pa + 1
+    return PairBatch(verts, hull_off, pa, pb, name=f"{kind}{pts.shape[1]}_s{sigma}")
+
+
+def make_mixed(n_pairs: int, sigma: float, seed: int = 12345, n_lo: int = 4, n_hi: int = 64) -> PairBatch:
+    """cfg4: hull(n) with n ~ U{n_lo..n_hi} per body."""
+    rng = np.random.default_rng(seed)
+    m = 2 * n_pairs
+    n = rng.integers(n_lo, n_hi + 1, size=m)
+    hull_off = np.zeros(m + 1, dtype=np.int64)
+    np.cumsum(n, out=hull_off[1:])
+    total = int(hull_off[-1])
+    owner = np.repeat(np.arange(m), n)
+    d = rng.standard_normal((total, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    ax = rng.uniform(0.5, 1.0, size=(m, 3))
+    loc = d * ax[owner]
+    rot = _quat_rot(rng, m)
+    pts = np.einsum("vij,vj->vi", rot[owner], loc)
+    off = np.zeros((m, 3))
+    off[1::2] = rng.standard_normal((n_pairs, 3)) * sigma
+    pts += off[owner]
+    # pack per hull as [x(n)|y(n)|z(n)]
+    verts = np.empty(3 * total)
+    local = np.arange(total) - hull_off[owner]
+    base = 3 * hull_off[owner]
+    verts[base + local] = pts[:, 0]
+    verts[base + n[owner] + local] = pts[:, 1]
+    verts[base + 2 * n[owner] + local] = pts[:, 2]
+    pa = np.arange(0, m, 2, dtype=np.int32)
+    return PairBatch(verts, hull_off, pa, pa + 1, name=f"mixed{n_lo}-{n_hi}_s{sigma}")
+
+
+def make_shared_store(n_bodies: int, n_pairs: int, n_vert: int = 16, seed: int = 12345,
+                      spacing: float = 1.6) -> PairBatch:
+    """cfg5: a shared store of n_bodies hull(n_vert) bodies scattered in a cube whose side gives one
+    body per `spacing`^3, and a broad-phase-like pair list: each pair joins a body with one of its
+    nearby bodies in a spatially sorted order, so a sizeable fraction overlaps."""
+    rng = np.random.default_rng(seed)
+    loc = _hull_local(rng, n_bodies, n_vert)
+    rot = _quat_rot(rng, n_bodies)
+    pts = np.einsum("mij,mvj->mvi", rot, loc)
+    side = spacing * n_bodies ** (1.0 / 3.0)
+    pos = rng.uniform(0.0, side, size=(n_bodies, 3))
+    # sort bodies along a coarse grid key so that neighbours in index are neighbours in space
+    cell = np.floor(pos / (2.0 * spacing)).astype(np.int64)
+    g = int(np.ceil(side / (2.0 * spacing))) + 1
+    key = (cell[:, 2] * g + cell[:, 1]) * g + cell[:, 0]
+    order = np.argsort(key, kind="stable")
+    pos = pos[order]
+    pts = pts + pos[:, None, :]
+    verts, hull_off = _pack_uniform(pts)
+    a = rng.integers(0, n_bodies, size=n_pairs, dtype=np.int64)
+    delta = rng.integers(1, 9, size=n_pairs, dtype=np.int64)
+    b = (a + delta) % n_bodies
+    return PairBatch(verts, hull_off, a.astype(np.int32), b.astype(np.int32), name=f"store{n_bodies}x{n_vert}")
+
+
+def unit_cubes(offset=(0.5, 0.0, 0.0)) -> PairBatch:
+    """cfg1: A = [-.5,.5]^3, B = A + offset."""
+    sx = np.array([-1, 1, -1, 1, -1, 1, -1, 1.0])
+    sy = np.array([-1, -1, 1, 1, -1, -1, 1, 1.0])
+    sz = np.array([-1, -1, -1, -1, 1, 1, 1, 1.0])
+    a = 0.5 * np.stack([sx, sy, sz], axis=1)
+    b = a + np.asarray(offset, dtype=np.float64)[None, :]
+    verts, hull_off = _pack_uniform(np.stack([a, b]))
+    return PairBatch(verts, hull_off, np.array([0], np.int32), np.array([1], np.int32), name="cubes")
+
+
+CONFIGS = {
+    # name: (factory, kwargs, mode)   -- BASELINE.json configs[1..4]
+    "cfg2": (make_pairs, dict(kind="box8", sigma=1.0), "gjk"),
+    "cfg3": (make_pairs, dict(kind="hull", n_vert=32, sigma=0.85), "epa"),
+    "cfg4": (make_mixed, dict(sigma=0.25), "epa"),
+    "cfg4deep": (make_pairs, dict(kind="hull", n_vert=64, sigma=0.05), "epa"),
+}

@@ -1,0 +1,183 @@
+"""Host-side mirror of the reference interface for the GJK+EPA path.
+
+``GJKEPA(version_, TOL_FF_, p1_, p2_)`` keeps the argument names and meaning of
+``SUBROUTINE GJKEPA`` (reference src/GCLIB_GJKEPA.f90:39-52) and returns its six outputs;
+``Engine`` is the batch form (one context per GPU).  Everything computes in the CUDA library
+through the C ABI of include/gjkepa.h -- there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import MODE_EPA, MODE_FULL, MODE_GJK
+
+EXIT_NAMES = {
+    0: "none", 1: "sphere", 2: "init_cap", 3: "dup3", 4: "tri_origin", 5: "coplanar4",
+    6: "init_contain", 7: "loop_cap", 8: "loop_collinear", 9: "loop_coplanar",
+    10: "loop_contain", 11: "loop_stall", 12: "stop",
+}
+ST_EPA_CAP, ST_STOP, ST_HULL_FAIL, ST_BAD_VERSION, ST_H1, ST_TOPO_WARN = (
+    1 << 24, 1 << 25, 1 << 26, 1 << 27, 1 << 28, 1 << 29)
+
+_MODES = {"gjk": MODE_GJK, "epa": MODE_EPA, "full": MODE_FULL,
+          MODE_GJK: MODE_GJK, MODE_EPA: MODE_EPA, MODE_FULL: MODE_FULL}
+
+
+class GjkEpaError(RuntimeError):
+    pass
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+class Engine:
+    """One narrow-phase context bound to one GPU (wraps gjkepa_create/gjkepa_destroy)."""
+
+    def __init__(self, device: int = 0, lanes: int = 0):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        rc = self._L.gjkepa_create(C.byref(h), int(device))
+        if rc != _lib.OK or not h:
+            raise GjkEpaError(
+                f"gjkepa_create(device={device}) failed with code {rc}: no usable sm_100a CUDA device "
+                "(this package has no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+        if lanes:
+            self.set_lanes(lanes)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gjkepa_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != _lib.OK:
+            msg = self._L.gjkepa_last_error(self._h)
+            raise GjkEpaError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+    def set_lanes(self, lanes: int):
+        self._check(self._L.gjkepa_set_lanes(self._h, int(lanes)), "gjkepa_set_lanes")
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._L.gjkepa_set_stream(self._h, C.c_void_p(int(cuda_stream))), "gjkepa_set_stream")
+
+    def sync(self):
+        self._check(self._L.gjkepa_sync(self._h), "gjkepa_sync")
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self._L.gjkepa_launch_count(self._h, 1 if reset else 0))
+
+    # ---- HOST buffers (numpy): copies in, runs, copies out -- the reference-facing call ----
+    def batch_host(self, verts, hull_off, pair_a, pair_b, mode="full", version: int = 1,
+                   tol_ff: float = 1.0, out: Optional[dict] = None, want_status: bool = True,
+                   want_contacts: bool = False) -> dict:
+        mode = _MODES[mode]
+        verts = np.ascontiguousarray(verts, dtype=np.float64)
+        hull_off = np.ascontiguousarray(hull_off, dtype=np.int64)
+        pair_a = np.ascontiguousarray(pair_a, dtype=np.int32)
+        pair_b = np.ascontiguousarray(pair_b, dtype=np.int32)
+        n = int(pair_a.shape[0])
+        nh = int(hull_off.shape[0] - 1)
+        if out is None:
+            out = {"collision": np.empty(n, np.uint8)}
+            if want_status:
+                out["status"] = np.empty(n, np.uint32)
+            if mode >= MODE_EPA:
+                out["depth"] = np.empty(n, np.float64)
+                out["normal"] = np.empty((n, 3), np.float64)
+            if mode >= MODE_FULL:
+                out["colli_type"] = np.empty(n, np.int32)
+                out["nearest"] = np.empty((n, 6), np.float64)
+                out["point"] = np.empty((n, 3), np.float64)
+            if want_contacts:
+                out["contact_index"] = np.empty(n, np.int32)
+        nc = C.c_int64(0)
+        rc = self._L.gjkepa_batch_f64(
+            self._h, int(version), float(tol_ff), nh, _np_ptr(verts), _np_ptr(hull_off), n,
+            _np_ptr(pair_a), _np_ptr(pair_b), mode,
+            _np_ptr(out.get("collision")), _np_ptr(out.get("colli_type")), _np_ptr(out.get("nearest")),
+            _np_ptr(out.get("normal")), _np_ptr(out.get("point")), _np_ptr(out.get("depth")),
+            _np_ptr(out.get("status")),
+            C.cast(C.byref(nc), C.c_void_p) if want_contacts else C.c_void_p(0),
+            _np_ptr(out.get("contact_index")))
+        self._check(rc, "gjkepa_batch_f64")
+        if want_contacts:
+            out["n_contacts"] = int(nc.value)
+        return out
+
+    # ---- DEVICE buffers (torch CUDA tensors already resident in HBM), asynchronous ----
+    def batch_device(self, verts, hull_off, pair_a, pair_b, mode="full", version: int = 1,
+                     tol_ff: float = 1.0, out: Optional[dict] = None, want_status: bool = True,
+                     want_contacts: bool = False) -> dict:
+        import torch
+        mode = _MODES[mode]
+        dev = verts.device
+        assert dev.type == "cuda" and verts.dtype == torch.float64 and hull_off.dtype == torch.int64
+        assert pair_a.dtype == torch.int32 and pair_b.dtype == torch.int32
+        n = int(pair_a.shape[0])
+        nh = int(hull_off.shape[0] - 1)
+        if out is None:
+            out = {"collision": torch.empty(n, dtype=torch.uint8, device=dev)}
+            if want_status:
+                out["status"] = torch.empty(n, dtype=torch.int32, device=dev)
+            if mode >= MODE_EPA:
+                out["depth"] = torch.empty(n, dtype=torch.float64, device=dev)
+                out["normal"] = torch.empty((n, 3), dtype=torch.float64, device=dev)
+            if mode >= MODE_FULL:
+                out["colli_type"] = torch.empty(n, dtype=torch.int32, device=dev)
+                out["nearest"] = torch.empty((n, 6), dtype=torch.float64, device=dev)
+                out["point"] = torch.empty((n, 3), dtype=torch.float64, device=dev)
+            if want_contacts:
+                out["n_contacts"] = torch.zeros(1, dtype=torch.int64, device=dev)
+                out["contact_index"] = torch.empty(n, dtype=torch.int32, device=dev)
+
+        def p(t):
+            return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+        self.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        rc = self._L.gjkepa_batch_device_f64(
+            self._h, int(version), float(tol_ff), nh, p(verts), p(hull_off), n, p(pair_a), p(pair_b), mode,
+            p(out.get("collision")), p(out.get("colli_type")), p(out.get("nearest")), p(out.get("normal")),
+            p(out.get("point")), p(out.get("depth")), p(out.get("status")),
+            p(out.get("n_contacts")), p(out.get("contact_index")))
+        self._check(rc, "gjkepa_batch_device_f64")
+        return out
+
+
+def GJKEPA(version_: int, TOL_FF_: float, p1_, p2_):
+    """Drop-in for ``CALL GJKEPA(version_, TOL_FF_, p1_, p2_, collision_, colliType_,
+    nearest_points_, collision_normal_, collision_point_, penetration_depth_)`` (F:39-52).
+
+    p1_, p2_: (n,3) vertex arrays.  Returns ``(collision_, colliType_, nearest_points_(2,3),
+    collision_normal_(3), collision_point_(3), penetration_depth_)``.  Goes through the C ABI's
+    ``gjkepa_pair_f64`` with every scalar passed by reference, as a Fortran caller would.
+    """
+    L = _lib.lib()
+    p1 = np.asfortranarray(np.asarray(p1_, dtype=np.float64))      # column-major (n,3) = [x|y|z]
+    p2 = np.asfortranarray(np.asarray(p2_, dtype=np.float64))
+    if p1.ndim != 2 or p1.shape[1] != 3 or p2.ndim != 2 or p2.shape[1] != 3:
+        raise ValueError("p1_, p2_ must be (n,3)")
+    ver, tol = C.c_int32(int(version_)), C.c_double(float(TOL_FF_))
+    n1, n2 = C.c_int32(p1.shape[0]), C.c_int32(p2.shape[0])
+    col, typ, dep = C.c_uint8(0), C.c_int32(0), C.c_double(0.0)
+    near = np.zeros((2, 3), order="F")
+    nrm, pt = np.zeros(3), np.zeros(3)
+    dp = C.POINTER(C.c_double)
+    rc = L.gjkepa_pair_f64(C.byref(ver), C.byref(tol), p1.ctypes.data_as(dp), C.byref(n1),
+                           p2.ctypes.data_as(dp), C.byref(n2), C.byref(col), C.byref(typ),
+                           near.ctypes.data_as(dp), nrm.ctypes.data_as(dp), pt.ctypes.data_as(dp), C.byref(dep))
+    if rc != _lib.OK:
+        raise GjkEpaError(f"gjkepa_pair_f64 failed with code {rc} (no usable sm_100a CUDA device?)")
+    return bool(col.value), int(typ.value), np.ascontiguousarray(near), nrm, pt, float(dep.value)

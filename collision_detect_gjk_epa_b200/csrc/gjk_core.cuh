@@ -1,0 +1,441 @@
+// gjk_core.cuh -- GJK intersection test for one convex-hull pair, run by a sub-warp of L lanes.
+//
+// Path: GJKEPA driver (reference src/GCLIB_GJKEPA.f90:76-236, "F:<line>") with support_mapping
+// (F:1030-1062), update_simplex_GJK (F:1070-1157), isPointInSimplex (F:1217-1265), IS_INSIDE_PF
+// (F:1271-1337), UTZVEC/UNINML/DIST_PF_SIGN/VEC_PL (F:1343-1440).  This is not a translation:
+//  * one pair is worked by L in {1,2,4} lanes; lane l owns tetrahedron faces l, l+L, ... and hull
+//    vertices l, l+L, ...; the support function is a sub-warp (value,index) max-dot reduction;
+//  * the four face normals are computed ONCE per simplex and shared by the containment test of
+//    this walk step and the face pick of the next (the reference computes them twice), and the
+//    degeneracy tests reuse face (1,2,3)'s cross product;
+//  * the two opposite initial supports come from one pass (first arg-max and first arg-min).
+// Flags must be bit-exact with the reference arithmetic, so every product/sum that feeds a
+// comparison goes through mul()/add() (never contracted to FMA), divisions and square roots are
+// IEEE, scans keep the first index on ties and reductions break ties towards the lower index.
+//
+// The L=1 instantiation is plain C++ and is also compiled by g++ (tests/host_sim) to check the
+// shared logic against the oracle on a machine without a GPU.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define GJK_HD __host__ __device__ __forceinline__
+#define GJK_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define GJK_HD inline
+#define GJK_HD_NOINLINE
+#endif
+
+namespace gjk {
+
+// ---- exit paths (values = include/gjkepa.h GJKEPA_EXIT_*) ----
+enum : int {
+    EXIT_SPHERE = 1, EXIT_INIT_CAP = 2, EXIT_DUP3 = 3, EXIT_TRI_ORIGIN = 4, EXIT_COPLANAR4 = 5,
+    EXIT_INIT_CONTAIN = 6, EXIT_LOOP_CAP = 7, EXIT_LOOP_COLLINEAR = 8, EXIT_LOOP_COPLANAR = 9,
+    EXIT_LOOP_CONTAIN = 10, EXIT_LOOP_STALL = 11, EXIT_STOP = 12
+};
+GJK_HD bool exit_is_collision(int e) { return e == EXIT_TRI_ORIGIN || e == EXIT_INIT_CONTAIN || e == EXIT_LOOP_CONTAIN; }
+
+// ---- non-contracting arithmetic ----
+GJK_HD double mul(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;            // host builds use -ffp-contract=off
+#endif
+}
+GJK_HD double add(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+GJK_HD double sub(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+
+struct Vec3 { double x, y, z; };
+
+GJK_HD Vec3 v3(double x, double y, double z) { Vec3 r; r.x = x; r.y = y; r.z = z; return r; }
+GJK_HD Vec3 operator-(Vec3 a, Vec3 b) { return v3(sub(a.x, b.x), sub(a.y, b.y), sub(a.z, b.z)); }
+GJK_HD Vec3 neg(Vec3 a) { return v3(-a.x, -a.y, -a.z); }
+GJK_HD double dot3(Vec3 a, Vec3 b)
+{   // DOT_PRODUCT: ((a1*b1) + a2*b2) + a3*b3   (the leading 0+ only affects the sign of zero)
+    return add(add(mul(a.x, b.x), mul(a.y, b.y)), mul(a.z, b.z));
+}
+GJK_HD Vec3 cross3(Vec3 a, Vec3 b)
+{   // F:1208-1210
+    return v3(sub(mul(a.y, b.z), mul(a.z, b.y)),
+              sub(mul(a.z, b.x), mul(a.x, b.z)),
+              sub(mul(a.x, b.y), mul(a.y, b.x)));
+}
+GJK_HD double norm3(Vec3 v) { return sqrt(add(add(mul(v.x, v.x), mul(v.y, v.y)), mul(v.z, v.z))); }
+GJK_HD Vec3 divs(Vec3 v, double s) { return v3(v.x / s, v.y / s, v.z / s); }
+GJK_HD Vec3 utzvec_md(Vec3 v, double md) { return md < 1.0e-12 ? v3(0.0, 0.0, 0.0) : divs(v, md); }   // F:1349-1350
+GJK_HD Vec3 utzvec(Vec3 v) { return utzvec_md(v, norm3(v)); }
+GJK_HD bool close3(Vec3 a, Vec3 b)
+{ return fabs(sub(a.x, b.x)) < 1.0e-8 && fabs(sub(a.y, b.y)) < 1.0e-8 && fabs(sub(a.z, b.z)) < 1.0e-8; }
+GJK_HD Vec3 sel(bool c, Vec3 a, Vec3 b) { return v3(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
+GJK_HD Vec3 pick4(const Vec3 *s, int i)
+{   // register-friendly s[i] for runtime i
+    Vec3 r = s[0];
+    r = sel(i == 1, s[1], r); r = sel(i == 2, s[2], r); r = sel(i == 3, s[3], r);
+    return r;
+}
+
+// IS_INSIDE_PF for a triangle, F:1271-1337 (quirks Q2/Q3 kept).  Cold: only inside the 1e-8 bands.
+GJK_HD_NOINLINE bool inside_pf3(Vec3 v0, Vec3 v1, Vec3 v2, Vec3 p)
+{
+    double c0 = sub(mul(sub(v1.x, v0.x), sub(p.y, v0.y)), mul(sub(v1.y, v0.y), sub(p.x, v0.x)));
+    double c1 = sub(mul(sub(v2.x, v1.x), sub(p.y, v1.y)), mul(sub(v2.y, v1.y), sub(p.x, v1.x)));
+    double c2 = sub(mul(sub(v0.x, v2.x), sub(p.y, v2.y)), mul(sub(v0.y, v2.y), sub(p.x, v2.x)));
+    if (fabs(c0) < 1.0e-12) c0 = 0.0;
+    if (fabs(c1) < 1.0e-12) c1 = 0.0;
+    if (fabs(c2) < 1.0e-12) c2 = 0.0;
+    if (!(c0 > 1.0e-15 || c1 > 1.0e-15 || c2 > 1.0e-15)) {        // F:1310: re-project on XZ
+        c0 = sub(mul(sub(v1.x, v0.x), sub(p.z, v0.z)), mul(sub(v1.z, v0.z), sub(p.x, v0.x)));
+        c1 = sub(mul(sub(v2.x, v1.x), sub(p.z, v1.z)), mul(sub(v2.z, v1.z), sub(p.x, v1.x)));
+        c2 = sub(mul(sub(v0.x, v2.x), sub(p.z, v2.z)), mul(sub(v0.z, v2.z), sub(p.x, v2.x)));
+    }
+    if (mul(c0, c0) < 0.0) return false;
+    if (mul(c0, c1) < 0.0) return false;
+    if (mul(c0, c2) < 0.0) return false;
+    return true;
+}
+
+// ---- hull access ----
+struct HullView {
+    const double *x, *y, *z;     // Fortran p(n,3) block: y = x+n, z = x+2n
+    int n;
+    GJK_HD Vec3 get(int i) const
+    {
+#if defined(__CUDA_ARCH__)
+        return v3(__ldg(x + i), __ldg(y + i), __ldg(z + i));
+#else
+        return v3(x[i], y[i], z[i]);
+#endif
+    }
+};
+
+// per-hull envelope sphere, F:1175-1182 (pair independent: computed once per hull by K0)
+struct Sphere { double cx, cy, cz, r; };
+
+GJK_HD Sphere hull_sphere(const HullView &h)
+{
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int i = 0; i < h.n; ++i) { Vec3 v = h.get(i); sx = add(sx, v.x); sy = add(sy, v.y); sz = add(sz, v.z); }
+    double dn = (double)h.n;
+    Sphere s; s.cx = sx / dn; s.cy = sy / dn; s.cz = sz / dn;
+    double r = -DBL_MAX;
+    Vec3 c = v3(s.cx, s.cy, s.cz);
+    for (int i = 0; i < h.n; ++i) { double t = norm3(h.get(i) - c); if (t > r) r = t; }
+    s.r = r;
+    return s;
+}
+GJK_HD bool sphere_hit(const Sphere &a, const Sphere &b)
+{   // F:1185: NORM2(mp1-mp2) <= r1 + r2 + 1.0
+    return norm3(v3(a.cx, a.cy, a.cz) - v3(b.cx, b.cy, b.cz)) <= add(add(a.r, b.r), 1.0);
+}
+
+// ---- sub-warp of L lanes ----
+template <int L> struct Lanes;
+
+template <> struct Lanes<1> {
+    int lane;
+    GJK_HD Lanes() : lane(0) {}
+    GJK_HD double bcast(double v, int) const { return v; }
+    GJK_HD int bcast_i(int v, int) const { return v; }
+    GJK_HD bool all(bool p) const { return p; }
+    GJK_HD bool any(bool p) const { return p; }
+    GJK_HD void argmax_first(double &, int &) const {}
+    GJK_HD void argmin_first(double &, int &) const {}
+};
+
+#if defined(__CUDACC__)
+template <int L> struct Lanes {
+    int lane;            // lane within the group
+    unsigned mask;       // warp mask of the group's lanes
+    __device__ __forceinline__ Lanes()
+    {
+        int wl = threadIdx.x & 31;
+        lane = wl & (L - 1);
+        mask = (L == 32) ? 0xffffffffu : (((1u << (L & 31)) - 1u) << (wl & ~(L - 1)));
+    }
+    __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(mask, v, src, L); }
+    __device__ __forceinline__ int bcast_i(int v, int src) const { return __shfl_sync(mask, v, src, L); }
+    __device__ __forceinline__ bool all(bool p) const { return (__ballot_sync(mask, p) & mask) == mask; }
+    __device__ __forceinline__ bool any(bool p) const { return (__ballot_sync(mask, p) & mask) != 0u; }
+    // larger value wins; equal values -> lower index (== first occurrence of the maximum)
+    __device__ __forceinline__ void argmax_first(double &v, int &i) const
+    {
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(mask, v, o, L);
+            int oi = __shfl_xor_sync(mask, i, o, L);
+            bool take = (ov > v) || (ov == v && oi < i);
+            v = take ? ov : v; i = take ? oi : i;
+        }
+    }
+    __device__ __forceinline__ void argmin_first(double &v, int &i) const
+    {
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(mask, v, o, L);
+            int oi = __shfl_xor_sync(mask, i, o, L);
+            bool take = (ov < v) || (ov == v && oi < i);
+            v = take ? ov : v; i = take ? oi : i;
+        }
+    }
+};
+#endif
+
+// support_mapping, F:1030-1062: p1(first argmax d.p1) - p2(first argmax (-d).p2)
+template <int L>
+GJK_HD Vec3 support(const Lanes<L> &g, const HullView &A, const HullView &B, Vec3 d)
+{
+    double bA = -DBL_MAX, bB = -DBL_MAX; int iA = 0, iB = 0;
+    for (int v = g.lane; v < A.n; v += L) { double t = dot3(d, A.get(v)); if (t > bA) { bA = t; iA = v; } }
+    Vec3 nd = neg(d);
+    for (int v = g.lane; v < B.n; v += L) { double t = dot3(nd, B.get(v)); if (t > bB) { bB = t; iB = v; } }
+    g.argmax_first(bA, iA);
+    g.argmax_first(bB, iB);
+    return A.get(iA) - B.get(iB);
+}
+
+// supports along +d and -d from one pass (F:97 and F:103): dot(-d,v) == -dot(d,v) bit for bit, so
+// the first arg-max of dot(-d,.) is the first arg-min of dot(d,.).
+template <int L>
+GJK_HD void support_both(const Lanes<L> &g, const HullView &A, const HullView &B, Vec3 d, Vec3 &sp, Vec3 &sm)
+{
+    double hiA = -DBL_MAX, loA = DBL_MAX, hiB = -DBL_MAX, loB = DBL_MAX;
+    int ihA = 0, ilA = 0, ihB = 0, ilB = 0;
+    for (int v = g.lane; v < A.n; v += L) {
+        double t = dot3(d, A.get(v));
+        if (t > hiA) { hiA = t; ihA = v; }
+        if (t < loA) { loA = t; ilA = v; }
+    }
+    for (int v = g.lane; v < B.n; v += L) {
+        double t = dot3(d, B.get(v));
+        if (t > hiB) { hiB = t; ihB = v; }
+        if (t < loB) { loB = t; ilB = v; }
+    }
+    g.argmax_first(hiA, ihA); g.argmin_first(loA, ilA);
+    g.argmax_first(hiB, ihB); g.argmin_first(loB, ilB);
+    sp = A.get(ihA) - B.get(ilB);      // direction +d
+    sm = A.get(ilA) - B.get(ihB);      // direction -d
+}
+
+#if defined(__CUDACC__)
+__constant__ double c_dir_table[100][3] = {
+#include "dirtable.inc"
+};
+#endif
+static const double h_dir_table[100][3] = {
+#include "dirtable.inc"
+};
+GJK_HD Vec3 dir_table(int row0)
+{
+#if defined(__CUDA_ARCH__)
+    return v3(c_dir_table[row0][0], c_dir_table[row0][1], c_dir_table[row0][2]);
+#else
+    return v3(h_dir_table[row0][0], h_dir_table[row0][1], h_dir_table[row0][2]);
+#endif
+}
+
+// faces (1,3,4) (1,2,4) (1,2,3) (2,3,4) of F:1093-1118 / idFc F:1227-1229, 0-based
+GJK_HD void face_rows(int f, int &a, int &b, int &c)
+{
+    a = (f == 3) ? 1 : 0;
+    b = (f == 0 || f == 3) ? 2 : 1;
+    c = (f == 2) ? 2 : 3;
+}
+
+template <int L> struct Faces {
+    static constexpr int FPL = 4 / L;
+    Vec3 q[FPL];        // UTZVEC((Sa-Sb) x (Sb-Sc)), unflipped
+    double md[FPL];     // |cross|
+};
+
+template <int L>
+GJK_HD void compute_faces(const Lanes<L> &g, const Vec3 *S, Faces<L> &F)
+{
+#pragma unroll
+    for (int j = 0; j < Faces<L>::FPL; ++j) {
+        int f = g.lane + j * L, a, b, c;
+        face_rows(f, a, b, c);
+        Vec3 sa = pick4(S, a), sb = pick4(S, b), sc = pick4(S, c);
+        Vec3 cr = cross3(sa - sb, sb - sc);
+        double m = norm3(cr);
+        F.md[j] = m;
+        F.q[j] = utzvec_md(cr, m);
+    }
+}
+
+GJK_HD Vec3 simplex_mean(const Vec3 *S)
+{   // SUM(simplex_(:,i)) / 4, F:1086, F:1232
+    return v3(add(add(add(S[0].x, S[1].x), S[2].x), S[3].x) / 4.0,
+              add(add(add(S[0].y, S[1].y), S[2].y), S[3].y) / 4.0,
+              add(add(add(S[0].z, S[1].z), S[2].z), S[3].z) / 4.0);
+}
+
+// isPointInSimplex(O, S), F:1217-1265, from precomputed face normals
+template <int L>
+GJK_HD bool contains_origin(const Lanes<L> &g, const Vec3 *S, const Faces<L> &F, Vec3 M)
+{
+    bool band_hit = false, all_pos = true;
+#pragma unroll
+    for (int j = 0; j < Faces<L>::FPL; ++j) {
+        int f = g.lane + j * L;
+        Vec3 ref = pick4(S, f);                                   // simplex_(i,:), F:1240
+        Vec3 n = F.q[j];
+        if (dot3(n, ref - M) < 0.0) n = neg(n);
+        double dist = dot3(ref, n);                               // (simplex_(i,:) - O) . nml(i,:)
+        all_pos = all_pos && (dist > 0.0);
+        if (fabs(dist) < 1.0e-8) {                                // F:1248
+            int a, b, c;
+            face_rows(f, a, b, c);
+            if (inside_pf3(pick4(S, a), pick4(S, b), pick4(S, c), v3(0.0, 0.0, 0.0))) band_hit = true;
+        }
+    }
+    return g.any(band_hit) || g.all(all_pos);
+}
+
+// face pick of update_simplex_GJK, F:1093-1124: returns k and the search direction
+template <int L>
+GJK_HD int pick_face(const Lanes<L> &g, const Vec3 *S, const Faces<L> &F, Vec3 M, Vec3 &dir)
+{
+    Vec3 nu[Faces<L>::FPL];
+    double wbest = 0.0; int fbest = 0;
+#pragma unroll
+    for (int j = 0; j < Faces<L>::FPL; ++j) {
+        int f = g.lane + j * L;
+        Vec3 ref = (f == 3) ? S[1] : S[0];
+        Vec3 n = F.q[j];
+        if (dot3(n, ref - M) < 0.0) n = neg(n);
+        nu[j] = n;
+        double w = dot3(neg(n), ref);                             // DOT(-nml, simplex_(ref,:) - O)
+        if (j == 0 || w > wbest) { wbest = w; fbest = f; }        // MAXLOC: first maximum
+    }
+    g.argmax_first(wbest, fbest);
+    int k = fbest, slot = k / L;
+    Vec3 mine = nu[0];
+#pragma unroll
+    for (int j = 1; j < Faces<L>::FPL; ++j) mine = sel(slot == j, nu[j], mine);
+    dir = v3(g.bcast(mine.x, k % L), g.bcast(mine.y, k % L), g.bcast(mine.z, k % L));
+    return k;
+}
+
+struct GjkOut {
+    int exit_path;
+    int iters;          // walk steps taken, F:182-236
+    int n_support;
+    bool stop_flag;     // reference STOP path (F:1369)
+};
+
+// The whole GJKEPA flag path for one pair.  S: 4 rows, final simplex on return (row 3 zero on the
+// F:140 path, hazard H1).  All lanes of the group return the same values.
+template <int L>
+GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HullView &A, const HullView &B,
+                       const Sphere &sa, const Sphere &sb, Vec3 *S)
+{
+    constexpr int FPL = Faces<L>::FPL;
+    GjkOut o; o.exit_path = 0; o.iters = 0; o.n_support = 0; o.stop_flag = false;
+    const Vec3 O = v3(0.0, 0.0, 0.0);
+    S[0] = S[1] = S[2] = S[3] = O;
+
+    if (!sphere_hit(sa, sb)) { o.exit_path = EXIT_SPHERE; return o; }          // F:76-77
+
+    // ---- initial tetrahedron, F:82-170 ----
+    int it = 0;
+    for (;;) {
+        ++it;
+        if (it > 99) { o.exit_path = EXIT_INIT_CAP; return o; }               // F:86
+        support_both(g, A, B, dir_table(it - 1), S[0], S[1]);                // F:94-103
+        o.n_support += 2;
+        if (!close3(S[0], S[1])) break;                                      // F:106
+    }
+    Vec3 dir;
+    {   // VEC_PL(O, S0, S1), F:1431-1438 (quirk Q4: points from O to its foot on the line)
+        Vec3 ab = S[1] - S[0], ac = O - S[0];
+        double nab = norm3(ab);
+        double t = dot3(ac, ab) / nab;
+        Vec3 u = utzvec_md(ab, nab);
+        Vec3 D = v3(add(S[0].x, mul(t, u.x)), add(S[0].y, mul(t, u.y)), add(S[0].z, mul(t, u.z)));
+        dir = utzvec(D - O);
+    }
+    S[2] = support(g, A, B, dir); ++o.n_support;                             // F:119
+    if (close3(S[2], S[0]) || close3(S[2], S[1])) { o.exit_path = EXIT_DUP3; return o; }   // F:123
+
+    Vec3 c3 = cross3(S[1] - S[0], S[2] - S[1]);                              // F:132-135
+    double md3 = norm3(c3);
+    dir = utzvec_md(c3, md3);
+    {
+        Vec3 vo = O - S[2];
+        double dt = dot3(vo, dir);
+        if (fabs(dt) < 1.0e-8 && inside_pf3(S[0], S[1], S[2], O)) { o.exit_path = EXIT_TRI_ORIGIN; return o; }   // F:140
+        if (dt < 0.0) dir = neg(dir);                                        // F:151
+    }
+    S[3] = support(g, A, B, dir); ++o.n_support;                             // F:154
+    {   // DIST_PF_SIGN(S3, (S0,S1,S2)), F:157, with UNINML's own zero rule (F:1392)
+        bool nz = fabs(c3.x) > 1.0e-12 || fabs(c3.y) > 1.0e-12 || fabs(c3.z) > 1.0e-12;
+        Vec3 n = nz ? divs(c3, md3) : O;
+        if (fabs(n.x) < 1.0e-12 && fabs(n.y) < 1.0e-12 && fabs(n.z) < 1.0e-12) { o.exit_path = EXIT_STOP; o.stop_flag = true; return o; }
+        if (fabs(dot3(S[3] - S[0], n)) < 1.0e-8) { o.exit_path = EXIT_COPLANAR4; return o; }
+    }
+    Faces<L> F;
+    compute_faces(g, S, F);
+    Vec3 M = simplex_mean(S);
+    if (contains_origin(g, S, F, M)) { o.exit_path = EXIT_INIT_CONTAIN; return o; }   // F:164
+
+    // ---- tetrahedron walk, F:178-236 ----
+    Vec3 last1[FPL], last2[FPL];                  // rows lane + j*L of simplex_last_1 / _2
+#pragma unroll
+    for (int j = 0; j < FPL; ++j) { last1[j] = O; last2[j] = O; }
+
+    for (int iter = 1; ; ++iter) {
+        if (iter > 50) { o.iters = 50; o.exit_path = EXIT_LOOP_CAP; return o; }       // F:186
+        o.iters = iter;
+#pragma unroll
+        for (int j = 0; j < FPL; ++j) { last2[j] = last1[j]; last1[j] = pick4(S, g.lane + j * L); }   // F:193-194
+
+        int k = pick_face(g, S, F, M, dir);                                  // F:1093-1124
+        Vec3 sm = support(g, A, B, dir); ++o.n_support;                      // F:1127
+        {
+            int a, b, c;
+            face_rows(k, a, b, c);
+            Vec3 n0 = pick4(S, a), n1 = pick4(S, b), n2 = pick4(S, c);       // F:1130-1150
+            S[0] = n0; S[1] = n1; S[2] = n2; S[3] = sm;
+        }
+        compute_faces(g, S, F);
+        M = simplex_mean(S);
+        {   // F:199-206: face (1,2,3)'s cross product is the one compute_faces used for face 2
+            const int owner = 2 % L, slot = 2 / L;
+            double m2 = g.bcast(F.md[slot], owner);
+            if (m2 < 1.0e-8) { o.exit_path = EXIT_LOOP_COLLINEAR; return o; }
+            Vec3 n = v3(g.bcast(F.q[slot].x, owner), g.bcast(F.q[slot].y, owner), g.bcast(F.q[slot].z, owner));
+            if (fabs(dot3(S[3] - S[0], n)) < 1.0e-8) { o.exit_path = EXIT_LOOP_COPLANAR; return o; }
+        }
+        if (contains_origin(g, S, F, M)) { o.exit_path = EXIT_LOOP_CONTAIN; return o; }   // F:210
+        {   // F:219-234
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < FPL; ++j) {
+                Vec3 r = pick4(S, g.lane + j * L);
+                ok = ok && (close3(r, last1[j]) || close3(r, last2[j]));
+            }
+            if (g.all(ok)) { o.exit_path = EXIT_LOOP_STALL; return o; }
+        }
+    }
+}
+
+}  // namespace gjk

@@ -1,0 +1,349 @@
+// gjkepa_capi.cu -- C ABI (include/gjkepa.h) and host batch scheduler of libgjkepa_b200.so.
+//
+// Replaces, for batches, the call  CALL GJKEPA(version_, TOL_FF_, p1_, p2_, collision_, ...)
+// (reference src/GCLIB_GJKEPA.f90:39-52).  Pipeline per batch, all on one CUDA stream:
+//   K0 hull_prep  -> K1 gjk_kernel<L> (flags + EPA work list) -> K3 epa_kernel (depth, normal,
+//   contact epilogue) on the colliding pairs only.
+// There is no CPU compute path: without a usable device every entry point fails.
+#include "../../include/gjkepa.h"
+#include "gjk_kernels.cuh"
+#include "epa_kernel.cuh"
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+struct gjkepa_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int lanes = 0;
+    // workspace (device)
+    gjk::Sphere *d_sphere = nullptr; int64_t cap_sphere = 0;
+    int32_t *d_wl_pair = nullptr; double *d_wl_simplex = nullptr; int64_t cap_wl = 0;
+    unsigned long long *d_counters = nullptr;      // [0] work-list length, [1] EPA queue head
+    // staging for the host-buffer entry (device)
+    void *d_stage = nullptr; size_t cap_stage = 0;
+    unsigned long long *h_counters = nullptr;      // pinned
+};
+
+namespace {
+
+int fail(gjkepa_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, GJKEPA_ERR_CUDA, #call, e_); } while (0)
+
+template <typename T>
+int ensure(gjkepa_ctx *ctx, T *&p, int64_t &cap, int64_t need)
+{
+    if (need <= cap) return GJKEPA_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    int64_t ncap = need + need / 8 + 1024;
+    cudaError_t e = cudaMalloc((void **)&p, (size_t)ncap * sizeof(T));
+    if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc workspace", e);
+    cap = ncap;
+    return GJKEPA_OK;
+}
+
+int pick_lanes(const gjkepa_ctx *ctx) { return ctx->lanes ? ctx->lanes : 4; }
+
+}  // namespace
+
+extern "C" {
+
+int gjkepa_create(gjkepa_ctx **out, int32_t device)
+{
+    if (!out) return GJKEPA_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return GJKEPA_ERR_CUDA;
+    gjkepa_ctx *ctx = new gjkepa_ctx();
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_counters, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&ctx->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) {
+        // the kernels are built for sm_100a only: fail loudly when the image cannot load here
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, gjk::gjk_kernel<4>);
+    }
+    if (e != cudaSuccess) {
+        fprintf(stderr, "gjkepa_create: %s\n", cudaGetErrorString(e));
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+        if (ctx->d_counters) cudaFree(ctx->d_counters);
+        if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+        delete ctx;
+        return GJKEPA_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return GJKEPA_OK;
+}
+
+int gjkepa_destroy(gjkepa_ctx *ctx)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_sphere) cudaFree(ctx->d_sphere);
+    if (ctx->d_wl_pair) cudaFree(ctx->d_wl_pair);
+    if (ctx->d_wl_simplex) cudaFree(ctx->d_wl_simplex);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return GJKEPA_OK;
+}
+
+int gjkepa_set_stream(gjkepa_ctx *ctx, void *s)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return GJKEPA_OK;
+}
+
+const char *gjkepa_last_error(const gjkepa_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t gjkepa_launch_count(const gjkepa_ctx *ctx, int32_t reset)
+{
+    if (!ctx) return -1;
+    int64_t n = ctx->launches;
+    if (reset) const_cast<gjkepa_ctx *>(ctx)->launches = 0;
+    return n;
+}
+
+int gjkepa_set_lanes(gjkepa_ctx *ctx, int32_t lanes)
+{
+    if (!ctx || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4)) return GJKEPA_ERR_ARG;
+    ctx->lanes = lanes;
+    return GJKEPA_OK;
+}
+
+int gjkepa_sync(gjkepa_ctx *ctx)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return GJKEPA_OK;
+}
+
+int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                            int64_t n_hulls, const double *verts, const int64_t *hull_off,
+                            int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b,
+                            int32_t mode,
+                            uint8_t *collision, int32_t *colli_type, double *nearest,
+                            double *normal, double *point, double *depth,
+                            uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (n_pairs < 0 || n_hulls < 0 || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL)
+        return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or mode");
+    if (n_pairs > 0 && (!verts || !hull_off || !pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    // outputs of non-colliding pairs are zero (F:65-71)
+    if (n_pairs > 0) {
+        if (colli_type) CU(cudaMemsetAsync(colli_type, 0, (size_t)n_pairs * sizeof(int32_t), st));
+        if (nearest)    CU(cudaMemsetAsync(nearest, 0, (size_t)n_pairs * 6 * sizeof(double), st));
+        if (normal)     CU(cudaMemsetAsync(normal, 0, (size_t)n_pairs * 3 * sizeof(double), st));
+        if (point)      CU(cudaMemsetAsync(point, 0, (size_t)n_pairs * 3 * sizeof(double), st));
+        if (depth)      CU(cudaMemsetAsync(depth, 0, (size_t)n_pairs * sizeof(double), st));
+    }
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    if (n_pairs == 0) {
+        if (n_contacts) CU(cudaMemsetAsync(n_contacts, 0, sizeof(int64_t), st));
+        return GJKEPA_OK;
+    }
+
+    int rc = ensure(ctx, ctx->d_sphere, ctx->cap_sphere, n_hulls);
+    if (rc) return rc;
+    const bool want_list = (mode >= GJKEPA_MODE_EPA) || n_contacts || contact_index;
+    if (want_list) {
+        if (n_pairs > ctx->cap_wl) {
+            if (ctx->d_wl_pair) cudaFree(ctx->d_wl_pair);
+            if (ctx->d_wl_simplex) cudaFree(ctx->d_wl_simplex);
+            ctx->d_wl_pair = nullptr; ctx->d_wl_simplex = nullptr; ctx->cap_wl = 0;
+            int64_t ncap = n_pairs + n_pairs / 8 + 1024;
+            cudaError_t e = cudaMalloc((void **)&ctx->d_wl_pair, (size_t)ncap * sizeof(int32_t));
+            if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_wl_simplex, (size_t)ncap * 12 * sizeof(double));
+            if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc EPA work list", e);
+            ctx->cap_wl = ncap;
+        }
+    }
+
+    // K0
+    {
+        int threads = 256;
+        int64_t blocks = (n_hulls + threads - 1) / threads;
+        gjk::hull_prep_kernel<<<(unsigned)blocks, threads, 0, st>>>(verts, hull_off, n_hulls, ctx->d_sphere);
+        ++ctx->launches;
+    }
+    // K1
+    gjk::BatchArgs a;
+    a.verts = verts; a.hull_off = hull_off; a.sphere = ctx->d_sphere;
+    a.pair_a = pair_a; a.pair_b = pair_b; a.n_pairs = n_pairs; a.n_hulls = n_hulls;
+    a.collision = collision; a.status = status;
+    a.wl_pair = want_list ? ctx->d_wl_pair : nullptr;
+    a.wl_simplex = want_list ? ctx->d_wl_simplex : nullptr;
+    a.wl_count = ctx->d_counters;
+    {
+        const int L = pick_lanes(ctx);
+        const int threads = 128;
+        const int64_t groups_per_block = threads / L;
+        int64_t blocks = (n_pairs + groups_per_block - 1) / groups_per_block;
+        const int64_t max_blocks = (int64_t)ctx->sm_count * 64;
+        if (blocks > max_blocks) blocks = max_blocks;
+        if (L == 1)      gjk::gjk_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(a);
+        else if (L == 2) gjk::gjk_kernel<2><<<(unsigned)blocks, threads, 0, st>>>(a);
+        else             gjk::gjk_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(a);
+        ++ctx->launches;
+    }
+    CU(cudaGetLastError());
+
+    // K3 on the colliding pairs
+    if (mode >= GJKEPA_MODE_EPA) {
+        epa::EpaArgs e;
+        e.verts = verts; e.hull_off = hull_off; e.pair_a = pair_a; e.pair_b = pair_b;
+        e.wl_pair = ctx->d_wl_pair; e.wl_simplex = ctx->d_wl_simplex;
+        e.wl_count = ctx->d_counters; e.queue_head = ctx->d_counters + 1;
+        e.version = version; e.tol_ff = tol_ff; e.full = (mode == GJKEPA_MODE_FULL);
+        e.colli_type = colli_type; e.nearest = nearest; e.normal = normal; e.point = point;
+        e.depth = depth; e.status = status;
+        int blocks = 0;
+        rc = epa::launch(e, ctx->sm_count, st, &blocks);
+        if (rc) return fail(ctx, GJKEPA_ERR_CUDA, "epa launch", (cudaError_t)rc);
+        ++ctx->launches;
+        CU(cudaGetLastError());
+    }
+    if (n_contacts)
+        CU(cudaMemcpyAsync(n_contacts, ctx->d_counters, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    if (contact_index)   // the list length lives on the device: copy n_pairs slots, entries beyond *n_contacts are unspecified
+        CU(cudaMemcpyAsync(contact_index, ctx->d_wl_pair, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return GJKEPA_OK;
+}
+
+int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                     int64_t n_hulls, const double *verts, const int64_t *hull_off,
+                     int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
+                     uint8_t *collision, int32_t *colli_type, double *nearest,
+                     double *normal, double *point, double *depth,
+                     uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (n_pairs < 0 || n_hulls < 0) return fail(ctx, GJKEPA_ERR_ARG, "bad sizes");
+    if (n_pairs > 0 && (!verts || !hull_off || !pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (n_pairs == 0) { if (n_contacts) *n_contacts = 0; return GJKEPA_OK; }
+
+    const int64_t n_vert = hull_off[n_hulls];
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const bool need_flags = collision || contact_index || n_contacts;
+    size_t o_verts = 0;
+    size_t o_off   = o_verts + al((size_t)n_vert * 3 * sizeof(double));
+    size_t o_pa    = o_off + al((size_t)(n_hulls + 1) * sizeof(int64_t));
+    size_t o_pb    = o_pa + al((size_t)n_pairs * sizeof(int32_t));
+    size_t o_col   = o_pb + al((size_t)n_pairs * sizeof(int32_t));
+    size_t o_type  = o_col + al(need_flags ? (size_t)n_pairs : 0);
+    size_t o_near  = o_type + al(colli_type ? (size_t)n_pairs * sizeof(int32_t) : 0);
+    size_t o_nrm   = o_near + al(nearest ? (size_t)n_pairs * 6 * sizeof(double) : 0);
+    size_t o_pt    = o_nrm + al(normal ? (size_t)n_pairs * 3 * sizeof(double) : 0);
+    size_t o_dep   = o_pt + al(point ? (size_t)n_pairs * 3 * sizeof(double) : 0);
+    size_t o_st    = o_dep + al(depth ? (size_t)n_pairs * sizeof(double) : 0);
+    size_t total   = o_st + al(status ? (size_t)n_pairs * sizeof(uint32_t) : 0);
+    if (total > ctx->cap_stage) {
+        if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->cap_stage = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_stage, total + total / 8);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
+        ctx->cap_stage = total + total / 8;
+    }
+    char *base = (char *)ctx->d_stage;
+    CU(cudaMemcpyAsync(base + o_verts, verts, (size_t)n_vert * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_off, hull_off, (size_t)(n_hulls + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_pa, pair_a, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_pb, pair_b, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+
+    int rc = gjkepa_batch_device_f64(ctx, version, tol_ff, n_hulls,
+        (const double *)(base + o_verts), (const int64_t *)(base + o_off), n_pairs,
+        (const int32_t *)(base + o_pa), (const int32_t *)(base + o_pb), mode,
+        need_flags ? (uint8_t *)(base + o_col) : nullptr,
+        colli_type ? (int32_t *)(base + o_type) : nullptr,
+        nearest ? (double *)(base + o_near) : nullptr,
+        normal ? (double *)(base + o_nrm) : nullptr,
+        point ? (double *)(base + o_pt) : nullptr,
+        depth ? (double *)(base + o_dep) : nullptr,
+        status ? (uint32_t *)(base + o_st) : nullptr, nullptr, nullptr);
+    if (rc) return rc;
+
+    std::vector<uint8_t> tmp_flags;
+    uint8_t *h_flags = collision;
+    if (need_flags && !h_flags) { tmp_flags.resize((size_t)n_pairs); h_flags = tmp_flags.data(); }
+    if (need_flags) CU(cudaMemcpyAsync(h_flags, base + o_col, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    if (colli_type) CU(cudaMemcpyAsync(colli_type, base + o_type, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (nearest)    CU(cudaMemcpyAsync(nearest, base + o_near, (size_t)n_pairs * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (normal)     CU(cudaMemcpyAsync(normal, base + o_nrm, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (point)      CU(cudaMemcpyAsync(point, base + o_pt, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (depth)      CU(cudaMemcpyAsync(depth, base + o_dep, (size_t)n_pairs * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (status)     CU(cudaMemcpyAsync(status, base + o_st, (size_t)n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+
+    if (n_contacts || contact_index) {
+        int64_t c = 0;
+        for (int64_t i = 0; i < n_pairs; ++i)
+            if (h_flags[i]) { if (contact_index) contact_index[c] = (int32_t)i; ++c; }
+        if (n_contacts) *n_contacts = c;
+    }
+    return GJKEPA_OK;
+}
+
+// ---- drop-in single pair: same dummy-argument list as GJKEPA (F:39-52), everything by reference ----
+static std::mutex g_default_mu;
+static gjkepa_ctx *g_default_ctx = nullptr;
+
+int gjkepa_pair_f64(const int32_t *version, const double *tol_ff,
+                    const double *p1, const int32_t *n1, const double *p2, const int32_t *n2,
+                    uint8_t *collision, int32_t *colli_type,
+                    double *nearest, double *normal, double *point, double *depth)
+{
+    if (!version || !tol_ff || !p1 || !n1 || !p2 || !n2 || *n1 <= 0 || *n2 <= 0) return GJKEPA_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default_ctx) {
+        int rc = gjkepa_create(&g_default_ctx, 0);
+        if (rc) return rc;
+    }
+    std::vector<double> verts((size_t)3 * (*n1 + *n2));
+    std::memcpy(verts.data(), p1, (size_t)3 * *n1 * sizeof(double));
+    std::memcpy(verts.data() + 3 * *n1, p2, (size_t)3 * *n2 * sizeof(double));
+    int64_t off[3] = { 0, *n1, (int64_t)*n1 + *n2 };
+    int32_t pa = 0, pb = 1;
+    uint8_t col = 0; int32_t type = 0; double nr[6] = {0}, nm[3] = {0}, pt[3] = {0}, dp = 0.0;
+    int rc = gjkepa_batch_f64(g_default_ctx, *version, *tol_ff, 2, verts.data(), off, 1, &pa, &pb,
+                              GJKEPA_MODE_FULL, &col, &type, nr, nm, pt, &dp, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (collision) *collision = col;          /* LOGICAL*1: write 1, read "!= 0" */
+    if (colli_type) *colli_type = type;
+    if (nearest) std::memcpy(nearest, nr, sizeof nr);
+    if (normal) std::memcpy(normal, nm, sizeof nm);
+    if (point) std::memcpy(point, pt, sizeof pt);
+    if (depth) *depth = dp;
+    return GJKEPA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+/* gjkepa.h -- C ABI of the B200-native batched GJK+EPA narrow phase (libgjkepa_b200.so).
+ *
+ * Drop-in boundary for ONE path of xiejihong0306/collision-detect-GJK-EPA: the public subroutine
+ *     SUBROUTINE GJKEPA(version_, TOL_FF_, p1_, p2_, collision_, colliType_, nearest_points_,
+ *                       collision_normal_, collision_point_, penetration_depth_)
+ * of MODULE GCLIB_GJKEPA (reference src/GCLIB_GJKEPA.f90:39-52, cited below as F:<line>).
+ * Plain pointers and sizes only; no C++/torch types.  All compute runs in hand-written sm_100a CUDA
+ * kernels; there is NO CPU fallback -- every entry point returns GJKEPA_ERR_CUDA when no device
+ * (or no loadable kernel image) is available.
+ *
+ * Array conventions (Fortran, column-major), identical to the reference dummy arguments:
+ *   hull block   p(n,3)            -> [x(1..n) | y(1..n) | z(1..n)]            (F:46)
+ *   nearest      nearest_points_(2,3) -> [p1x,p2x,p1y,p2y,p1z,p2z]             (F:49)
+ *   normal/point (3)                                                            (F:50-51)
+ * A hull store packs blocks back to back: hull h starts at double index 3*hull_off[h] and has
+ * n_h = hull_off[h+1]-hull_off[h] vertices (hull_off in VERTEX units, n_hulls+1 entries).
+ */
+#ifndef GJKEPA_H
+#define GJKEPA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gjkepa_ctx gjkepa_ctx;
+
+/* return codes: never exit(), never block on stdin (the reference PAUSEs / READs / STOPs at
+ * F:300-302, 337-339, 1370-1372; those paths become status bits below) */
+#define GJKEPA_OK            0
+#define GJKEPA_ERR_ARG       1
+#define GJKEPA_ERR_CUDA      2
+#define GJKEPA_ERR_NOMEM     3
+
+/* how far along the reference call chain a batch goes */
+#define GJKEPA_MODE_GJK      0   /* collision_ only                       (F:76-236)            */
+#define GJKEPA_MODE_EPA      1   /* + penetration_depth_, collision_normal_ (F:263-323, 863-1022) */
+#define GJKEPA_MODE_FULL     2   /* + nearest_points_, collision_point_, colliType_ (F:326-343)  */
+
+/* per-pair status word: bits 0-7 GJK exit path, 8-15 GJK walk iterations (F:182-236),
+ * 16-23 EPA iterations (F:296-323), 24-31 flags */
+#define GJKEPA_EXIT_SPHERE          1   /* F:77  */
+#define GJKEPA_EXIT_INIT_CAP        2   /* F:86  */
+#define GJKEPA_EXIT_DUP3            3   /* F:123 */
+#define GJKEPA_EXIT_TRI_ORIGIN      4   /* F:140 (collision) */
+#define GJKEPA_EXIT_COPLANAR4       5   /* F:157 */
+#define GJKEPA_EXIT_INIT_CONTAIN    6   /* F:164 (collision) */
+#define GJKEPA_EXIT_LOOP_CAP        7   /* F:186 */
+#define GJKEPA_EXIT_LOOP_COLLINEAR  8   /* F:199 */
+#define GJKEPA_EXIT_LOOP_COPLANAR   9   /* F:203 */
+#define GJKEPA_EXIT_LOOP_CONTAIN    10  /* F:210 (collision) */
+#define GJKEPA_EXIT_LOOP_STALL      11  /* F:219-234 */
+#define GJKEPA_EXIT_STOP            12  /* F:1369 degenerate plane: reference STOPs; here FALSE + flag */
+#define GJKEPA_ST_EPA_CAP      (1u << 24)  /* F:299 */
+#define GJKEPA_ST_STOP         (1u << 25)
+#define GJKEPA_ST_HULL_FAIL    (1u << 26)  /* EPA polytope degenerate or over capacity */
+#define GJKEPA_ST_BAD_VERSION  (1u << 27)  /* version_ not 1 or 3 (F:329-340) */
+#define GJKEPA_ST_H1           (1u << 28)  /* F:140 path (simplex row 4 defined as zero) */
+
+/* ---- context: one per GPU (one process per GPU; pairs shard by index across contexts) ---- */
+int  gjkepa_create(gjkepa_ctx **ctx, int32_t device);
+int  gjkepa_destroy(gjkepa_ctx *ctx);
+/* launch on the caller's CUDA stream (cudaStream_t cast to void*); NULL = the context's own stream */
+int  gjkepa_set_stream(gjkepa_ctx *ctx, void *cuda_stream);
+const char *gjkepa_last_error(const gjkepa_ctx *ctx);
+/* kernels launched by this context since creation (or since the last reset); for bench accounting */
+int64_t gjkepa_launch_count(const gjkepa_ctx *ctx, int32_t reset);
+/* tuning knob: lanes per pair in the GJK kernel (1, 2 or 4; 0 = automatic) */
+int  gjkepa_set_lanes(gjkepa_ctx *ctx, int32_t lanes);
+
+/* ---- replaces CALL GJKEPA(...) (F:39-52): one pair, every scalar by reference, HOST arrays ----
+ * Uses a process-wide default context on device 0 (created on first call). */
+int gjkepa_pair_f64(const int32_t *version, const double *tol_ff,
+                    const double *p1, const int32_t *n1, const double *p2, const int32_t *n2,
+                    uint8_t *collision, int32_t *colli_type,
+                    double *nearest /*[6]*/, double *normal /*[3]*/, double *point /*[3]*/,
+                    double *depth);
+
+/* ---- batch form of the same call: n_pairs independent (p1_, p2_) pairs out of one hull store ----
+ * HOST buffers; H2D / D2H copies are part of the call.  Output pointers may be NULL (not wanted).
+ * Outputs are written at the pair's index and are zero for non-colliding pairs, as F:65-71.
+ * contact_index (optional, n_pairs entries) receives the indices of colliding pairs in ascending
+ * order, *n_contacts their count. */
+int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                     int64_t n_hulls, const double *verts, const int64_t *hull_off,
+                     int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
+                     uint8_t *collision, int32_t *colli_type, double *nearest /*6*np*/,
+                     double *normal /*3*np*/, double *point /*3*np*/, double *depth,
+                     uint32_t *status, int64_t *n_contacts, int32_t *contact_index);
+
+/* ---- same, DEVICE buffers already resident in HBM (no copies; asynchronous on the stream) ----
+ * n_contacts_dev: device int64 (optional).  contact_index_dev: optional, UNORDERED on this path. */
+int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                            int64_t n_hulls, const double *verts_dev, const int64_t *hull_off_dev,
+                            int64_t n_pairs, const int32_t *pair_a_dev, const int32_t *pair_b_dev,
+                            int32_t mode,
+                            uint8_t *collision_dev, int32_t *colli_type_dev, double *nearest_dev,
+                            double *normal_dev, double *point_dev, double *depth_dev,
+                            uint32_t *status_dev, int64_t *n_contacts_dev, int32_t *contact_index_dev);
+
+/* block until everything queued by this context has finished */
+int gjkepa_sync(gjkepa_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,28 @@
+// Host build of the product's GJK core (L = 1 lane instantiation of csrc/gjk_core.cuh) so that the
+// logic shared with the CUDA kernels can be compared against the oracle on a machine with no GPU.
+// Test-only: the shipped library never runs this path.
+#include "../../collision_detect_gjk_epa_b200/csrc/gjk_core.cuh"
+#include <cstring>
+
+extern "C" void hostsim_gjk_batch(const double *verts, const int64_t *hull_off, int64_t n_pairs,
+                                  const int32_t *pa, const int32_t *pb,
+                                  uint8_t *collision, uint32_t *status, int32_t *n_support, double *simplex)
+{
+    using namespace gjk;
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        HullView A, B;
+        int64_t oa = hull_off[pa[i]], ob = hull_off[pb[i]];
+        A.n = (int)(hull_off[pa[i] + 1] - oa); A.x = verts + 3 * oa; A.y = A.x + A.n; A.z = A.y + A.n;
+        B.n = (int)(hull_off[pb[i] + 1] - ob); B.x = verts + 3 * ob; B.y = B.x + B.n; B.z = B.y + B.n;
+        Sphere sa = hull_sphere(A), sb = hull_sphere(B);
+        Lanes<1> g;
+        Vec3 S[4];
+        GjkOut o = gjk_pair<1>(g, A, B, sa, sb, S);
+        collision[i] = exit_is_collision(o.exit_path) ? 1 : 0;
+        status[i] = (uint32_t)o.exit_path | ((uint32_t)o.iters << 8) | (o.stop_flag ? (1u << 25) : 0u)
+                  | (o.exit_path == EXIT_TRI_ORIGIN ? (1u << 28) : 0u);
+        n_support[i] = o.n_support;
+        if (simplex) std::memcpy(simplex + 12 * i, S, 12 * sizeof(double));
+    }
+}

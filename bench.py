@@ -1,0 +1,338 @@
+#!/usr/bin/env python3
+"""bench.py -- the GJK(+EPA) hot path on synthetic convex-hull pairs (BASELINE.json / SURVEY.md §8d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg4deep|cfg5]
+    python bench.py --impl reference ...      # the CPU path (oracle port, OpenMP over pairs)
+
+A "step" is one pass of the hot path over one batch.  N=1 workload: BASELINE.json configs[1]
+(1M random pairs of 8-vertex boxes, GJK intersection test only).  For N>1 (torchrun, one rank per
+GPU) the pairs shard by index: every rank runs its own 1M-pair shard, no data-path collective
+("weak" scaling).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "gjk_pair_queries_per_sec"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary GJK+EPA measurement")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def make_workload(name: str, n_pairs: int, seed: int):
+    from collision_detect_gjk_epa_b200 import workloads as W
+    if name == "cfg2":
+        return W.make_pairs("box8", n_pairs, 1.0, seed=seed), "gjk", \
+            "cfg2: 1M random pairs of 8-vertex boxes (random pose, offset N(0,1)), GJK intersection test only"
+    if name == "cfg3":
+        return W.make_pairs("hull", n_pairs, 0.85, seed=seed, n_vert=32), "epa", \
+            "cfg3: 1M pairs of 32-vertex hulls, ~52% overlapping, GJK+EPA depth and normal"
+    if name == "cfg4":
+        return W.make_mixed(n_pairs, 0.25, seed=seed), "epa", "cfg4: mixed 4-64 vertex hulls, offset N(0,0.25), GJK+EPA"
+    if name == "cfg4deep":
+        return W.make_pairs("hull", n_pairs, 0.05, seed=seed, n_vert=64), "epa", "cfg4 deep slice: 64-vertex hulls, offset N(0,0.05)"
+    if name == "cfg5":
+        return W.make_shared_store(max(1000, n_pairs // 10), n_pairs, n_vert=16, seed=seed), "epa", \
+            "cfg5: pairs over a shared store of 16-vertex hulls (10 pairs per body), GJK+EPA"
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": float(self.max_mhz) if self.max_mhz else None,
+                "samples": len(self.samples), "reasons": sorted(self.reasons)}
+
+
+def cpu_rate(batch, mode, sample_pairs, threads=0, repeats=1):
+    """Times the CPU path (oracle port: C restatement of GCLIB_GJKEPA.f90, OpenMP over pairs)."""
+    from oracle import orc
+    n = min(sample_pairs, batch.n_pairs)
+    omode = {"gjk": orc.MODE_GJK, "epa": orc.MODE_EPA, "full": orc.MODE_FULL}[mode]
+    pa, pb = batch.pair_a[:n], batch.pair_b[:n]
+    best, used, hits = None, 1, 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        o = orc.batch(batch.verts, batch.hull_off, pa, pb, mode=omode, n_threads=threads)
+        dt = time.perf_counter() - t0
+        used, hits = o["threads"], int(o["collision"].sum())
+        best = dt if best is None else min(best, dt)
+    return n / best, used, n, hits, best
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    batch, mode, desc = make_workload(args.workload, args.pairs, seed=12345)
+    sample = min(batch.n_pairs, 250_000)
+    for _ in range(args.warmup):
+        cpu_rate(batch, mode, min(sample, 20_000))
+    t0 = time.perf_counter()
+    n_done = 0
+    for _ in range(args.steps):
+        rate, used, n, hits, dt = cpu_rate(batch, mode, sample)
+        n_done += n
+    total = time.perf_counter() - t0
+    value = n_done / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "pairs_per_step": sample, "mode": mode},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
+                         "sample": f"first {sample} pairs of the workload per step; C restatement of "
+                                   "GCLIB_GJKEPA.f90 (not gfortran: no Fortran compiler in the image), "
+                                   "OpenMP parallel-for over pairs"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from collision_detect_gjk_epa_b200 import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the GJK/EPA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch, mode, desc = make_workload(args.workload, args.pairs, seed=12345 + rank)
+    eng = Engine(local_rank, lanes=args.lanes)
+    n = batch.n_pairs
+    out_bytes = {"gjk": 1, "epa": 33, "full": 109}[mode]
+    bytes_per_pair = batch.algorithmic_bytes_per_pair(out_bytes)
+
+    # ---- device-resident inputs ----
+    d_in = [torch.from_numpy(x).to(dev) for x in (batch.verts, batch.hull_off, batch.pair_a, batch.pair_b)]
+    out = None
+
+    def step_device():
+        nonlocal out
+        out = eng.batch_device(*d_in, mode=mode, out=out, want_status=False)
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    eng.launch_count(reset=True)
+    kern = {"hull_prep": 0.0, "gjk": 0.0, "epa": 0.0}
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.launch_count()
+    # per-kernel durations: one more (untimed) profiled step gives a per-launch sample of each kernel
+    ksamples = []
+    eng.set_profiling(True)
+    for _ in range(5):
+        step_device()
+        ksamples.append(eng.kernel_ms())
+    for k in kern:
+        kern[k] = float(np.median([s[k] for s in ksamples]))
+    eng.set_profiling(False)
+    hits = int(out["collision"].sum().item())
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n), float(hits)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total = float(t.item())
+    pairs_all, hits_all = float(tot[0].item()), float(tot[1].item())
+    value = pairs_all * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region) ----
+    def pin(a):
+        tt = torch.from_numpy(a).pin_memory()
+        return tt, tt.numpy()
+    keep = []
+    h_in = []
+    for x in (batch.verts, batch.hull_off, batch.pair_a, batch.pair_b):
+        tt, npv = pin(x)
+        keep.append(tt); h_in.append(npv)
+    h_out = {}
+    okeys = {"gjk": ["collision"], "epa": ["collision", "depth", "normal"],
+             "full": ["collision", "depth", "normal", "colli_type", "nearest", "point"]}[mode]
+    shapes = {"collision": ((n,), np.uint8), "depth": ((n,), np.float64), "normal": ((n, 3), np.float64),
+              "colli_type": ((n,), np.int32), "nearest": ((n, 6), np.float64), "point": ((n, 3), np.float64)}
+    for k in okeys:
+        tt = torch.empty(shapes[k][0], dtype=getattr(torch, np.dtype(shapes[k][1]).name), pin_memory=True)
+        keep.append(tt); h_out[k] = tt.numpy()
+    h2d = int(sum(x.nbytes for x in h_in))
+    d2h = int(sum(v.nbytes for v in h_out.values()))
+    eng._L.gjkepa_use_own_stream(eng._h)
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        eng.batch_host(*h_in, mode=mode, out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.batch_host(*h_in, mode=mode, out=h_out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = pairs_all * e2e_steps / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = None, "fallback"
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text()); peak_src = "measured"
+    peak_gbs = float(peaks["hbm_gbs"]) if peaks else 6650.0
+    dom = "epa" if (mode != "gjk" and kern["epa"] > kern["gjk"]) else "gjk"
+    dom_units = hits if dom == "epa" else n                       # units one launch of that kernel processes (rank 0)
+    dom_bytes = bytes_per_pair * dom_units
+    achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9 if kern[dom] > 0 else None
+    step_ms = ms_total / args.steps
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "pairs_per_gpu_per_step": n, "mode": mode, "sharding": f"pairs by index x{world}",
+                   "l2": "inputs larger than L2 (hull store %.0f MB per GPU)" % (batch.verts.nbytes / 1e6),
+                   "algorithmic_bytes_per_pair": bytes_per_pair,
+                   "colliding_fraction": hits_all / pairs_all, "lanes_per_pair": args.lanes or 4},
+        "contacts_per_s": hits_all * args.steps / (ms_total * 1e-3),
+        "roofline": {"bound": "hbm", "kernel": {"gjk": "gjk_kernel", "epa": "epa_kernel"}[dom],
+                     "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": (achieved / peak_gbs) if achieved else None, "peak_source": peak_src, "traffic": None,
+                     "kernel_ms": kern, "kernel_share_of_step": kern[dom] / step_ms if step_ms else None},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "api": "gjkepa_batch_f64 (C ABI, pinned host buffers)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if not args.no_cpu:
+        sample = min(n, 1_000_000)
+        rate, used, ns, _, dt = cpu_rate(batch, mode, sample, repeats=2)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": used, "kind": "port",
+                                "sample": f"first {ns} pairs of the same workload, best of 2 ({dt:.2f} s); C restatement "
+                                          "of GCLIB_GJKEPA.f90 (no Fortran compiler in the image), OpenMP over pairs"}
+    if not args.no_extra and args.workload == "cfg2" and world == 1:
+        # secondary headline: GJK+EPA contacts/s on cfg3 (1M pairs of 32-vertex hulls)
+        b3, m3, d3 = make_workload("cfg3", args.pairs, seed=12345)
+        t3 = [torch.from_numpy(x).to(dev) for x in (b3.verts, b3.hull_off, b3.pair_a, b3.pair_b)]
+        o3 = None
+        for _ in range(3):
+            o3 = eng.batch_device(*t3, mode=m3, out=o3, want_status=False)
+        torch.cuda.synchronize()
+        k3 = max(3, min(args.steps, 20))
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(k3):
+            o3 = eng.batch_device(*t3, mode=m3, out=o3, want_status=False)
+        f1.record()
+        torch.cuda.synchronize()
+        ms3 = f0.elapsed_time(f1) / k3
+        h3 = int(o3["collision"].sum().item())
+        line["extra"] = {"workload": d3, "ms_per_step": ms3, "pairs_per_s": b3.n_pairs / ms3 * 1e3,
+                         "contacts_per_s": h3 / ms3 * 1e3, "contacts": h3,
+                         "algorithmic_gbs": b3.algorithmic_bytes_per_pair(33) * b3.n_pairs / (ms3 * 1e-3) / 1e9}
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,8 +20,8 @@ MODE_GJK, MODE_EPA, MODE_FULL = 0, 1, 2
 
 # every symbol include/gjkepa.h declares
 SYMBOLS = [
-    "gjkepa_create", "gjkepa_destroy", "gjkepa_set_stream", "gjkepa_last_error",
-    "gjkepa_launch_count", "gjkepa_set_lanes", "gjkepa_pair_f64", "gjkepa_batch_f64",
+    "gjkepa_create", "gjkepa_destroy", "gjkepa_set_stream", "gjkepa_use_own_stream", "gjkepa_last_error",
+    "gjkepa_launch_count", "gjkepa_set_lanes", "gjkepa_set_profiling", "gjkepa_kernel_ms", "gjkepa_pair_f64", "gjkepa_batch_f64",
     "gjkepa_batch_device_f64", "gjkepa_sync",
 ]
 
@@ -60,12 +60,18 @@ def lib() -> C.CDLL:
     L.gjkepa_destroy.restype = C.c_int
     L.gjkepa_set_stream.argtypes = [vp, vp]
     L.gjkepa_set_stream.restype = C.c_int
+    L.gjkepa_use_own_stream.argtypes = [vp]
+    L.gjkepa_use_own_stream.restype = C.c_int
     L.gjkepa_last_error.argtypes = [vp]
     L.gjkepa_last_error.restype = C.c_char_p
     L.gjkepa_launch_count.argtypes = [vp, C.c_int32]
     L.gjkepa_launch_count.restype = C.c_int64
     L.gjkepa_set_lanes.argtypes = [vp, C.c_int32]
     L.gjkepa_set_lanes.restype = C.c_int
+    L.gjkepa_set_profiling.argtypes = [vp, C.c_int32]
+    L.gjkepa_set_profiling.restype = C.c_int
+    L.gjkepa_kernel_ms.argtypes = [vp, dp]
+    L.gjkepa_kernel_ms.restype = C.c_int
     L.gjkepa_sync.argtypes = [vp]
     L.gjkepa_sync.restype = C.c_int
     L.gjkepa_pair_f64.argtypes = [ip, dp, dp, ip, dp, ip, C.POINTER(C.c_uint8), ip, dp, dp, dp, dp]

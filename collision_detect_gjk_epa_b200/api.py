@@ -73,6 +73,15 @@ class Engine:
     def set_stream(self, cuda_stream: int):
         self._check(self._L.gjkepa_set_stream(self._h, C.c_void_p(int(cuda_stream))), "gjkepa_set_stream")
 
+    def set_profiling(self, on: bool):
+        self._check(self._L.gjkepa_set_profiling(self._h, 1 if on else 0), "gjkepa_set_profiling")
+
+    def kernel_ms(self) -> dict:
+        """Durations (ms) of K0 hull-prep, K1 GJK, K3 EPA of the last batch (needs set_profiling(True))."""
+        ms = (C.c_double * 3)()
+        self._check(self._L.gjkepa_kernel_ms(self._h, ms), "gjkepa_kernel_ms")
+        return {"hull_prep": ms[0], "gjk": ms[1], "epa": ms[2]}
+
     def sync(self):
         self._check(self._L.gjkepa_sync(self._h), "gjkepa_sync")
 

@@ -31,6 +31,10 @@ struct gjkepa_ctx {
     // staging for the host-buffer entry (device)
     void *d_stage = nullptr; size_t cap_stage = 0;
     unsigned long long *h_counters = nullptr;      // pinned
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool profiling = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid[3] = {false, false, false};      // K0, K1, K3 recorded by the last batch
 };
 
 namespace {
@@ -82,6 +86,7 @@ int gjkepa_create(gjkepa_ctx **out, int32_t device)
         cudaFuncAttributes fa;
         e = cudaFuncGetAttributes(&fa, gjk::gjk_kernel<4>);
     }
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e != cudaSuccess) {
         fprintf(stderr, "gjkepa_create: %s\n", cudaGetErrorString(e));
         if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -107,6 +112,7 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
     return GJKEPA_OK;
 }
@@ -114,7 +120,14 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
 int gjkepa_set_stream(gjkepa_ctx *ctx, void *s)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    ctx->stream = (cudaStream_t)s;          // taken literally: NULL is CUDA's legacy default stream
+    return GJKEPA_OK;
+}
+
+int gjkepa_use_own_stream(gjkepa_ctx *ctx)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    ctx->stream = ctx->own_stream;
     return GJKEPA_OK;
 }
 
@@ -132,6 +145,28 @@ int gjkepa_set_lanes(gjkepa_ctx *ctx, int32_t lanes)
 {
     if (!ctx || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4)) return GJKEPA_ERR_ARG;
     ctx->lanes = lanes;
+    return GJKEPA_OK;
+}
+
+int gjkepa_set_profiling(gjkepa_ctx *ctx, int32_t on)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    ctx->profiling = on != 0;
+    return GJKEPA_OK;
+}
+
+int gjkepa_kernel_ms(gjkepa_ctx *ctx, double *ms)
+{
+    if (!ctx || !ms) return GJKEPA_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    for (int k = 0; k < 3; ++k) {
+        ms[k] = 0.0;
+        if (!ctx->ev_valid[k]) continue;
+        float t = 0.f;
+        CU(cudaEventSynchronize(ctx->ev[2 * k + 1]));
+        CU(cudaEventElapsedTime(&t, ctx->ev[2 * k], ctx->ev[2 * k + 1]));
+        ms[k] = (double)t;
+    }
     return GJKEPA_OK;
 }
 
@@ -188,11 +223,15 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         }
     }
 
+    ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = false;
+    const bool prof = ctx->profiling;
     // K0
     {
         int threads = 256;
         int64_t blocks = (n_hulls + threads - 1) / threads;
+        if (prof) CU(cudaEventRecord(ctx->ev[0], st));
         gjk::hull_prep_kernel<<<(unsigned)blocks, threads, 0, st>>>(verts, hull_off, n_hulls, ctx->d_sphere);
+        if (prof) { CU(cudaEventRecord(ctx->ev[1], st)); ctx->ev_valid[0] = true; }
         ++ctx->launches;
     }
     // K1
@@ -210,9 +249,11 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         int64_t blocks = (n_pairs + groups_per_block - 1) / groups_per_block;
         const int64_t max_blocks = (int64_t)ctx->sm_count * 64;
         if (blocks > max_blocks) blocks = max_blocks;
+        if (prof) CU(cudaEventRecord(ctx->ev[2], st));
         if (L == 1)      gjk::gjk_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(a);
         else if (L == 2) gjk::gjk_kernel<2><<<(unsigned)blocks, threads, 0, st>>>(a);
         else             gjk::gjk_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(a);
+        if (prof) { CU(cudaEventRecord(ctx->ev[3], st)); ctx->ev_valid[1] = true; }
         ++ctx->launches;
     }
     CU(cudaGetLastError());
@@ -227,8 +268,10 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         e.colli_type = colli_type; e.nearest = nearest; e.normal = normal; e.point = point;
         e.depth = depth; e.status = status;
         int blocks = 0;
+        if (prof) CU(cudaEventRecord(ctx->ev[4], st));
         rc = epa::launch(e, ctx->sm_count, st, &blocks);
         if (rc) return fail(ctx, GJKEPA_ERR_CUDA, "epa launch", (cudaError_t)rc);
+        if (prof) { CU(cudaEventRecord(ctx->ev[5], st)); ctx->ev_valid[2] = true; }
         ++ctx->launches;
         CU(cudaGetLastError());
     }

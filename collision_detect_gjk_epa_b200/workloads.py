@@ -126,27 +126,33 @@ def make_mixed(n_pairs: int, sigma: float, seed: int = 12345, n_lo: int = 4, n_h
 
 
 def make_shared_store(n_bodies: int, n_pairs: int, n_vert: int = 16, seed: int = 12345,
-                      spacing: float = 1.6) -> PairBatch:
-    """cfg5: a shared store of n_bodies hull(n_vert) bodies scattered in a cube whose side gives one
-    body per `spacing`^3, and a broad-phase-like pair list: each pair joins a body with one of its
-    nearby bodies in a spatially sorted order, so a sizeable fraction overlaps."""
+                      spacing: float = 1.0, chunk: int = 1 << 20) -> PairBatch:
+    """cfg5: a shared store of n_bodies hull(n_vert) bodies on a jittered cubic lattice (pitch
+    `spacing`, body i at lattice site (i % g, i//g % g, i//g^2)) and a broad-phase-like pair list:
+    each pair joins a random body with one of its 13 forward lattice neighbours, so x-neighbours are
+    adjacent in the store and y/z-neighbours are far apart in memory.  Built in chunks to bound host
+    memory at 10M bodies."""
     rng = np.random.default_rng(seed)
-    loc = _hull_local(rng, n_bodies, n_vert)
-    rot = _quat_rot(rng, n_bodies)
-    pts = np.einsum("mij,mvj->mvi", rot, loc)
-    side = spacing * n_bodies ** (1.0 / 3.0)
-    pos = rng.uniform(0.0, side, size=(n_bodies, 3))
-    # sort bodies along a coarse grid key so that neighbours in index are neighbours in space
-    cell = np.floor(pos / (2.0 * spacing)).astype(np.int64)
-    g = int(np.ceil(side / (2.0 * spacing))) + 1
-    key = (cell[:, 2] * g + cell[:, 1]) * g + cell[:, 0]
-    order = np.argsort(key, kind="stable")
-    pos = pos[order]
-    pts = pts + pos[:, None, :]
-    verts, hull_off = _pack_uniform(pts)
+    g = int(np.ceil(n_bodies ** (1.0 / 3.0)))
+    verts = np.empty(3 * n_vert * n_bodies)
+    vview = verts.reshape(n_bodies, 3, n_vert)
+    for lo in range(0, n_bodies, chunk):
+        hi = min(n_bodies, lo + chunk)
+        m = hi - lo
+        loc = _hull_local(rng, m, n_vert)
+        rot = _quat_rot(rng, m)
+        pts = np.einsum("mij,mvj->mvi", rot, loc)
+        idx = np.arange(lo, hi)
+        site = np.stack([idx % g, (idx // g) % g, idx // (g * g)], axis=1).astype(np.float64)
+        pos = (site + rng.uniform(-0.3, 0.3, size=(m, 3))) * spacing
+        pts += pos[:, None, :]
+        vview[lo:hi] = pts.transpose(0, 2, 1)
+    hull_off = np.arange(n_bodies + 1, dtype=np.int64) * n_vert
+    fwd = np.array([(dx, dy, dz) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)
+                    if (dz, dy, dx) > (0, 0, 0)], dtype=np.int64)           # 13 forward neighbours
+    stride = fwd[:, 0] + g * fwd[:, 1] + g * g * fwd[:, 2]
     a = rng.integers(0, n_bodies, size=n_pairs, dtype=np.int64)
-    delta = rng.integers(1, 9, size=n_pairs, dtype=np.int64)
-    b = (a + delta) % n_bodies
+    b = (a + stride[rng.integers(0, 13, size=n_pairs)]) % n_bodies
     return PairBatch(verts, hull_off, a.astype(np.int32), b.astype(np.int32), name=f"store{n_bodies}x{n_vert}")
 
 

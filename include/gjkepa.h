@@ -60,11 +60,19 @@ typedef struct gjkepa_ctx gjkepa_ctx;
 /* ---- context: one per GPU (one process per GPU; pairs shard by index across contexts) ---- */
 int  gjkepa_create(gjkepa_ctx **ctx, int32_t device);
 int  gjkepa_destroy(gjkepa_ctx *ctx);
-/* launch on the caller's CUDA stream (cudaStream_t cast to void*); NULL = the context's own stream */
+/* A new context launches on its own non-blocking stream.  gjkepa_set_stream switches to the
+ * caller's stream (cudaStream_t cast to void*, taken literally: NULL is CUDA's legacy default
+ * stream); gjkepa_use_own_stream switches back. */
 int  gjkepa_set_stream(gjkepa_ctx *ctx, void *cuda_stream);
+int  gjkepa_use_own_stream(gjkepa_ctx *ctx);
 const char *gjkepa_last_error(const gjkepa_ctx *ctx);
 /* kernels launched by this context since creation (or since the last reset); for bench accounting */
 int64_t gjkepa_launch_count(const gjkepa_ctx *ctx, int32_t reset);
+/* optional per-kernel timing: when on, every batch records CUDA events around K0 (hull prep),
+ * K1 (GJK) and K3 (EPA) on the launching stream; gjkepa_kernel_ms waits for the last batch and
+ * returns their durations in milliseconds in ms[0..2] (0 for a kernel that did not run). */
+int  gjkepa_set_profiling(gjkepa_ctx *ctx, int32_t on);
+int  gjkepa_kernel_ms(gjkepa_ctx *ctx, double *ms /*[3]*/);
 /* tuning knob: lanes per pair in the GJK kernel (1, 2 or 4; 0 = automatic) */
 int  gjkepa_set_lanes(gjkepa_ctx *ctx, int32_t lanes);
 

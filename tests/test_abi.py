@@ -1,0 +1,50 @@
+"""The C-ABI shared library: loads, exports every symbol include/gjkepa.h declares, and refuses to
+work without a CUDA device (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_functions():
+    txt = (ROOT / "include" / "gjkepa.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gjkepa_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from collision_detect_gjk_epa_b200 import _lib
+    _lib.build()
+    L = C.CDLL(str(_lib.SO_PATH))
+    names = header_functions()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from collision_detect_gjk_epa_b200 import Engine, GjkEpaError, GJKEPA, workloads, _lib
+    with pytest.raises(GjkEpaError):
+        Engine(0)
+    b = workloads.unit_cubes()
+    with pytest.raises(GjkEpaError):
+        GJKEPA(1, 1.0, b.hull(0), b.hull(1))
+    h = C.c_void_p()
+    assert _lib.lib().gjkepa_create(C.byref(h), 0) == _lib.ERR_CUDA and not h
+
+
+def test_product_does_not_touch_the_oracle():
+    # the product path may not import, link or execute anything under oracle/
+    pkg = ROOT / "collision_detect_gjk_epa_b200"
+    bad = re.compile(r"(from\s+oracle|import\s+oracle|oracle/|gjkepa_oracle|orc_gjkepa|liborc)")
+    for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("Makefile")):
+        assert not bad.search(p.read_text()), p
+    out = __import__("subprocess").run(["ldd", str(pkg / "libgjkepa_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out

@@ -1,0 +1,196 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI (ctypes -> libgjkepa_b200.so),
+against the oracle on the same seeded inputs, the committed golden fixture, and size-independent
+properties at full size.  Bars: collision flags and GJK exit path / walk iterations BIT-EXACT;
+penetration depth |d_gpu - d_ref| <= 1e-9 * max(d_ref, 1) (unit hull scale) and normal
+1 - |cos| <= 1e-9 (north_star: "about 1e-9 in real(8)")."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+DEPTH_RTOL = 1e-9
+NORMAL_TOL = 1e-9
+
+
+def check_against_oracle(orc, eng, b, mode, lanes=(1, 2, 4), version=1, tol_ff=1.0):
+    omode = {"gjk": orc.MODE_GJK, "epa": orc.MODE_EPA, "full": orc.MODE_FULL}[mode]
+    ref = orc.batch(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=omode, version=version, tol_ff=tol_ff)
+    for L in lanes:
+        eng.set_lanes(L)
+        got = eng.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=mode, version=version, tol_ff=tol_ff)
+        assert np.array_equal(got["collision"], ref["collision"]), f"flags differ (lanes={L})"
+        assert np.array_equal(got["status"] & 0xffff, ref["status"] & 0xffff), f"GJK exit path/iterations differ (lanes={L})"
+        if mode == "gjk":
+            continue
+        hit = ref["collision"] > 0
+        clean = hit & ((ref["status"] >> 24) == 0)
+        assert np.all((got["status"][clean] >> 24) == 0)
+        d_ref, d_got = ref["depth"][clean], got["depth"][clean]
+        assert np.all(np.abs(d_got - d_ref) <= DEPTH_RTOL * np.maximum(d_ref, 1.0))
+        cosd = np.sum(got["normal"][clean] * ref["normal"][clean], axis=1)
+        if version == 1:
+            assert np.all(1.0 - cosd <= NORMAL_TOL)                  # same orientation too
+        # non-colliding pairs keep the zeroed outputs of F:65-71
+        assert np.all(got["depth"][~hit] == 0.0) and np.all(got["normal"][~hit] == 0.0)
+        if mode == "full":
+            assert np.array_equal(got["colli_type"][clean], ref["colli_type"][clean])
+            assert np.all(got["colli_type"][~hit] == 0) and np.all(got["nearest"][~hit] == 0.0)
+            # collision point: a selected vertex / mean of vertices under the oracle's tie rules
+            assert np.mean(np.all(np.abs(got["point"][clean] - ref["point"][clean]) <= 1e-9, axis=1)) > 0.999
+            # nearest points are support vertices along +-normal: ties between near-coplanar vertices may
+            # resolve differently (normals differ in the last bits), the support VALUE may not
+            n = np.diff(b.hull_off)
+            idx = np.nonzero(clean)[0][:2000]
+            for i in idx:
+                A, B = b.hull(b.pair_a[i]), b.hull(b.pair_b[i])
+                nr = got["normal"][i]
+                pa = got["nearest"][i].reshape(3, 2)[:, 0]; pb = got["nearest"][i].reshape(3, 2)[:, 1]
+                assert abs(pa @ nr - (A @ nr).max()) <= 1e-9 and abs(pb @ nr - (B @ nr).min()) <= 1e-9
+    return ref
+
+
+@pytest.mark.parametrize("off,coll,depth,nrm", [
+    ((0.5, 0.0, 0.0), True, 0.5, (1, 0, 0)),
+    ((0.5, 0.25, 0.125), True, 0.5, (1, 0, 0)),
+    ((1.5, 0.0, 0.0), False, 0.0, (0, 0, 0)),
+    ((1.0, 0.0, 0.0), True, 0.0, (1, 0, 0)),
+])
+def test_cfg1_unit_cubes_through_the_drop_in_call(W, orc, off, coll, depth, nrm):
+    # BASELINE.json configs[0], through gjkepa_pair_f64 (all scalars by reference)
+    from collision_detect_gjk_epa_b200 import GJKEPA
+    b = W.unit_cubes(off)
+    col, typ, near, n, pt, dep = GJKEPA(1, 1.0, b.hull(0), b.hull(1))
+    assert col == coll and abs(dep - depth) < 1e-12 and np.allclose(n, nrm, atol=1e-12)
+    o = orc.pair(b.hull(0), b.hull(1))
+    assert col == o["collision"] and typ == o["colli_type"] and np.allclose(pt, o["point"], atol=1e-12)
+    assert near.shape == (2, 3)
+    if coll:
+        assert abs(near[0] @ n - 0.5) < 1e-12                        # p1 support along +normal
+
+
+def test_cfg1_cubes_batch_all_lane_widths(W, orc, engine):
+    for off in [(0.5, 0, 0), (0.5, 0.25, 0.125), (1.5, 0, 0), (1.0, 0, 0), (0.5, 0.5, 0), (0.25, 0.5, 0.75), (1, 1, 1)]:
+        check_against_oracle(orc, engine, W.unit_cubes(off), "full")
+
+
+def test_coincident_cubes_defined_status(W, orc, engine):
+    b = W.unit_cubes((0.0, 0.0, 0.0))                                # hazard H1: never blocks, never exits
+    got = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="full")
+    assert got["collision"][0] == 1 and (got["status"][0] & 0xff) == 4 and got["status"][0] & (1 << 28)
+    assert got["depth"][0] == 0.0
+
+
+def test_cfg2_box8_gjk_flags_bit_exact(W, orc, engine):
+    check_against_oracle(orc, engine, W.make_pairs("box8", 300000, 1.0), "gjk")
+
+
+def test_box8_full_outputs(W, orc, engine):
+    check_against_oracle(orc, engine, W.make_pairs("box8", 60000, 1.0, seed=3), "full")
+
+
+def test_cfg3_hull32_gjk_epa(W, orc, engine):
+    check_against_oracle(orc, engine, W.make_pairs("hull", 120000, 0.85, n_vert=32), "full")
+
+
+def test_cfg4_mixed_sizes_and_deep_penetration(W, orc, engine):
+    check_against_oracle(orc, engine, W.make_mixed(60000, 0.25), "full")
+    check_against_oracle(orc, engine, W.make_pairs("hull", 8000, 0.05, n_vert=64), "epa")
+
+
+def test_cfg5_shared_hull_store(W, orc, engine):
+    b = W.make_shared_store(50000, 200000, n_vert=16)
+    ref = check_against_oracle(orc, engine, b, "epa", lanes=(4,))
+    assert 0.02 < ref["collision"].mean() < 0.98
+
+
+def test_small_and_ragged_hulls(W, orc, engine):
+    check_against_oracle(orc, engine, W.make_pairs("hull", 100000, 0.15, n_vert=5), "full")
+    check_against_oracle(orc, engine, W.make_pairs("hull", 100000, 0.5, n_vert=4), "full")
+    check_against_oracle(orc, engine, W.make_mixed(30000, 0.6, seed=5, n_lo=4, n_hi=9), "full")
+
+
+def test_version3_turntable_contact_point(W, orc, engine):
+    check_against_oracle(orc, engine, W.make_pairs("hull", 20000, 0.5, seed=8, n_vert=12), "full", version=3)
+
+
+def test_tolff_threshold_is_honoured(W, orc, engine):
+    check_against_oracle(orc, engine, W.make_pairs("box8", 20000, 0.8, seed=9), "full", tol_ff=0.05)
+
+
+def test_golden_fixture(W, golden, engine):
+    g = golden
+    for L in (1, 2, 4):
+        engine.set_lanes(L)
+        got = engine.batch_host(g["verts"], g["hull_off"], g["pair_a"], g["pair_b"], mode="epa")
+        assert np.array_equal(got["collision"], g["collision"])
+        assert np.array_equal(got["status"] & 0xff, g["exit_path"])
+        assert np.array_equal((got["status"] >> 8) & 0xff, g["gjk_iters"])
+        m = g["epa_ok"] > 0
+        assert np.all(np.abs(got["depth"][m] - g["depth"][m]) <= DEPTH_RTOL * np.maximum(g["depth"][m], 1.0))
+        assert np.all(1.0 - np.sum(got["normal"][m] * g["normal"][m], axis=1) <= NORMAL_TOL)
+
+
+def test_empty_batch_and_single_pair(W, engine):
+    b = W.make_pairs("box8", 4, 1.0)
+    got = engine.batch_host(b.verts, b.hull_off, b.pair_a[:0], b.pair_b[:0], mode="full", want_contacts=True)
+    assert got["collision"].shape == (0,) and got["n_contacts"] == 0
+    got = engine.batch_host(b.verts, b.hull_off, b.pair_a[:1], b.pair_b[:1], mode="full", want_contacts=True)
+    assert got["collision"].shape == (1,) and got["n_contacts"] == int(got["collision"][0])
+
+
+def test_contact_list_is_sorted_and_complete(W, engine):
+    b = W.make_pairs("hull", 50000, 0.85, n_vert=16)
+    got = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="epa", want_contacts=True)
+    idx = got["contact_index"][:got["n_contacts"]]
+    assert np.array_equal(idx, np.nonzero(got["collision"])[0])
+
+
+def test_device_resident_entry_matches_host_entry(W, engine):
+    import torch
+    b = W.make_pairs("hull", 100000, 0.85, n_vert=32)
+    host = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="full")
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(x).to(dev) for x in (b.verts, b.hull_off, b.pair_a, b.pair_b)]
+    out = engine.batch_device(*t, mode="full", want_contacts=True)
+    torch.cuda.synchronize()
+    for k in ("collision", "depth", "normal", "colli_type", "nearest", "point"):
+        assert np.array_equal(out[k].cpu().numpy(), host[k]), k
+    assert np.array_equal(out["status"].cpu().numpy().view(np.uint32), host["status"])
+    nc = int(out["n_contacts"].item())
+    assert nc == int(host["collision"].sum())
+    assert np.array_equal(np.sort(out["contact_index"][:nc].cpu().numpy()), np.nonzero(host["collision"])[0])
+    engine.sync()
+
+
+def test_full_size_properties_1m_pairs(W, orc, engine):
+    """BASELINE.json sizes (1M pairs), through properties that need no full oracle run:
+    determinism across runs and lane widths, zeroed outputs for misses, unit normals, and
+    'translate p2 by (depth +- margin) * normal' separates / keeps the contact."""
+    b = W.make_pairs("hull", 1_000_000, 0.85, n_vert=32)
+    engine.set_lanes(4)
+    r4 = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="epa")
+    engine.set_lanes(1)
+    r1 = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="epa")
+    for k in ("collision", "status", "depth", "normal"):
+        assert np.array_equal(r4[k], r1[k]), k                       # idempotent, lane-width independent
+    hit = r4["collision"] > 0
+    assert 0.45 < hit.mean() < 0.60                                  # ~52.5 % collide
+    assert np.all((r4["status"][hit] >> 24) == 0)
+    assert np.all(np.abs(np.linalg.norm(r4["normal"][hit], axis=1) - 1.0) < 1e-12)
+    assert np.all(r4["depth"][hit] >= 0.0) and np.all(r4["depth"][~hit] == 0.0)
+    # spot-check a bounded sample against the oracle at this size
+    sel = np.random.default_rng(0).choice(b.n_pairs, 20000, replace=False).astype(np.int64)
+    ref = orc.batch(b.verts, b.hull_off, b.pair_a[sel], b.pair_b[sel], mode=orc.MODE_EPA)
+    assert np.array_equal(ref["collision"], r4["collision"][sel])
+    h = ref["collision"] > 0
+    assert np.all(np.abs(ref["depth"][h] - r4["depth"][sel][h]) <= DEPTH_RTOL * np.maximum(ref["depth"][h], 1.0))
+    # separation property on the colliding pairs: shift body B and re-run GJK only
+    for sign, expect in ((+1.0, 0), (-1.0, 1)):
+        verts = b.verts.copy()
+        n = 32
+        v = verts.reshape(-1, 3, n)                                  # per hull [x|y|z]
+        shift = np.zeros((b.n_pairs, 3))
+        shift[hit] = (r4["depth"][hit] + sign * 1e-6)[:, None] * r4["normal"][hit]
+        v[1::2] += shift[:, :, None]
+        g = engine.batch_host(verts, b.hull_off, b.pair_a, b.pair_b, mode="gjk")
+        assert np.all(g["collision"][hit] == expect)

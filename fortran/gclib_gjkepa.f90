@@ -1,0 +1,126 @@
+!  gclib_gjkepa.f90 -- drop-in replacement for MODULE GCLIB_GJKEPA of
+!  xiejihong0306/collision-detect-GJK-EPA (src/GCLIB_GJKEPA.f90), backed by libgjkepa_b200.so.
+!
+!  Host code keeps  USE GCLIB_GJKEPA  and  CALL GJKEPA(version_, TOL_FF_, p1_, p2_, collision_,
+!  colliType_, nearest_points_, collision_normal_, collision_point_, penetration_depth_)  with the
+!  dummy-argument list of the reference (lines 39-52 there); the body is a thin ISO_C_BINDING call
+!  into the C ABI of include/gjkepa.h.  GJKEPA_BATCH is new: n_pairs independent pairs per call, which
+!  is where the GPU pays off (one pair per call costs two PCIe round trips).
+!
+!  NOT COMPILED IN THIS REPOSITORY'S IMAGE: there is no Fortran compiler here (see INTEGRATION.md).
+!  Build with e.g.  gfortran -c gclib_gjkepa.f90  and link  -L<repo>/collision_detect_gjk_epa_b200
+!  -lgjkepa_b200.  The C ABI underneath is exercised by the test-suite through ctypes with exactly
+!  these conventions (every scalar by reference, column-major arrays).
+MODULE GCLIB_GJKEPA
+    USE, INTRINSIC :: ISO_C_BINDING
+    IMPLICIT NONE
+    PRIVATE
+    PUBLIC :: GJKEPA, GJKEPA_BATCH, GJKEPA_CTX_CREATE, GJKEPA_CTX_DESTROY
+
+    INTEGER(C_INT32_T), PARAMETER, PUBLIC :: GJKEPA_MODE_GJK = 0, GJKEPA_MODE_EPA = 1, GJKEPA_MODE_FULL = 2
+
+    INTERFACE
+        FUNCTION gjkepa_pair_f64(version, tol_ff, p1, n1, p2, n2, collision, colli_type, &
+                                 nearest, normal, point, depth) BIND(C, NAME="gjkepa_pair_f64") RESULT(rc)
+            IMPORT :: C_INT, C_INT32_T, C_DOUBLE, C_INT8_T
+            INTEGER(C_INT32_T), INTENT(IN)  :: version, n1, n2
+            REAL(C_DOUBLE),     INTENT(IN)  :: tol_ff
+            REAL(C_DOUBLE),     INTENT(IN)  :: p1(*), p2(*)          ! p(n,3) column-major = [x|y|z]
+            INTEGER(C_INT8_T),  INTENT(OUT) :: collision
+            INTEGER(C_INT32_T), INTENT(OUT) :: colli_type
+            REAL(C_DOUBLE),     INTENT(OUT) :: nearest(2,3), normal(3), point(3), depth
+            INTEGER(C_INT) :: rc
+        END FUNCTION gjkepa_pair_f64
+
+        FUNCTION gjkepa_create(ctx, device) BIND(C, NAME="gjkepa_create") RESULT(rc)
+            IMPORT :: C_PTR, C_INT, C_INT32_T
+            TYPE(C_PTR), INTENT(OUT) :: ctx
+            INTEGER(C_INT32_T), VALUE :: device
+            INTEGER(C_INT) :: rc
+        END FUNCTION gjkepa_create
+
+        FUNCTION gjkepa_destroy(ctx) BIND(C, NAME="gjkepa_destroy") RESULT(rc)
+            IMPORT :: C_PTR, C_INT
+            TYPE(C_PTR), VALUE :: ctx
+            INTEGER(C_INT) :: rc
+        END FUNCTION gjkepa_destroy
+
+        FUNCTION gjkepa_batch_f64(ctx, version, tol_ff, n_hulls, verts, hull_off, n_pairs, pair_a, pair_b, &
+                                  mode, collision, colli_type, nearest, normal, point, depth, status, &
+                                  n_contacts, contact_index) BIND(C, NAME="gjkepa_batch_f64") RESULT(rc)
+            IMPORT :: C_PTR, C_INT, C_INT32_T, C_INT64_T, C_DOUBLE
+            TYPE(C_PTR), VALUE :: ctx
+            INTEGER(C_INT32_T), VALUE :: version, mode
+            REAL(C_DOUBLE), VALUE :: tol_ff
+            INTEGER(C_INT64_T), VALUE :: n_hulls, n_pairs
+            TYPE(C_PTR), VALUE :: verts, hull_off, pair_a, pair_b
+            TYPE(C_PTR), VALUE :: collision, colli_type, nearest, normal, point, depth, status
+            TYPE(C_PTR), VALUE :: n_contacts, contact_index
+            INTEGER(C_INT) :: rc
+        END FUNCTION gjkepa_batch_f64
+    END INTERFACE
+
+CONTAINS
+
+    ! Same dummy list as the reference's GJKEPA.  p1_/p2_ stay assumed-shape; passing them to the
+    ! explicit-size BIND(C) dummies makes the compiler hand over contiguous column-major copies.
+    SUBROUTINE GJKEPA(version_, TOL_FF_, p1_, p2_, collision_, colliType_, &
+                      nearest_points_, collision_normal_, collision_point_, penetration_depth_)
+        INTEGER*4, INTENT(IN)  :: version_
+        REAL*8,    INTENT(IN)  :: TOL_FF_
+        REAL*8,    INTENT(IN)  :: p1_(:,:), p2_(:,:)
+        LOGICAL*1, INTENT(OUT) :: collision_
+        INTEGER*4, INTENT(OUT) :: colliType_
+        REAL*8,    INTENT(OUT) :: nearest_points_(2,3), collision_normal_(3), collision_point_(3)
+        REAL*8,    INTENT(OUT) :: penetration_depth_
+        INTEGER(C_INT8_T)  :: flag
+        INTEGER(C_INT32_T) :: n1, n2
+        INTEGER(C_INT)     :: rc
+        n1 = INT(SIZE(p1_, 1), C_INT32_T)
+        n2 = INT(SIZE(p2_, 1), C_INT32_T)
+        rc = gjkepa_pair_f64(version_, TOL_FF_, p1_, n1, p2_, n2, flag, colliType_, &
+                             nearest_points_, collision_normal_, collision_point_, penetration_depth_)
+        IF (rc /= 0) ERROR STOP "GJKEPA: the CUDA narrow phase is unavailable (no CPU fallback)"
+        collision_ = (flag /= 0)        ! the library writes 1; Intel's .TRUE. is -1, so test "/= 0"
+    END SUBROUTINE GJKEPA
+
+    SUBROUTINE GJKEPA_CTX_CREATE(ctx, device)
+        TYPE(C_PTR), INTENT(OUT) :: ctx
+        INTEGER*4, INTENT(IN) :: device
+        IF (gjkepa_create(ctx, INT(device, C_INT32_T)) /= 0) ERROR STOP "GJKEPA_CTX_CREATE failed"
+    END SUBROUTINE GJKEPA_CTX_CREATE
+
+    SUBROUTINE GJKEPA_CTX_DESTROY(ctx)
+        TYPE(C_PTR), INTENT(INOUT) :: ctx
+        INTEGER(C_INT) :: rc
+        rc = gjkepa_destroy(ctx)
+        ctx = C_NULL_PTR
+    END SUBROUTINE GJKEPA_CTX_DESTROY
+
+    ! verts: hull blocks back to back, hull h = p(n_h,3) column-major starting at 3*hull_off(h)+1
+    ! (hull_off is 0-based, in vertices, n_hulls+1 entries).  pair_a/pair_b: 0-based hull numbers.
+    SUBROUTINE GJKEPA_BATCH(ctx, version_, TOL_FF_, verts, hull_off, pair_a, pair_b, mode, &
+                            collision_, colliType_, nearest_points_, collision_normal_, &
+                            collision_point_, penetration_depth_, status_)
+        TYPE(C_PTR), INTENT(IN) :: ctx
+        INTEGER*4, INTENT(IN) :: version_, mode
+        REAL*8,    INTENT(IN) :: TOL_FF_
+        REAL(C_DOUBLE),     INTENT(IN), TARGET, CONTIGUOUS :: verts(:)
+        INTEGER(C_INT64_T), INTENT(IN), TARGET, CONTIGUOUS :: hull_off(:)
+        INTEGER(C_INT32_T), INTENT(IN), TARGET, CONTIGUOUS :: pair_a(:), pair_b(:)
+        INTEGER(C_INT8_T),  INTENT(OUT), TARGET, CONTIGUOUS :: collision_(:)
+        INTEGER(C_INT32_T), INTENT(OUT), TARGET, CONTIGUOUS :: colliType_(:), status_(:)
+        REAL(C_DOUBLE),     INTENT(OUT), TARGET, CONTIGUOUS :: nearest_points_(:,:,:)   ! (2,3,n_pairs)
+        REAL(C_DOUBLE),     INTENT(OUT), TARGET, CONTIGUOUS :: collision_normal_(:,:)   ! (3,n_pairs)
+        REAL(C_DOUBLE),     INTENT(OUT), TARGET, CONTIGUOUS :: collision_point_(:,:)    ! (3,n_pairs)
+        REAL(C_DOUBLE),     INTENT(OUT), TARGET, CONTIGUOUS :: penetration_depth_(:)
+        INTEGER(C_INT) :: rc
+        rc = gjkepa_batch_f64(ctx, version_, TOL_FF_, INT(SIZE(hull_off) - 1, C_INT64_T), C_LOC(verts), &
+                              C_LOC(hull_off), INT(SIZE(pair_a), C_INT64_T), C_LOC(pair_a), C_LOC(pair_b), mode, &
+                              C_LOC(collision_), C_LOC(colliType_), C_LOC(nearest_points_), &
+                              C_LOC(collision_normal_), C_LOC(collision_point_), C_LOC(penetration_depth_), &
+                              C_LOC(status_), C_NULL_PTR, C_NULL_PTR)
+        IF (rc /= 0) ERROR STOP "GJKEPA_BATCH: the CUDA narrow phase failed"
+    END SUBROUTINE GJKEPA_BATCH
+
+END MODULE GCLIB_GJKEPA

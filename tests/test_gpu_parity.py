@@ -24,6 +24,9 @@ def check_against_oracle(orc, eng, b, mode, lanes=(1, 2, 4), version=1, tol_ff=1
             continue
         hit = ref["collision"] > 0
         clean = hit & ((ref["status"] >> 24) == 0)
+        if not clean.any():
+            assert np.all(got["depth"][~hit] == 0.0)
+            continue
         assert np.all((got["status"][clean] >> 24) == 0)
         d_ref, d_got = ref["depth"][clean], got["depth"][clean]
         assert np.all(np.abs(d_got - d_ref) <= DEPTH_RTOL * np.maximum(d_ref, 1.0))
@@ -39,8 +42,7 @@ def check_against_oracle(orc, eng, b, mode, lanes=(1, 2, 4), version=1, tol_ff=1
             assert np.mean(np.all(np.abs(got["point"][clean] - ref["point"][clean]) <= 1e-9, axis=1)) > 0.999
             # nearest points are support vertices along +-normal: ties between near-coplanar vertices may
             # resolve differently (normals differ in the last bits), the support VALUE may not
-            n = np.diff(b.hull_off)
-            idx = np.nonzero(clean)[0][:2000]
+            idx = np.nonzero(clean)[0][:2000] if version == 1 else []    # version 3 overwrites the normal (F:335)
             for i in idx:
                 A, B = b.hull(b.pair_a[i]), b.hull(b.pair_b[i])
                 nr = got["normal"][i]

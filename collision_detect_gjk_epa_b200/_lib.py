@@ -21,8 +21,8 @@ MODE_GJK, MODE_EPA, MODE_FULL = 0, 1, 2
 # every symbol include/gjkepa.h declares
 SYMBOLS = [
     "gjkepa_create", "gjkepa_destroy", "gjkepa_set_stream", "gjkepa_use_own_stream", "gjkepa_last_error",
-    "gjkepa_launch_count", "gjkepa_set_lanes", "gjkepa_set_profiling", "gjkepa_kernel_ms", "gjkepa_pair_f64", "gjkepa_batch_f64",
-    "gjkepa_batch_device_f64", "gjkepa_sync",
+    "gjkepa_launch_count", "gjkepa_set_lanes", "gjkepa_set_max_hull_vertices", "gjkepa_set_profiling", "gjkepa_kernel_ms", "gjkepa_pair_f64", "gjkepa_batch_f64",
+    "gjkepa_batch_device_f64", "gjkepa_sync", "gjkepa_debug_fp64",
 ]
 
 
@@ -68,6 +68,8 @@ def lib() -> C.CDLL:
     L.gjkepa_launch_count.restype = C.c_int64
     L.gjkepa_set_lanes.argtypes = [vp, C.c_int32]
     L.gjkepa_set_lanes.restype = C.c_int
+    L.gjkepa_set_max_hull_vertices.argtypes = [vp, C.c_int32]
+    L.gjkepa_set_max_hull_vertices.restype = C.c_int
     L.gjkepa_set_profiling.argtypes = [vp, C.c_int32]
     L.gjkepa_set_profiling.restype = C.c_int
     L.gjkepa_kernel_ms.argtypes = [vp, dp]
@@ -82,5 +84,7 @@ def lib() -> C.CDLL:
     L.gjkepa_batch_f64.restype = C.c_int
     L.gjkepa_batch_device_f64.argtypes = batch_args
     L.gjkepa_batch_device_f64.restype = C.c_int
+    L.gjkepa_debug_fp64.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
+    L.gjkepa_debug_fp64.restype = C.c_int
     _lib = L
     return L

@@ -70,6 +70,9 @@ class Engine:
     def set_lanes(self, lanes: int):
         self._check(self._L.gjkepa_set_lanes(self._h, int(lanes)), "gjkepa_set_lanes")
 
+    def set_max_hull_vertices(self, n: int):
+        self._check(self._L.gjkepa_set_max_hull_vertices(self._h, int(n)), "gjkepa_set_max_hull_vertices")
+
     def set_stream(self, cuda_stream: int):
         self._check(self._L.gjkepa_set_stream(self._h, C.c_void_p(int(cuda_stream))), "gjkepa_set_stream")
 

@@ -28,6 +28,8 @@
 #define GJK_HD_NOINLINE
 #endif
 
+#include "fp64_exact.cuh"
+
 namespace gjk {
 
 // ---- exit paths (values = include/gjkepa.h GJKEPA_EXIT_*) ----
@@ -83,8 +85,41 @@ GJK_HD double norm3(Vec3 v) { return sqrt(add(add(mul(v.x, v.x), mul(v.y, v.y)),
 GJK_HD Vec3 divs(Vec3 v, double s) { return v3(v.x / s, v.y / s, v.z / s); }
 GJK_HD Vec3 utzvec_md(Vec3 v, double md) { return md < 1.0e-12 ? v3(0.0, 0.0, 0.0) : divs(v, md); }   // F:1349-1350
 GJK_HD Vec3 utzvec(Vec3 v) { return utzvec_md(v, norm3(v)); }
+
+// Two interchangeable arithmetic policies with bit-identical results: Exact uses the compiler's
+// sqrt and '/', Fast the straight-line sequences of fp64_exact.cuh (shared reciprocal per vector,
+// no control flow) and clears `ok` when an operand leaves their range -- the caller then redoes the
+// block with Exact.
+struct MathExact {
+    static GJK_HD double nrm(Vec3 v, bool &) { return norm3(v); }
+    static GJK_HD Vec3 dv(Vec3 v, double s, bool &) { return divs(v, s); }
+    static GJK_HD void dv4(Vec3 v, double w, double s, Vec3 &qv, double &qw, bool &) { qv = divs(v, s); qw = w / s; }
+};
+struct MathFast {
+    static GJK_HD double nrm(Vec3 v, bool &ok)
+    { return sqrt_fast(add(add(mul(v.x, v.x), mul(v.y, v.y)), mul(v.z, v.z)), ok); }
+    static GJK_HD Vec3 dv(Vec3 v, double s, bool &ok)
+    {
+        double r = rcp_div_seed(s);
+        return v3(div_with_seed(v.x, s, r, ok), div_with_seed(v.y, s, r, ok), div_with_seed(v.z, s, r, ok));
+    }
+    static GJK_HD void dv4(Vec3 v, double w, double s, Vec3 &qv, double &qw, bool &ok)
+    {
+        double r = rcp_div_seed(s);
+        qv = v3(div_with_seed(v.x, s, r, ok), div_with_seed(v.y, s, r, ok), div_with_seed(v.z, s, r, ok));
+        qw = div_with_seed(w, s, r, ok);
+    }
+};
 GJK_HD bool close3(Vec3 a, Vec3 b)
 { return fabs(sub(a.x, b.x)) < 1.0e-8 && fabs(sub(a.y, b.y)) < 1.0e-8 && fabs(sub(a.z, b.z)) < 1.0e-8; }
+GJK_HD double nan_marker()
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(0x7ff8000000000000LL);
+#else
+    return NAN;
+#endif
+}
 GJK_HD Vec3 sel(bool c, Vec3 a, Vec3 b) { return v3(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
 GJK_HD Vec3 pick4(const Vec3 *s, int i)
 {   // register-friendly s[i] for runtime i
@@ -114,8 +149,9 @@ GJK_HD_NOINLINE bool inside_pf3(Vec3 v0, Vec3 v1, Vec3 v2, Vec3 p)
 }
 
 // ---- hull access ----
+// Global-memory view of a Fortran p(n,3) block [x(n) | y(n) | z(n)].
 struct HullView {
-    const double *x, *y, *z;     // Fortran p(n,3) block: y = x+n, z = x+2n
+    const double *x, *y, *z;     // y = x+n, z = x+2n
     int n;
     GJK_HD Vec3 get(int i) const
     {
@@ -127,19 +163,36 @@ struct HullView {
     }
 };
 
+// The same block staged in shared memory, transposed across the CTA's pairs: element e of the block
+// lives at base[e * stride] (stride = pairs per tile + 1, odd, so that consecutive threads hit
+// consecutive 8-byte banks when they read the same element of their own pair).
+struct HullViewStrided {
+    const double *base;
+    int n, stride;
+    GJK_HD Vec3 get(int i) const
+    { return v3(base[i * stride], base[(n + i) * stride], base[(2 * n + i) * stride]); }
+};
+
 // per-hull envelope sphere, F:1175-1182 (pair independent: computed once per hull by K0)
 struct Sphere { double cx, cy, cz, r; };
 
-GJK_HD Sphere hull_sphere(const HullView &h)
+template <class HV>
+GJK_HD Sphere hull_sphere(const HV &h)
 {
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (int i = 0; i < h.n; ++i) { Vec3 v = h.get(i); sx = add(sx, v.x); sy = add(sy, v.y); sz = add(sz, v.z); }
     double dn = (double)h.n;
     Sphere s; s.cx = sx / dn; s.cy = sy / dn; s.cz = sz / dn;
-    double r = -DBL_MAX;
+    // MAXVAL(NORM2(v_i - c)): a correctly rounded sqrt is monotone, so the maximum of the norms is the
+    // sqrt of the maximum squared norm, bit for bit -- one sqrt per hull instead of n
+    double r2 = -1.0;
     Vec3 c = v3(s.cx, s.cy, s.cz);
-    for (int i = 0; i < h.n; ++i) { double t = norm3(h.get(i) - c); if (t > r) r = t; }
-    s.r = r;
+    for (int i = 0; i < h.n; ++i) {
+        Vec3 d = h.get(i) - c;
+        double t = add(add(mul(d.x, d.x), mul(d.y, d.y)), mul(d.z, d.z));
+        if (t > r2) r2 = t;
+    }
+    s.r = (h.n > 0) ? sqrt(r2) : -DBL_MAX;
     return s;
 }
 GJK_HD bool sphere_hit(const Sphere &a, const Sphere &b)
@@ -200,8 +253,8 @@ template <int L> struct Lanes {
 #endif
 
 // support_mapping, F:1030-1062: p1(first argmax d.p1) - p2(first argmax (-d).p2)
-template <int L>
-GJK_HD Vec3 support(const Lanes<L> &g, const HullView &A, const HullView &B, Vec3 d)
+template <int L, class HV>
+GJK_HD Vec3 support(const Lanes<L> &g, const HV &A, const HV &B, Vec3 d)
 {
     double bA = -DBL_MAX, bB = -DBL_MAX; int iA = 0, iB = 0;
     for (int v = g.lane; v < A.n; v += L) { double t = dot3(d, A.get(v)); if (t > bA) { bA = t; iA = v; } }
@@ -214,8 +267,8 @@ GJK_HD Vec3 support(const Lanes<L> &g, const HullView &A, const HullView &B, Vec
 
 // supports along +d and -d from one pass (F:97 and F:103): dot(-d,v) == -dot(d,v) bit for bit, so
 // the first arg-max of dot(-d,.) is the first arg-min of dot(d,.).
-template <int L>
-GJK_HD void support_both(const Lanes<L> &g, const HullView &A, const HullView &B, Vec3 d, Vec3 &sp, Vec3 &sm)
+template <int L, class HV>
+GJK_HD void support_both(const Lanes<L> &g, const HV &A, const HV &B, Vec3 d, Vec3 &sp, Vec3 &sm)
 {
     double hiA = -DBL_MAX, loA = DBL_MAX, hiB = -DBL_MAX, loB = DBL_MAX;
     int ihA = 0, ilA = 0, ihB = 0, ilB = 0;
@@ -266,19 +319,35 @@ template <int L> struct Faces {
     double md[FPL];     // |cross|
 };
 
-template <int L>
+template <int L, class M, int SKIP>
+GJK_HD bool faces_from_cross(const Vec3 *cr, Faces<L> &F)
+{
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < Faces<L>::FPL; ++j) if (j != SKIP) F.md[j] = M::nrm(cr[j], ok);
+#pragma unroll
+    for (int j = 0; j < Faces<L>::FPL; ++j) if (j != SKIP) {
+        Vec3 q = M::dv(cr[j], F.md[j], ok);
+        F.q[j] = (F.md[j] < 1.0e-12) ? v3(0.0, 0.0, 0.0) : q;       // UTZVEC, F:1349-1350
+    }
+    return ok;
+}
+
+// Unflipped unit normals of the four faces.  SKIP = 2 (L = 1 only): face (1,2,3) of the new simplex is
+// the face the walk just kept, whose cross product has the very same operands, so the caller has
+// already put its normal and norm in slot 2 and it is not recomputed.
+template <int L, int SKIP = -1>
 GJK_HD void compute_faces(const Lanes<L> &g, const Vec3 *S, Faces<L> &F)
 {
+    Vec3 cr[Faces<L>::FPL];
 #pragma unroll
-    for (int j = 0; j < Faces<L>::FPL; ++j) {
+    for (int j = 0; j < Faces<L>::FPL; ++j) if (j != SKIP) {
         int f = g.lane + j * L, a, b, c;
         face_rows(f, a, b, c);
         Vec3 sa = pick4(S, a), sb = pick4(S, b), sc = pick4(S, c);
-        Vec3 cr = cross3(sa - sb, sb - sc);
-        double m = norm3(cr);
-        F.md[j] = m;
-        F.q[j] = utzvec_md(cr, m);
+        cr[j] = cross3(sa - sb, sb - sc);
     }
+    if (!faces_from_cross<L, MathFast, SKIP>(cr, F)) faces_from_cross<L, MathExact, SKIP>(cr, F);
 }
 
 GJK_HD Vec3 simplex_mean(const Vec3 *S)
@@ -335,6 +404,24 @@ GJK_HD int pick_face(const Lanes<L> &g, const Vec3 *S, const Faces<L> &F, Vec3 M
     return k;
 }
 
+// tail of VEC_PL(O, (A, B)), F:1436-1438: D = A + (AC.AB / |AB|) * UTZVEC(AB); returns UTZVEC(D - O).
+// With MathFast a NaN x-component tells the caller to redo the block with MathExact.
+template <class M>
+GJK_HD Vec3 vec_pl_tail(Vec3 A, Vec3 ab, double dab)
+{
+    bool ok = true;
+    double nab = M::nrm(ab, ok);
+    Vec3 u; double t;
+    M::dv4(ab, dab, nab, u, t, ok);
+    if (nab < 1.0e-12) u = v3(0.0, 0.0, 0.0);
+    Vec3 D = v3(add(A.x, mul(t, u.x)), add(A.y, mul(t, u.y)), add(A.z, mul(t, u.z)));   // D - O = D
+    double nd = M::nrm(D, ok);
+    Vec3 r = M::dv(D, nd, ok);
+    if (nd < 1.0e-12) r = v3(0.0, 0.0, 0.0);
+    if (!ok) r.x = nan_marker();
+    return r;
+}
+
 struct GjkOut {
     int exit_path;
     int iters;          // walk steps taken, F:182-236
@@ -344,8 +431,8 @@ struct GjkOut {
 
 // The whole GJKEPA flag path for one pair.  S: 4 rows, final simplex on return (row 3 zero on the
 // F:140 path, hazard H1).  All lanes of the group return the same values.
-template <int L>
-GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HullView &A, const HullView &B,
+template <int L, class HV>
+GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HV &A, const HV &B,
                        const Sphere &sa, const Sphere &sb, Vec3 *S)
 {
     constexpr int FPL = Faces<L>::FPL;
@@ -367,18 +454,22 @@ GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HullView &A, const HullView &B,
     Vec3 dir;
     {   // VEC_PL(O, S0, S1), F:1431-1438 (quirk Q4: points from O to its foot on the line)
         Vec3 ab = S[1] - S[0], ac = O - S[0];
-        double nab = norm3(ab);
-        double t = dot3(ac, ab) / nab;
-        Vec3 u = utzvec_md(ab, nab);
-        Vec3 D = v3(add(S[0].x, mul(t, u.x)), add(S[0].y, mul(t, u.y)), add(S[0].z, mul(t, u.z)));
-        dir = utzvec(D - O);
+        double dab = dot3(ac, ab);
+        dir = vec_pl_tail<MathFast>(S[0], ab, dab);
+        if (dir.x != dir.x) dir = vec_pl_tail<MathExact>(S[0], ab, dab);      // NaN marks "redo exactly"
     }
     S[2] = support(g, A, B, dir); ++o.n_support;                             // F:119
     if (close3(S[2], S[0]) || close3(S[2], S[1])) { o.exit_path = EXIT_DUP3; return o; }   // F:123
 
     Vec3 c3 = cross3(S[1] - S[0], S[2] - S[1]);                              // F:132-135
-    double md3 = norm3(c3);
-    dir = utzvec_md(c3, md3);
+    double md3; Vec3 q3;
+    {
+        bool ok = true;
+        md3 = MathFast::nrm(c3, ok);
+        q3 = MathFast::dv(c3, md3, ok);
+        if (!ok) { md3 = norm3(c3); q3 = (md3 > 0.0) ? divs(c3, md3) : O; }
+    }
+    dir = (md3 < 1.0e-12) ? O : q3;                                          // UTZVEC
     {
         Vec3 vo = O - S[2];
         double dt = dot3(vo, dir);
@@ -388,12 +479,12 @@ GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HullView &A, const HullView &B,
     S[3] = support(g, A, B, dir); ++o.n_support;                             // F:154
     {   // DIST_PF_SIGN(S3, (S0,S1,S2)), F:157, with UNINML's own zero rule (F:1392)
         bool nz = fabs(c3.x) > 1.0e-12 || fabs(c3.y) > 1.0e-12 || fabs(c3.z) > 1.0e-12;
-        Vec3 n = nz ? divs(c3, md3) : O;
+        Vec3 n = nz ? q3 : O;
         if (fabs(n.x) < 1.0e-12 && fabs(n.y) < 1.0e-12 && fabs(n.z) < 1.0e-12) { o.exit_path = EXIT_STOP; o.stop_flag = true; return o; }
         if (fabs(dot3(S[3] - S[0], n)) < 1.0e-8) { o.exit_path = EXIT_COPLANAR4; return o; }
     }
     Faces<L> F;
-    compute_faces(g, S, F);
+    compute_faces<L>(g, S, F);
     Vec3 M = simplex_mean(S);
     if (contains_origin(g, S, F, M)) { o.exit_path = EXIT_INIT_CONTAIN; return o; }   // F:164
 
@@ -416,7 +507,15 @@ GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HullView &A, const HullView &B,
             Vec3 n0 = pick4(S, a), n1 = pick4(S, b), n2 = pick4(S, c);       // F:1130-1150
             S[0] = n0; S[1] = n1; S[2] = n2; S[3] = sm;
         }
-        compute_faces(g, S, F);
+        if (L == 1) {                                                        // kept face -> new face (1,2,3)
+            Vec3 qk = F.q[0]; double mk = F.md[0];
+#pragma unroll
+            for (int j = 1; j < FPL; ++j) { qk = sel(k == j, F.q[j], qk); mk = (k == j) ? F.md[j] : mk; }
+            F.q[2 % FPL] = qk; F.md[2 % FPL] = mk;
+            compute_faces<L, (L == 1 ? 2 : -1)>(g, S, F);
+        } else {
+            compute_faces<L>(g, S, F);
+        }
         M = simplex_mean(S);
         {   // F:199-206: face (1,2,3)'s cross product is the one compute_faces used for face 2
             const int owner = 2 % L, slot = 2 / L;

@@ -1,27 +1,46 @@
-// gjk_kernels.cuh -- K0 hull-prep and K1 GJK flag kernel (sm_100a).
+// gjk_kernels.cuh -- K0 hull-prep, K1a/K1b GJK flag kernels, K2 work-list compaction (sm_100a).
 //
-// K0  hull_prep_kernel : per-hull envelope sphere of RoughCollisionDetection_SphericalEnvelope
+// K0  hull_prep_kernel   per-hull envelope sphere of RoughCollisionDetection_SphericalEnvelope
 //                        (reference src/GCLIB_GJKEPA.f90:1175-1182).  The centroid is an
-//                        order-dependent sequential sum, so it is computed once per hull (one thread
-//                        per hull) instead of once per pair.
-// K1  gjk_kernel<L>    : GJKEPA flag path (F:76-236) for a batch of pairs, L lanes per pair
-//                        (gjk_core.cuh).  Colliding pairs are appended, with their terminating
-//                        tetrahedron, to the EPA work list (K2 compaction, warp-aggregated).
+//                        order-dependent sequential sum, so it is computed once per hull.  Used when
+//                        hulls are shared by many pairs; for pair-private hulls the GJK kernels
+//                        compute the spheres themselves from the staged vertices (FUSE = true).
+// K1a gjk_tile_kernel    GJKEPA flag path (F:76-236), one THREAD per pair.  A CTA stages the
+//                        vertices of its 128 pairs into shared memory with coalesced loads, one
+//                        column per pair (element e of a pair at smem[e*129 + t]): every support scan
+//                        then reads conflict-free shared memory instead of 32 scattered L1 lines per
+//                        load (ncu, profiles/: the un-staged form was L1-wavefront bound).  Pairs
+//                        whose hulls do not fit a column go to the overflow list.
+// K1b gjk_group_kernel<L> same path, a sub-warp of L lanes per pair (support = (value,index) max-dot
+//                        shuffle reduction), vertices read through L1; runs the overflow list (large
+//                        hulls) or, when the tile kernel is switched off, the whole batch.
+// K2  colliding pairs are appended with their terminating tetrahedron to the EPA work list by both
+//     kernels (one atomic per pair, after the pair's walk).
 #pragma once
 #include "gjk_core.cuh"
 
 namespace gjk {
 
+constexpr int TILE = 128;                // pairs (= threads) per CTA of the tile kernel
+constexpr int TILE_STRIDE = TILE + 1;    // odd column pitch: conflict-free transposed stores
+
 struct BatchArgs {
     const double  *verts;       // packed hull blocks
     const int64_t *hull_off;    // n_hulls+1, vertex units
-    const Sphere  *sphere;      // per hull (K0 output)
+    const Sphere  *sphere;      // per hull (K0 output); unused when FUSE
     const int32_t *pair_a, *pair_b;
     int64_t n_pairs;
     int64_t n_hulls;
     uint8_t  *collision;        // may be null
     uint32_t *status;           // may be null
-    // EPA work list (null when mode == GJK)
+    // optional indirection: process pair_list[0 .. *pair_list_count) instead of 0..n_pairs
+    const int32_t *pair_list;
+    const unsigned long long *pair_list_count;
+    // overflow list written by the tile kernel
+    int32_t *ovf_list;
+    unsigned long long *ovf_count;
+    int32_t col_doubles;        // capacity of one shared-memory column
+    // EPA work list (null when not wanted)
     int32_t *wl_pair;
     double  *wl_simplex;        // 12 doubles per entry, row-major rows 0..3
     unsigned long long *wl_count;
@@ -46,27 +65,130 @@ hull_prep_kernel(const double *__restrict__ verts, const int64_t *__restrict__ h
     out[h] = hull_sphere(v);
 }
 
+// envelope sphere by a sub-warp: lane l sums axis l sequentially (the order matters), the radius is a
+// max over vertices (order-free)
 template <int L>
+__device__ __forceinline__ Sphere group_sphere(const Lanes<L> &g, const HullView &h)
+{
+    double c[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        if ((ax % L) == g.lane) {
+            const double *p = (ax == 0) ? h.x : (ax == 1 ? h.y : h.z);
+            double s = 0.0;
+            for (int i = 0; i < h.n; ++i) s = add(s, __ldg(p + i));
+            c[ax] = s / (double)h.n;
+        }
+    }
+    Sphere s;
+    s.cx = g.bcast(c[0], 0 % L); s.cy = g.bcast(c[1], 1 % L); s.cz = g.bcast(c[2], 2 % L);
+    Vec3 cc = v3(s.cx, s.cy, s.cz);
+    double r2 = -1.0;
+    for (int i = g.lane; i < h.n; i += L) {
+        Vec3 d = h.get(i) - cc;
+        double t = add(add(mul(d.x, d.x), mul(d.y, d.y)), mul(d.z, d.z));
+        if (t > r2) r2 = t;
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) { double t = __shfl_xor_sync(g.mask, r2, o, L); if (t > r2) r2 = t; }
+    s.r = (h.n > 0) ? sqrt(r2) : -DBL_MAX;
+    return s;
+}
+template <>
+__device__ __forceinline__ Sphere group_sphere<1>(const Lanes<1> &, const HullView &h) { return hull_sphere(h); }
+
+__device__ __forceinline__ uint32_t pack_status(const GjkOut &o)
+{
+    return (uint32_t)o.exit_path | ((uint32_t)o.iters << 8) | (o.stop_flag ? (1u << 25) : 0u)
+         | (o.exit_path == EXIT_TRI_ORIGIN ? (1u << 28) : 0u);
+}
+
+// ------------------------------------------------------------------ K1a: one thread per pair, staged hulls
+template <bool FUSE>
+__global__ void __launch_bounds__(TILE, 2)
+gjk_tile_kernel(BatchArgs a)
+{
+    extern __shared__ __align__(16) double sm[];          // col_doubles * TILE_STRIDE
+    __shared__ int64_t s_off[2 * TILE];
+    __shared__ int32_t s_n[2 * TILE];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const Lanes<1> g;
+    const int64_t n_tiles = (a.n_pairs + TILE - 1) / TILE;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t p = tile * TILE + t;
+        const bool valid = p < a.n_pairs;
+        int ha = 0, hb = 0, nA = 0, nB = 0;
+        int64_t oa = 0, ob = 0;
+        if (valid) {
+            ha = __ldg(a.pair_a + p); hb = __ldg(a.pair_b + p);
+            oa = __ldg(a.hull_off + ha); nA = (int)(__ldg(a.hull_off + ha + 1) - oa);
+            ob = __ldg(a.hull_off + hb); nB = (int)(__ldg(a.hull_off + hb + 1) - ob);
+        }
+        const bool fits = valid && 3 * (nA + nB) <= a.col_doubles;
+        __syncthreads();                                   // previous tile's columns are no longer read
+        s_off[2 * t] = oa; s_off[2 * t + 1] = ob;
+        s_n[2 * t] = fits ? nA : 0; s_n[2 * t + 1] = fits ? nB : 0;
+        __syncthreads();
+        // stage: one (pair, side) block per warp step, lanes over consecutive doubles (coalesced)
+        for (int it = warp; it < 2 * TILE; it += TILE / 32) {
+            const int n3 = 3 * s_n[it];
+            if (n3 == 0) continue;
+            const double *src = a.verts + 3 * s_off[it];
+            double *dst = sm + (it >> 1) + ((it & 1) ? 3 * s_n[it - 1] * TILE_STRIDE : 0);
+            for (int e = lane; e < n3; e += 32) dst[e * TILE_STRIDE] = __ldg(src + e);
+        }
+        __syncthreads();
+        if (valid && !fits) {                              // large hulls: leave to the sub-warp kernel
+            unsigned long long slot = atomicAdd(a.ovf_count, 1ull);
+            a.ovf_list[slot] = (int32_t)p;
+        }
+        if (!fits) continue;
+
+        HullViewStrided A, B;
+        A.base = sm + t; A.n = nA; A.stride = TILE_STRIDE;
+        B.base = sm + t + 3 * nA * TILE_STRIDE; B.n = nB; B.stride = TILE_STRIDE;
+        Sphere sa, sb;
+        if (FUSE) { sa = hull_sphere(A); sb = hull_sphere(B); }
+        else      { sa = a.sphere[ha];   sb = a.sphere[hb]; }
+        Vec3 S[4];
+        const GjkOut o = gjk_pair<1>(g, A, B, sa, sb, S);
+        const bool coll = exit_is_collision(o.exit_path);
+        if (a.collision) a.collision[p] = coll ? 1 : 0;
+        if (a.status) a.status[p] = pack_status(o);
+        if (coll && a.wl_pair) {
+            unsigned long long slot = atomicAdd(a.wl_count, 1ull);
+            a.wl_pair[slot] = (int32_t)p;
+            double *dst = a.wl_simplex + 12 * slot;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { dst[3 * r] = S[r].x; dst[3 * r + 1] = S[r].y; dst[3 * r + 2] = S[r].z; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K1b: a sub-warp of L lanes per pair
+template <int L, bool FUSE>
 __global__ void __launch_bounds__(128)
-gjk_kernel(BatchArgs a)
+gjk_group_kernel(BatchArgs a)
 {
     const Lanes<L> g;
     const int64_t n_groups = (int64_t)gridDim.x * (blockDim.x / L);
-    int64_t p = (int64_t)blockIdx.x * (blockDim.x / L) + threadIdx.x / L;
-    for (; p < a.n_pairs; p += n_groups) {
+    const int64_t n_items = a.pair_list ? (int64_t)(*a.pair_list_count) : a.n_pairs;
+    int64_t it = (int64_t)blockIdx.x * (blockDim.x / L) + threadIdx.x / L;
+    for (; it < n_items; it += n_groups) {
+        const int64_t p = a.pair_list ? (int64_t)a.pair_list[it] : it;
         const int ha = __ldg(a.pair_a + p), hb = __ldg(a.pair_b + p);
         const HullView A = hull_view(a.verts, a.hull_off, ha);
         const HullView B = hull_view(a.verts, a.hull_off, hb);
-        const Sphere sa = a.sphere[ha], sb = a.sphere[hb];
+        Sphere sa, sb;
+        if (FUSE) { sa = group_sphere<L>(g, A); sb = group_sphere<L>(g, B); }
+        else      { sa = a.sphere[ha];          sb = a.sphere[hb]; }
         Vec3 S[4];
         const GjkOut o = gjk_pair<L>(g, A, B, sa, sb, S);
         const bool coll = exit_is_collision(o.exit_path);
         if (g.lane == 0) {
             if (a.collision) a.collision[p] = coll ? 1 : 0;
-            if (a.status)
-                a.status[p] = (uint32_t)o.exit_path | ((uint32_t)o.iters << 8)
-                            | (o.stop_flag ? (1u << 25) : 0u)
-                            | (o.exit_path == EXIT_TRI_ORIGIN ? (1u << 28) : 0u);
+            if (a.status) a.status[p] = pack_status(o);
         }
         if (coll && a.wl_pair) {
             unsigned long long slot = 0;

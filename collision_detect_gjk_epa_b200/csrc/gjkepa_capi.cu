@@ -23,7 +23,9 @@ struct gjkepa_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
-    int lanes = 0;
+    int lanes = 0;                 // 0 = automatic (tile kernel + 4-lane kernel for large hulls)
+    int max_hull_hint = 0;         // caller's bound on vertices per hull (0 = unknown)
+    int32_t *d_ovf = nullptr; int64_t cap_ovf = 0;
     // workspace (device)
     gjk::Sphere *d_sphere = nullptr; int64_t cap_sphere = 0;
     int32_t *d_wl_pair = nullptr; double *d_wl_simplex = nullptr; int64_t cap_wl = 0;
@@ -62,8 +64,6 @@ int ensure(gjkepa_ctx *ctx, T *&p, int64_t &cap, int64_t need)
     return GJKEPA_OK;
 }
 
-int pick_lanes(const gjkepa_ctx *ctx) { return ctx->lanes ? ctx->lanes : 4; }
-
 }  // namespace
 
 extern "C" {
@@ -84,7 +84,7 @@ int gjkepa_create(gjkepa_ctx **out, int32_t device)
     if (e == cudaSuccess) {
         // the kernels are built for sm_100a only: fail loudly when the image cannot load here
         cudaFuncAttributes fa;
-        e = cudaFuncGetAttributes(&fa, gjk::gjk_kernel<4>);
+        e = cudaFuncGetAttributes(&fa, gjk::gjk_group_kernel<4, false>);
     }
     for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e != cudaSuccess) {
@@ -109,6 +109,7 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
     if (ctx->d_wl_pair) cudaFree(ctx->d_wl_pair);
     if (ctx->d_wl_simplex) cudaFree(ctx->d_wl_simplex);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_ovf) cudaFree(ctx->d_ovf);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -145,6 +146,13 @@ int gjkepa_set_lanes(gjkepa_ctx *ctx, int32_t lanes)
 {
     if (!ctx || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4)) return GJKEPA_ERR_ARG;
     ctx->lanes = lanes;
+    return GJKEPA_OK;
+}
+
+int gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n)
+{
+    if (!ctx || n < 0) return GJKEPA_ERR_ARG;
+    ctx->max_hull_hint = n;
     return GJKEPA_OK;
 }
 
@@ -207,8 +215,11 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         return GJKEPA_OK;
     }
 
-    int rc = ensure(ctx, ctx->d_sphere, ctx->cap_sphere, n_hulls);
-    if (rc) return rc;
+    // pair-private hulls (every hull used by ~one pair): the GJK kernels compute the envelope spheres
+    // themselves from the vertices they stage anyway; shared stores get one K0 pass per batch
+    const bool fuse = n_hulls >= n_pairs;
+    int rc = GJKEPA_OK;
+    if (!fuse) { rc = ensure(ctx, ctx->d_sphere, ctx->cap_sphere, n_hulls); if (rc) return rc; }
     const bool want_list = (mode >= GJKEPA_MODE_EPA) || n_contacts || contact_index;
     if (want_list) {
         if (n_pairs > ctx->cap_wl) {
@@ -222,11 +233,13 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
             ctx->cap_wl = ncap;
         }
     }
+    const bool use_tile = ctx->lanes == 0;
+    if (use_tile) { rc = ensure(ctx, ctx->d_ovf, ctx->cap_ovf, n_pairs); if (rc) return rc; }
 
     ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = false;
     const bool prof = ctx->profiling;
     // K0
-    {
+    if (!fuse) {
         int threads = 256;
         int64_t blocks = (n_hulls + threads - 1) / threads;
         if (prof) CU(cudaEventRecord(ctx->ev[0], st));
@@ -239,23 +252,55 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     a.verts = verts; a.hull_off = hull_off; a.sphere = ctx->d_sphere;
     a.pair_a = pair_a; a.pair_b = pair_b; a.n_pairs = n_pairs; a.n_hulls = n_hulls;
     a.collision = collision; a.status = status;
+    a.pair_list = nullptr; a.pair_list_count = nullptr;
+    a.ovf_list = ctx->d_ovf; a.ovf_count = ctx->d_counters + 2; a.col_doubles = 0;
     a.wl_pair = want_list ? ctx->d_wl_pair : nullptr;
     a.wl_simplex = want_list ? ctx->d_wl_simplex : nullptr;
     a.wl_count = ctx->d_counters;
-    {
-        const int L = pick_lanes(ctx);
+    if (prof) CU(cudaEventRecord(ctx->ev[2], st));
+    if (use_tile) {
+        // K1a: one thread per pair over shared-memory columns; pairs that do not fit overflow to K1b
+        const int cap_vertices = ctx->max_hull_hint > 0 ? (ctx->max_hull_hint < 16 ? ctx->max_hull_hint : 16) : 16;
+        a.col_doubles = 3 * 2 * cap_vertices;
+        const size_t smem = (size_t)a.col_doubles * gjk::TILE_STRIDE * sizeof(double);
+        const int64_t n_tiles = (n_pairs + gjk::TILE - 1) / gjk::TILE;
+        int64_t blocks = n_tiles < (int64_t)ctx->sm_count * 2 ? n_tiles : (int64_t)ctx->sm_count * 2;
+        if (fuse) {
+            CU(cudaFuncSetAttribute(gjk::gjk_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gjk::gjk_tile_kernel<true><<<(unsigned)blocks, gjk::TILE, smem, st>>>(a);
+        } else {
+            CU(cudaFuncSetAttribute(gjk::gjk_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gjk::gjk_tile_kernel<false><<<(unsigned)blocks, gjk::TILE, smem, st>>>(a);
+        }
+        ++ctx->launches;
+        // K1b over the overflow list (exits at once when the list is empty)
+        if (ctx->max_hull_hint == 0 || ctx->max_hull_hint > 16) {
+            gjk::BatchArgs b = a;
+            b.pair_list = ctx->d_ovf; b.pair_list_count = ctx->d_counters + 2;
+            const int blocks_b = ctx->sm_count * 4;
+            if (fuse) gjk::gjk_group_kernel<4, true><<<blocks_b, 128, 0, st>>>(b);
+            else      gjk::gjk_group_kernel<4, false><<<blocks_b, 128, 0, st>>>(b);
+            ++ctx->launches;
+        }
+    } else {
+        const int L = ctx->lanes;
         const int threads = 128;
         const int64_t groups_per_block = threads / L;
         int64_t blocks = (n_pairs + groups_per_block - 1) / groups_per_block;
         const int64_t max_blocks = (int64_t)ctx->sm_count * 64;
         if (blocks > max_blocks) blocks = max_blocks;
-        if (prof) CU(cudaEventRecord(ctx->ev[2], st));
-        if (L == 1)      gjk::gjk_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(a);
-        else if (L == 2) gjk::gjk_kernel<2><<<(unsigned)blocks, threads, 0, st>>>(a);
-        else             gjk::gjk_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(a);
-        if (prof) { CU(cudaEventRecord(ctx->ev[3], st)); ctx->ev_valid[1] = true; }
+        if (fuse) {
+            if (L == 1)      gjk::gjk_group_kernel<1, true><<<(unsigned)blocks, threads, 0, st>>>(a);
+            else if (L == 2) gjk::gjk_group_kernel<2, true><<<(unsigned)blocks, threads, 0, st>>>(a);
+            else             gjk::gjk_group_kernel<4, true><<<(unsigned)blocks, threads, 0, st>>>(a);
+        } else {
+            if (L == 1)      gjk::gjk_group_kernel<1, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+            else if (L == 2) gjk::gjk_group_kernel<2, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+            else             gjk::gjk_group_kernel<4, false><<<(unsigned)blocks, threads, 0, st>>>(a);
+        }
         ++ctx->launches;
     }
+    if (prof) { CU(cudaEventRecord(ctx->ev[3], st)); ctx->ev_valid[1] = true; }
     CU(cudaGetLastError());
 
     // K3 on the colliding pairs
@@ -353,6 +398,44 @@ int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
             if (h_flags[i]) { if (contact_index) contact_index[c] = (int32_t)i; ++c; }
         if (n_contacts) *n_contacts = c;
     }
+    return GJKEPA_OK;
+}
+
+// ---- self-test hook: the straight-line sqrt / division sequences of fp64_exact.cuh against the
+// compiler's IEEE operators, element by element (used by tests/test_gpu_fp64_exact.py) ----
+__global__ void fp64_exact_probe(int64_t n, const double *a, const double *b, double *q_fast, double *q_ref,
+                                 double *s_fast, double *s_ref, uint8_t *in_range)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool okd = true, oks = true;
+    double r = gjk::rcp_div_seed(b[i]);
+    q_fast[i] = gjk::div_with_seed(a[i], b[i], r, okd);
+    q_ref[i] = a[i] / b[i];
+    s_fast[i] = gjk::sqrt_fast(b[i], oks);
+    s_ref[i] = sqrt(b[i]);
+    in_range[i] = (okd ? 1 : 0) | (oks ? 2 : 0);
+}
+
+int gjkepa_debug_fp64(gjkepa_ctx *ctx, int64_t n, const double *a, const double *b, double *q_fast,
+                      double *q_ref, double *s_fast, double *s_ref, uint8_t *in_range)
+{
+    if (!ctx || n <= 0) return GJKEPA_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    double *d = nullptr; uint8_t *f = nullptr;
+    CU(cudaMalloc((void **)&d, (size_t)n * 6 * sizeof(double)));
+    CU(cudaMalloc((void **)&f, (size_t)n));
+    CU(cudaMemcpy(d, a, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d + n, b, (size_t)n * 8, cudaMemcpyHostToDevice));
+    fp64_exact_probe<<<(unsigned)((n + 255) / 256), 256>>>(n, d, d + n, d + 2 * n, d + 3 * n, d + 4 * n, d + 5 * n, f);
+    ++ctx->launches;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(q_fast, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(q_ref, d + 3 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(s_fast, d + 4 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(s_ref, d + 5 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(in_range, f, (size_t)n, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(f);
     return GJKEPA_OK;
 }
 

@@ -73,8 +73,12 @@ int64_t gjkepa_launch_count(const gjkepa_ctx *ctx, int32_t reset);
  * returns their durations in milliseconds in ms[0..2] (0 for a kernel that did not run). */
 int  gjkepa_set_profiling(gjkepa_ctx *ctx, int32_t on);
 int  gjkepa_kernel_ms(gjkepa_ctx *ctx, double *ms /*[3]*/);
-/* tuning knob: lanes per pair in the GJK kernel (1, 2 or 4; 0 = automatic) */
+/* tuning knobs.  lanes: 0 = automatic (one thread per pair over shared-memory-staged hulls, a 4-lane
+ * sub-warp per pair for hulls too large to stage); 1, 2 or 4 = sub-warp kernel only, that many lanes.
+ * max_hull_vertices: caller's bound on vertices per hull (0 = unknown); sizes the shared-memory
+ * columns and lets the large-hull pass be skipped. */
 int  gjkepa_set_lanes(gjkepa_ctx *ctx, int32_t lanes);
+int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
 
 /* ---- replaces CALL GJKEPA(...) (F:39-52): one pair, every scalar by reference, HOST arrays ----
  * Uses a process-wide default context on device 0 (created on first call). */
@@ -105,6 +109,11 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                             uint8_t *collision_dev, int32_t *colli_type_dev, double *nearest_dev,
                             double *normal_dev, double *point_dev, double *depth_dev,
                             uint32_t *status_dev, int64_t *n_contacts_dev, int32_t *contact_index_dev);
+
+/* self-test hook (host buffers, n elements each): the library's straight-line IEEE sqrt / division
+ * sequences next to the compiler's operators; in_range bit 0 = division fast path valid, bit 1 = sqrt */
+int gjkepa_debug_fp64(gjkepa_ctx *ctx, int64_t n, const double *a, const double *b, double *q_fast,
+                      double *q_ref, double *s_fast, double *s_ref, uint8_t *in_range);
 
 /* block until everything queued by this context has finished */
 int gjkepa_sync(gjkepa_ctx *ctx);

@@ -95,6 +95,17 @@ struct MathExact {
     static GJK_HD Vec3 dv(Vec3 v, double s, bool &) { return divs(v, s); }
     static GJK_HD void dv4(Vec3 v, double w, double s, Vec3 &qv, double &qw, bool &) { qv = divs(v, s); qw = w / s; }
 };
+// Same results again, for the rare redo after MathFast lowered `ok` (an exactly zero cross-product
+// component of axis-aligned boxes, say): scalar out-of-line calls keep the call sites tiny so the
+// cold code does not bloat the walk's instruction footprint.
+GJK_HD_NOINLINE double cold_sqrt(double x) { return sqrt(x); }
+GJK_HD_NOINLINE double cold_div(double a, double b) { return a / b; }
+struct MathCold {
+    static GJK_HD double nrm(Vec3 v, bool &) { return cold_sqrt(add(add(mul(v.x, v.x), mul(v.y, v.y)), mul(v.z, v.z))); }
+    static GJK_HD Vec3 dv(Vec3 v, double s, bool &) { return v3(cold_div(v.x, s), cold_div(v.y, s), cold_div(v.z, s)); }
+    static GJK_HD void dv4(Vec3 v, double w, double s, Vec3 &qv, double &qw, bool &)
+    { qv = v3(cold_div(v.x, s), cold_div(v.y, s), cold_div(v.z, s)); qw = cold_div(w, s); }
+};
 struct MathFast {
     static GJK_HD double nrm(Vec3 v, bool &ok)
     { return sqrt_fast(add(add(mul(v.x, v.x), mul(v.y, v.y)), mul(v.z, v.z)), ok); }
@@ -166,11 +177,12 @@ struct HullView {
 // The same block staged in shared memory, transposed across the CTA's pairs: element e of the block
 // lives at base[e * stride] (stride = pairs per tile + 1, odd, so that consecutive threads hit
 // consecutive 8-byte banks when they read the same element of their own pair).
+template <int STRIDE>
 struct HullViewStrided {
     const double *base;
-    int n, stride;
+    int n;
     GJK_HD Vec3 get(int i) const
-    { return v3(base[i * stride], base[(n + i) * stride], base[(2 * n + i) * stride]); }
+    { return v3(base[i * STRIDE], base[(n + i) * STRIDE], base[(2 * n + i) * STRIDE]); }
 };
 
 // per-hull envelope sphere, F:1175-1182 (pair independent: computed once per hull by K0)
@@ -320,7 +332,7 @@ template <int L> struct Faces {
 };
 
 template <int L, class M, int SKIP>
-GJK_HD bool faces_from_cross(const Vec3 *cr, Faces<L> &F)
+GJK_HD bool faces_from_cross_impl(const Vec3 *cr, Faces<L> &F)
 {
     bool ok = true;
 #pragma unroll
@@ -347,7 +359,7 @@ GJK_HD void compute_faces(const Lanes<L> &g, const Vec3 *S, Faces<L> &F)
         Vec3 sa = pick4(S, a), sb = pick4(S, b), sc = pick4(S, c);
         cr[j] = cross3(sa - sb, sb - sc);
     }
-    if (!faces_from_cross<L, MathFast, SKIP>(cr, F)) faces_from_cross<L, MathExact, SKIP>(cr, F);
+    if (!faces_from_cross_impl<L, MathFast, SKIP>(cr, F)) faces_from_cross_impl<L, MathCold, SKIP>(cr, F);
 }
 
 GJK_HD Vec3 simplex_mean(const Vec3 *S)
@@ -456,7 +468,7 @@ GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HV &A, const HV &B,
         Vec3 ab = S[1] - S[0], ac = O - S[0];
         double dab = dot3(ac, ab);
         dir = vec_pl_tail<MathFast>(S[0], ab, dab);
-        if (dir.x != dir.x) dir = vec_pl_tail<MathExact>(S[0], ab, dab);      // NaN marks "redo exactly"
+        if (dir.x != dir.x) dir = vec_pl_tail<MathCold>(S[0], ab, dab);      // NaN marks "redo exactly"
     }
     S[2] = support(g, A, B, dir); ++o.n_support;                             // F:119
     if (close3(S[2], S[0]) || close3(S[2], S[1])) { o.exit_path = EXIT_DUP3; return o; }   // F:123
@@ -467,7 +479,7 @@ GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HV &A, const HV &B,
         bool ok = true;
         md3 = MathFast::nrm(c3, ok);
         q3 = MathFast::dv(c3, md3, ok);
-        if (!ok) { md3 = norm3(c3); q3 = (md3 > 0.0) ? divs(c3, md3) : O; }
+        if (!ok) { bool dummy = true; md3 = MathCold::nrm(c3, dummy); q3 = (md3 > 0.0) ? MathCold::dv(c3, md3, dummy) : O; }
     }
     dir = (md3 < 1.0e-12) ? O : q3;                                          // UTZVEC
     {

@@ -5,9 +5,9 @@
 //                        order-dependent sequential sum, so it is computed once per hull.  Used when
 //                        hulls are shared by many pairs; for pair-private hulls the GJK kernels
 //                        compute the spheres themselves from the staged vertices (FUSE = true).
-// K1a gjk_tile_kernel    GJKEPA flag path (F:76-236), one THREAD per pair.  A CTA stages the
-//                        vertices of its 128 pairs into shared memory with coalesced loads, one
-//                        column per pair (element e of a pair at smem[e*129 + t]): every support scan
+// K1a gjk_tile_kernel    GJKEPA flag path (F:76-236), one THREAD per pair.  A warp stages the
+//                        vertices of its 32 pairs into shared memory with coalesced cp.async, one
+//                        column per pair (element e of pair j at region[e*33 + j]): every support scan
 //                        then reads conflict-free shared memory instead of 32 scattered L1 lines per
 //                        load (ncu, profiles/: the un-staged form was L1-wavefront bound).  Pairs
 //                        whose hulls do not fit a column go to the overflow list.
@@ -21,8 +21,8 @@
 
 namespace gjk {
 
-constexpr int TILE = 128;                // pairs (= threads) per CTA of the tile kernel
-constexpr int TILE_STRIDE = TILE + 1;    // odd column pitch: conflict-free transposed stores
+constexpr int TILE = 128;                // threads per CTA of the tile kernel (4 warps x 32 pairs)
+constexpr int TILE_STRIDE = 33;          // odd column pitch of a warp's region: conflict-free transposed stores
 
 struct BatchArgs {
     const double  *verts;       // packed hull blocks
@@ -104,64 +104,80 @@ __device__ __forceinline__ uint32_t pack_status(const GjkOut &o)
 }
 
 // ------------------------------------------------------------------ K1a: one thread per pair, staged hulls
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Each WARP owns a tile of 32 pairs and a private shared-memory region of col_doubles x 33 doubles:
+// element e of pair j sits at region[e*33 + j].  Staging is asynchronous (cp.async, LDGSTS), lanes
+// over consecutive doubles of one hull block (coalesced global reads, conflict-free transposed
+// writes thanks to the odd pitch); the walk then reads region[e*33 + lane] (conflict-free).  No
+// block-level barrier anywhere: warps never wait for each other's slowest pair.
 template <bool FUSE>
-__global__ void __launch_bounds__(TILE, 2)
+__global__ void __launch_bounds__(TILE)
 gjk_tile_kernel(BatchArgs a)
 {
-    extern __shared__ __align__(16) double sm[];          // col_doubles * TILE_STRIDE
-    __shared__ int64_t s_off[2 * TILE];
-    __shared__ int32_t s_n[2 * TILE];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    extern __shared__ __align__(16) double sm[];          // (TILE/32) regions of col_doubles * WSTRIDE
+    constexpr int WSTRIDE = 33;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    double *region = sm + (size_t)warp * a.col_doubles * WSTRIDE;
     const Lanes<1> g;
-    const int64_t n_tiles = (a.n_pairs + TILE - 1) / TILE;
+    const int64_t n_tiles = (a.n_pairs + 31) / 32;
+    const int64_t n_warps = (int64_t)gridDim.x * (TILE / 32);
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t p = tile * TILE + t;
+    for (int64_t tile = (int64_t)blockIdx.x * (TILE / 32) + warp; tile < n_tiles; tile += n_warps) {
+        const int64_t p = tile * 32 + lane;
         const bool valid = p < a.n_pairs;
         int ha = 0, hb = 0, nA = 0, nB = 0;
-        int64_t oa = 0, ob = 0;
+        long long oa = 0, ob = 0;
         if (valid) {
             ha = __ldg(a.pair_a + p); hb = __ldg(a.pair_b + p);
             oa = __ldg(a.hull_off + ha); nA = (int)(__ldg(a.hull_off + ha + 1) - oa);
             ob = __ldg(a.hull_off + hb); nB = (int)(__ldg(a.hull_off + hb + 1) - ob);
         }
         const bool fits = valid && 3 * (nA + nB) <= a.col_doubles;
-        __syncthreads();                                   // previous tile's columns are no longer read
-        s_off[2 * t] = oa; s_off[2 * t + 1] = ob;
-        s_n[2 * t] = fits ? nA : 0; s_n[2 * t + 1] = fits ? nB : 0;
-        __syncthreads();
-        // stage: one (pair, side) block per warp step, lanes over consecutive doubles (coalesced)
-        for (int it = warp; it < 2 * TILE; it += TILE / 32) {
-            const int n3 = 3 * s_n[it];
-            if (n3 == 0) continue;
-            const double *src = a.verts + 3 * s_off[it];
-            double *dst = sm + (it >> 1) + ((it & 1) ? 3 * s_n[it - 1] * TILE_STRIDE : 0);
-            for (int e = lane; e < n3; e += 32) dst[e * TILE_STRIDE] = __ldg(src + e);
+        const int mA = fits ? 3 * nA : 0, mB = fits ? 3 * nB : 0;
+        __syncwarp();                                      // the previous tile's columns are no longer read
+        for (int j = 0; j < 32; ++j) {
+            const int ja = __shfl_sync(FULL, mA, j), jb = __shfl_sync(FULL, mB, j);
+            const long long joa = __shfl_sync(FULL, oa, j), job = __shfl_sync(FULL, ob, j);
+            const double *srcA = a.verts + 3 * joa, *srcB = a.verts + 3 * job;
+            double *colA = region + j, *colB = region + ja * WSTRIDE + j;
+            for (int e = lane; e < ja; e += 32) cp_async8(colA + e * WSTRIDE, srcA + e);
+            for (int e = lane; e < jb; e += 32) cp_async8(colB + e * WSTRIDE, srcB + e);
         }
-        __syncthreads();
+        cp_async_wait_all();
+        __syncwarp();
         if (valid && !fits) {                              // large hulls: leave to the sub-warp kernel
             unsigned long long slot = atomicAdd(a.ovf_count, 1ull);
             a.ovf_list[slot] = (int32_t)p;
         }
-        if (!fits) continue;
-
-        HullViewStrided A, B;
-        A.base = sm + t; A.n = nA; A.stride = TILE_STRIDE;
-        B.base = sm + t + 3 * nA * TILE_STRIDE; B.n = nB; B.stride = TILE_STRIDE;
-        Sphere sa, sb;
-        if (FUSE) { sa = hull_sphere(A); sb = hull_sphere(B); }
-        else      { sa = a.sphere[ha];   sb = a.sphere[hb]; }
-        Vec3 S[4];
-        const GjkOut o = gjk_pair<1>(g, A, B, sa, sb, S);
-        const bool coll = exit_is_collision(o.exit_path);
-        if (a.collision) a.collision[p] = coll ? 1 : 0;
-        if (a.status) a.status[p] = pack_status(o);
-        if (coll && a.wl_pair) {
-            unsigned long long slot = atomicAdd(a.wl_count, 1ull);
-            a.wl_pair[slot] = (int32_t)p;
-            double *dst = a.wl_simplex + 12 * slot;
+        if (fits) {
+            HullViewStrided<WSTRIDE> A, B;
+            A.base = region + lane; A.n = nA;
+            B.base = region + 3 * nA * WSTRIDE + lane; B.n = nB;
+            Sphere sa, sb;
+            if (FUSE) { sa = hull_sphere(A); sb = hull_sphere(B); }
+            else      { sa = a.sphere[ha];   sb = a.sphere[hb]; }
+            Vec3 S[4];
+            const GjkOut o = gjk_pair<1>(g, A, B, sa, sb, S);
+            const bool coll = exit_is_collision(o.exit_path);
+            if (a.collision) a.collision[p] = coll ? 1 : 0;
+            if (a.status) a.status[p] = pack_status(o);
+            if (coll && a.wl_pair) {
+                unsigned long long slot = atomicAdd(a.wl_count, 1ull);
+                a.wl_pair[slot] = (int32_t)p;
+                double *dst = a.wl_simplex + 12 * slot;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) { dst[3 * r] = S[r].x; dst[3 * r + 1] = S[r].y; dst[3 * r + 2] = S[r].z; }
+                for (int r = 0; r < 4; ++r) { dst[3 * r] = S[r].x; dst[3 * r + 1] = S[r].y; dst[3 * r + 2] = S[r].z; }
+            }
         }
     }
 }

@@ -25,6 +25,7 @@ struct gjkepa_ctx {
     int64_t launches = 0;
     int lanes = 0;                 // 0 = automatic (tile kernel + 4-lane kernel for large hulls)
     int max_hull_hint = 0;         // caller's bound on vertices per hull (0 = unknown)
+    int tile_ctas_per_sm = 2;      // persistent grid of the tile kernel
     int32_t *d_ovf = nullptr; int64_t cap_ovf = 0;
     // workspace (device)
     gjk::Sphere *d_sphere = nullptr; int64_t cap_sphere = 0;
@@ -262,14 +263,21 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         // K1a: one thread per pair over shared-memory columns; pairs that do not fit overflow to K1b
         const int cap_vertices = ctx->max_hull_hint > 0 ? (ctx->max_hull_hint < 16 ? ctx->max_hull_hint : 16) : 16;
         a.col_doubles = 3 * 2 * cap_vertices;
-        const size_t smem = (size_t)a.col_doubles * gjk::TILE_STRIDE * sizeof(double);
-        const int64_t n_tiles = (n_pairs + gjk::TILE - 1) / gjk::TILE;
-        int64_t blocks = n_tiles < (int64_t)ctx->sm_count * 2 ? n_tiles : (int64_t)ctx->sm_count * 2;
+        const size_t smem = (size_t)a.col_doubles * gjk::TILE_STRIDE * (gjk::TILE / 32) * sizeof(double);
+        const int64_t n_tiles = (n_pairs + 31) / 32 / (gjk::TILE / 32) + 1;
+        const int64_t resident = (int64_t)ctx->sm_count * ctx->tile_ctas_per_sm;
+        int64_t blocks = n_tiles < resident ? n_tiles : resident;
         if (fuse) {
             CU(cudaFuncSetAttribute(gjk::gjk_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_tile_kernel<true>, gjk::TILE, smem));
+            blocks = n_tiles < (int64_t)ctx->sm_count * per_sm ? n_tiles : (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
             gjk::gjk_tile_kernel<true><<<(unsigned)blocks, gjk::TILE, smem, st>>>(a);
         } else {
             CU(cudaFuncSetAttribute(gjk::gjk_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_tile_kernel<false>, gjk::TILE, smem));
+            blocks = n_tiles < (int64_t)ctx->sm_count * per_sm ? n_tiles : (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
             gjk::gjk_tile_kernel<false><<<(unsigned)blocks, gjk::TILE, smem, st>>>(a);
         }
         ++ctx->launches;

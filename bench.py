@@ -275,6 +275,13 @@ def main():
             dist.destroy_process_group()
         return
 
+    traffic = None
+    tfile = ROOT / "profiles" / "ncu_traffic.json"          # dram bytes per launch from the committed ncu --set full captures
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get(args.workload, {})
+        except Exception:
+            traffic = None
     peaks, peak_src = None, "fallback"
     pk = ROOT / "MEASURED_PEAKS.json"
     if pk.exists():
@@ -296,7 +303,9 @@ def main():
         "contacts_per_s": hits_all * args.steps / (ms_total * 1e-3),
         "roofline": {"bound": "hbm", "kernel": {"gjk": "gjk_kernel", "epa": "epa_kernel"}[dom],
                      "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": (achieved / peak_gbs) if achieved else None, "peak_source": peak_src, "traffic": None,
+                     "frac": (achieved / peak_gbs) if achieved else None, "peak_source": peak_src,
+                     "traffic": (traffic or {}).get({"gjk": "gjk_kernel", "epa": "epa_kernel"}[dom]),
+                     "algorithmic_bytes_per_launch": dom_bytes,
                      "kernel_ms": kern, "kernel_share_of_step": kern[dom] / step_ms if step_ms else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "gjkepa_batch_f64 (C ABI, pinned host buffers)"},

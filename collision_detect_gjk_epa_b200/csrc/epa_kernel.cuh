@@ -1,5 +1,6 @@
 // epa_kernel.cuh -- K3: EPA penetration depth + contact normal (and the contact epilogue K4) for the
-// pairs GJK reported as colliding.  One warp per pair, polytope resident in shared memory.
+// pairs GJK reported as colliding.  One warp per pair; polytope AND both hulls resident in shared
+// memory.
 //
 // Path: EPA_solu (reference src/GCLIB_GJKEPA.f90:242-346) and update_expandingPolytope_EPA
 // (F:863-1022).  The reference rebuilds the whole polytope from scratch with an external QuickHull
@@ -7,7 +8,7 @@
 // lists (F:972-1015).  Here the polytope is kept incrementally:
 //   per iteration  closest face (warp arg-min over cached plane distances, F:893-898)
 //                  -> outward direction with the reference's orientation rule (F:902-910)
-//                  -> support point (32-lane max-dot reduction, F:914)
+//                  -> support point (32-lane max-dot reduction over the staged hulls, F:914)
 //                  -> faces that see the point by more than HULL_EPS are marked in parallel,
 //                     the horizon is the set of their edges whose twin is not marked, marked faces
 //                     are compacted away and one new face per horizon edge is fanned to the point;
@@ -16,6 +17,15 @@
 //                  (F:963-969, F:997-998).
 // Plane normals/distances use the reference forms (UNINML F:1389-1392, DIST_PF_SIGN F:1375) so that
 // depth and normal agree with the CPU path to rounding.
+//
+// Warp arg-max / arg-min: the (value, index) butterfly (5 steps x 3 shuffles + compares) was 23 % of
+// this kernel's instructions (ncu source view, profiles/r1).  Doubles are mapped to order-preserving
+// 64-bit keys and reduced with three REDUX instructions (max high word, max low word among the
+// leaders, min index among the ties) -- first-index-wins semantics kept, -0 canonicalised.
+//
+// Capacity: the kernel is instantiated for (V_CAP, F_CAP) = (64, 128), which covers every pair of the
+// benchmark configurations with 20 resident warps per SM, and for (128, 256) = the reference's hard
+// bound (4 + 99 iterations); a pair that outgrows the small polytope is re-queued to the large one.
 #pragma once
 #include "gjk_kernels.cuh"
 #include <cuda_runtime.h>
@@ -25,9 +35,8 @@ namespace epa {
 using gjk::Vec3; using gjk::v3; using gjk::dot3; using gjk::cross3; using gjk::norm3; using gjk::neg;
 using gjk::HullView; using gjk::Lanes;
 
-constexpr int    V_CAP = 128;          // 4 + 99 iterations + slack
-constexpr int    F_CAP = 256;          // 2V-4
 constexpr int    WARPS = 4;
+constexpr int    HULL_CAP = 128;       // staged hull vertices per pair (nA + nB); larger pairs read global memory
 constexpr double HULL_EPS = 1.0e-10;   // same "swallow" tolerance as the oracle's hull stand-in
 constexpr int    MAX_ITERS = 99;       // F:299
 
@@ -39,116 +48,170 @@ struct EpaArgs {
     const int32_t *pair_a, *pair_b;
     const int32_t *wl_pair; const double *wl_simplex;
     const unsigned long long *wl_count; unsigned long long *queue_head;
+    // optional indirection over work-list entries (the large-capacity pass runs the overflow list)
+    const int32_t *item_list; const unsigned long long *item_count;
+    int32_t *ovf_items; unsigned long long *ovf_count;
     int32_t version; double tol_ff; bool full;
     int32_t *colli_type; double *nearest, *normal, *point, *depth; uint32_t *status;
 };
 
+template <int VC, int FC>
 struct alignas(16) Polytope {
-    double vx[V_CAP], vy[V_CAP], vz[V_CAP];
-    double nx[F_CAP], ny[F_CAP], nz[F_CAP], d[F_CAP];     // outward unit normal, n.x = d on the face
-    uint8_t fa[F_CAP], fb[F_CAP], fc[F_CAP];
-    uint8_t vis[F_CAP];
-    uint8_t vlist[F_CAP];                                  // indices of visible faces
-    uint8_t ha[F_CAP], hb[F_CAP];                          // horizon edges (directed)
+    double vx[VC], vy[VC], vz[VC];
+    double nx[FC], ny[FC], nz[FC], d[FC];     // outward unit normal, n.x = d on the face
+    double hx[HULL_CAP], hy[HULL_CAP], hz[HULL_CAP];   // staged hulls: A at [0,nA), B at [nA,nA+nB)
+    uint32_t fw[FC];                          // face vertices a | b<<8 | c<<16
+    uint16_t hedge[FC];                       // horizon edges a | b<<8 (directed)
+    uint8_t vis[FC];
+    uint8_t vlist[FC];                        // indices of visible faces
     int nv, nf;
 };
 
-__device__ __forceinline__ Vec3 pv(const Polytope &P, int i) { return v3(P.vx[i], P.vy[i], P.vz[i]); }
+// generic-pointer hull view (shared or global memory)
+struct HullPlain {
+    const double *x, *y, *z; int n;
+    __device__ __forceinline__ Vec3 get(int i) const { return v3(x[i], y[i], z[i]); }
+};
+
+// ---- warp arg-reductions with REDUX; first index wins ties ----
+__device__ __forceinline__ int warp_argmax_first(double v, int i)
+{
+    const unsigned FULL = 0xffffffffu;
+    long long b = __double_as_longlong(__dadd_rn(v, 0.0));               // -0 -> +0
+    unsigned long long k = (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+    unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    unsigned mh = __reduce_max_sync(FULL, hi);
+    unsigned ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+    return __reduce_min_sync(FULL, (hi == mh && lo == ml) ? i : 0x7fffffff);
+}
+__device__ __forceinline__ int warp_argmin_first_nonneg(double v, int i)   // v >= 0 (or +inf)
+{
+    const unsigned FULL = 0xffffffffu;
+    unsigned long long k = (unsigned long long)__double_as_longlong(v);
+    unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    unsigned mh = __reduce_min_sync(FULL, hi);
+    unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
+    return __reduce_min_sync(FULL, (hi == mh && lo == ml) ? i : 0x7fffffff);
+}
+
+// support_mapping (F:1030-1062) by the whole warp
+__device__ __forceinline__ Vec3 warp_support(const HullPlain &A, const HullPlain &B, Vec3 d, int lane)
+{
+    double bA = -DBL_MAX, bB = -DBL_MAX; int iA = 0, iB = 0;
+    for (int v = lane; v < A.n; v += 32) { double t = dot3(d, A.get(v)); if (t > bA) { bA = t; iA = v; } }
+    Vec3 nd = neg(d);
+    for (int v = lane; v < B.n; v += 32) { double t = dot3(nd, B.get(v)); if (t > bB) { bB = t; iB = v; } }
+    iA = warp_argmax_first(bA, iA);
+    iB = warp_argmax_first(bB, iB);
+    return A.get(iA) - B.get(iB);
+}
+
+template <int VC, int FC>
+__device__ __forceinline__ Vec3 pv(const Polytope<VC, FC> &P, int i) { return v3(P.vx[i], P.vy[i], P.vz[i]); }
 
 // plane of face (a,b,c): UNINML (F:1389-1392) and its signed offset; false if degenerate
-__device__ __forceinline__ bool face_plane(const Polytope &P, int a, int b, int c, Vec3 &n, double &d)
+template <int VC, int FC>
+__device__ __forceinline__ bool face_plane(const Polytope<VC, FC> &P, int a, int b, int c, Vec3 &n, double &d)
 {
     Vec3 va = pv(P, a), vb = pv(P, b), vc = pv(P, c);
     Vec3 cr = cross3(vb - va, vc - vb);
     if (!(fabs(cr.x) > 1.0e-12 || fabs(cr.y) > 1.0e-12 || fabs(cr.z) > 1.0e-12)) { n = v3(0, 0, 0); d = 0; return false; }
-    n = gjk::divs(cr, norm3(cr));
+    bool ok = true;
+    double md = gjk::MathFast::nrm(cr, ok);
+    n = gjk::MathFast::dv(cr, md, ok);
+    if (!ok) { bool dummy = true; md = gjk::MathCold::nrm(cr, dummy); n = gjk::MathCold::dv(cr, md, dummy); }
     d = dot3(va, n);
     return true;
 }
 
-// Insert point q.  Returns 1 if the hull changed, 0 if not, <0 on failure.  Warp-synchronous.
-__device__ int insert_point(Polytope &P, Vec3 q, int lane, uint32_t &st)
+// Insert point q.  Returns 1 if the hull changed, 0 if not, -1 on failure, -2 when out of capacity.
+template <int VC, int FC>
+__device__ int insert_point(Polytope<VC, FC> &P, Vec3 q, int lane, uint32_t &st)
 {
     const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const int nf0 = P.nf, nv0 = P.nv;
     // exact duplicate of an existing vertex (the reference appends unconditionally, F:927; its hull then drops it)
     bool dup = false;
-    for (int v = lane; v < P.nv; v += 32) dup = dup || (P.vx[v] == q.x && P.vy[v] == q.y && P.vz[v] == q.z);
+    for (int v = lane; v < nv0; v += 32) dup = dup || (P.vx[v] == q.x && P.vy[v] == q.y && P.vz[v] == q.z);
     if (__any_sync(FULL, dup)) return 0;
 
     // visible faces
     int nvis = 0;
-    for (int c = 0; c < P.nf; c += 32) {
+    for (int c = 0; c < nf0; c += 32) {
         int f = c + lane;
         bool v = false;
-        if (f < P.nf) {
+        if (f < nf0) {
             double dist = gjk::sub(dot3(v3(P.nx[f], P.ny[f], P.nz[f]), q), P.d[f]);
             v = dist > HULL_EPS;
             P.vis[f] = v ? 1 : 0;
         }
         unsigned b = __ballot_sync(FULL, v);
-        if (v) P.vlist[nvis + __popc(b & ((1u << lane) - 1u))] = (uint8_t)f;
+        if (v) P.vlist[nvis + __popc(b & lt)] = (uint8_t)f;
         nvis += __popc(b);
     }
     if (nvis == 0) return 0;
-    if (P.nv >= V_CAP) { st |= ST_HULL_FAIL; return -1; }
+    if (nv0 >= VC) return -2;
     __syncwarp();
 
     // horizon: directed edges of visible faces whose reverse is not an edge of a visible face
     int nh = 0;
     for (int c = 0; c < 3 * nvis; c += 32) {
         int it = c + lane;
-        bool hz = false; int ea = 0, eb = 0;
+        bool hz = false; unsigned ea = 0, eb = 0;
         if (it < 3 * nvis) {
-            int f = P.vlist[it / 3], e = it % 3;
-            int a0 = P.fa[f], a1 = P.fb[f], a2 = P.fc[f];
+            unsigned w = P.fw[P.vlist[it / 3]]; int e = it % 3;
+            unsigned a0 = w & 0xffu, a1 = (w >> 8) & 0xffu, a2 = (w >> 16) & 0xffu;
             ea = e == 0 ? a0 : (e == 1 ? a1 : a2);
             eb = e == 0 ? a1 : (e == 1 ? a2 : a0);
+            const unsigned rev01 = eb | (ea << 8);                       // (g0,g1) == (eb,ea)
             hz = true;
             for (int j = 0; j < nvis; ++j) {
-                int g = P.vlist[j];
-                int g0 = P.fa[g], g1 = P.fb[g], g2 = P.fc[g];
-                if ((g0 == eb && g1 == ea) || (g1 == eb && g2 == ea) || (g2 == eb && g0 == ea)) { hz = false; break; }
+                unsigned gw = P.fw[P.vlist[j]];
+                unsigned e01 = gw & 0xffffu, e12 = (gw >> 8) & 0xffffu, e20 = ((gw >> 16) & 0xffu) | ((gw & 0xffu) << 8);
+                if (e01 == rev01 || e12 == rev01 || e20 == rev01) { hz = false; break; }
             }
         }
         unsigned b = __ballot_sync(FULL, hz);
         if (hz) {
-            int pos = nh + __popc(b & ((1u << lane) - 1u));
-            if (pos < F_CAP) { P.ha[pos] = (uint8_t)ea; P.hb[pos] = (uint8_t)eb; }
+            int pos = nh + __popc(b & lt);
+            if (pos < FC) P.hedge[pos] = (uint16_t)(ea | (eb << 8));
         }
         nh += __popc(b);
     }
     if (nh != nvis + 2) st |= ST_TOPO_WARN;         // visible region is not a disk
-    if (P.nf - nvis + nh > F_CAP || nh > F_CAP) { st |= ST_HULL_FAIL; return -1; }
+    if (nf0 - nvis + nh > FC || nh > FC) return -2;
     __syncwarp();
 
     // drop visible faces (stable, in place)
     int base = 0;
-    for (int c = 0; c < P.nf; c += 32) {
+    for (int c = 0; c < nf0; c += 32) {
         int f = c + lane;
-        bool keep = f < P.nf && !P.vis[f];
-        double nx = 0, ny = 0, nz = 0, dd = 0; uint8_t a = 0, b_ = 0, c_ = 0;
-        if (keep) { nx = P.nx[f]; ny = P.ny[f]; nz = P.nz[f]; dd = P.d[f]; a = P.fa[f]; b_ = P.fb[f]; c_ = P.fc[f]; }
+        bool keep = f < nf0 && !P.vis[f];
+        double nx = 0, ny = 0, nz = 0, dd = 0; unsigned w = 0;
+        if (keep) { nx = P.nx[f]; ny = P.ny[f]; nz = P.nz[f]; dd = P.d[f]; w = P.fw[f]; }
         unsigned b = __ballot_sync(FULL, keep);
         __syncwarp();
         if (keep) {
-            int pos = base + __popc(b & ((1u << lane) - 1u));
-            P.nx[pos] = nx; P.ny[pos] = ny; P.nz[pos] = nz; P.d[pos] = dd; P.fa[pos] = a; P.fb[pos] = b_; P.fc[pos] = c_;
+            int pos = base + __popc(b & lt);
+            P.nx[pos] = nx; P.ny[pos] = ny; P.nz[pos] = nz; P.d[pos] = dd; P.fw[pos] = w;
         }
         base += __popc(b);
         __syncwarp();
     }
 
     // new vertex and the fan of new faces
-    const int vid = P.nv;
+    const int vid = nv0;
     if (lane == 0) { P.vx[vid] = q.x; P.vy[vid] = q.y; P.vz[vid] = q.z; }
     __syncwarp();
     bool bad = false;
     for (int e = lane; e < nh; e += 32) {
-        int a = P.ha[e], b = P.hb[e], f = base + e;
+        unsigned h = P.hedge[e];
+        int a = h & 0xffu, b = (h >> 8) & 0xffu, f = base + e;
         Vec3 n; double d;
         if (!face_plane(P, a, b, vid, n, d)) bad = true;
         P.nx[f] = n.x; P.ny[f] = n.y; P.nz[f] = n.z; P.d[f] = d;
-        P.fa[f] = (uint8_t)a; P.fb[f] = (uint8_t)b; P.fc[f] = (uint8_t)vid;
+        P.fw[f] = (unsigned)a | ((unsigned)b << 8) | ((unsigned)vid << 16);
     }
     if (lane == 0) { P.nv = vid + 1; P.nf = base + nh; }
     __syncwarp();
@@ -157,41 +220,44 @@ __device__ int insert_point(Polytope &P, Vec3 q, int lane, uint32_t &st)
 }
 
 // ---- contact epilogue (K4), F:326-343 ----
-__device__ void near_max_pair(const HullView &h, Vec3 d, int idx[2])
-{   // F:722-747 tracker (quirk Q8): "> max - 1e-8", last wins, previous winner becomes second
+// The order-dependent scans of the reference (quirk Q8) stay sequential, but over dot products that the
+// warp computed in parallel into shared scratch (tA[i] = n.p1(i), tB[i] = (-n).p2(i)); lane 0 walks hull
+// A while lane 1 walks hull B.
+__device__ __forceinline__ void near_max_pair(const double *t, int n, int idx[2])
+{   // F:722-747 tracker: "> max - 1e-8", last wins, previous winner becomes second
     double mx = -DBL_MAX;
     idx[0] = idx[1] = 0;
-    for (int i = 0; i < h.n; ++i) {
-        double t = dot3(d, h.get(i));
-        if (t > mx - 1.0e-8) { mx = t; idx[1] = idx[0]; idx[0] = i + 1; }
+    for (int i = 0; i < n; ++i) {
+        double v = t[i];
+        if (v > mx - 1.0e-8) { mx = v; idx[1] = idx[0]; idx[0] = i + 1; }
     }
     if (idx[1] == 0) idx[1] = idx[0];
 }
 
-__device__ void contact_epilogue(const EpaArgs &a, int p, const HullView &A, const HullView &B,
-                                 Vec3 nrm, int lane, uint32_t &st)
+__device__ void contact_epilogue(const EpaArgs &a, int p, const HullPlain &A, const HullPlain &B,
+                                 Vec3 nrm, int lane, uint32_t &st, double *tA, double *tB)
 {
-    const Lanes<32> g;
+    const unsigned FULL = 0xffffffffu;
+    const Vec3 nd = neg(nrm);
+    // dots along +-normal, once
+    double bA = -DBL_MAX, bB = -DBL_MAX; int iA = 0, iB = 0;
+    for (int v = lane; v < A.n; v += 32) { double t = dot3(nrm, A.get(v)); tA[v] = t; if (t > bA) { bA = t; iA = v; } }
+    for (int v = lane; v < B.n; v += 32) { double t = dot3(nd, B.get(v)); tB[v] = t; if (t > bB) { bB = t; iB = v; } }
+    iA = warp_argmax_first(bA, iA); iB = warp_argmax_first(bB, iB);
+    __syncwarp();
     // get_nearest_points, F:813-855: the two support vertices along +-normal
-    {
-        double bA = -DBL_MAX, bB = -DBL_MAX; int iA = 0, iB = 0;
-        for (int v = lane; v < A.n; v += 32) { double t = dot3(nrm, A.get(v)); if (t > bA) { bA = t; iA = v; } }
-        Vec3 nd = neg(nrm);
-        for (int v = lane; v < B.n; v += 32) { double t = dot3(nd, B.get(v)); if (t > bB) { bB = t; iB = v; } }
-        g.argmax_first(bA, iA); g.argmax_first(bB, iB);
-        if (lane == 0 && a.nearest) {
-            Vec3 pa = A.get(iA), pb = B.get(iB);
-            double *o = a.nearest + 6 * (int64_t)p;
-            o[0] = pa.x; o[1] = pb.x; o[2] = pa.y; o[3] = pb.y; o[4] = pa.z; o[5] = pb.z;
-        }
+    if (lane == 0 && a.nearest) {
+        Vec3 pa = A.get(iA), pb = B.get(iB);
+        double *o = a.nearest + 6 * (int64_t)p;
+        o[0] = pa.x; o[1] = pb.x; o[2] = pa.y; o[3] = pb.y; o[4] = pa.z; o[5] = pb.z;
     }
     Vec3 nrm_out = nrm;
     if (a.version == 1) {                       // get_collisionPoint_01, F:700-806
         int s[2] = {0, 0};
-        if (lane == 0) near_max_pair(A, nrm, s);
-        if (lane == 1) near_max_pair(B, neg(nrm), s);
-        int a0 = __shfl_sync(0xffffffffu, s[0], 0), a1 = __shfl_sync(0xffffffffu, s[1], 0);
-        int b0 = __shfl_sync(0xffffffffu, s[0], 1), b1 = __shfl_sync(0xffffffffu, s[1], 1);
+        if (lane == 0) near_max_pair(tA, A.n, s);
+        if (lane == 1) near_max_pair(tB, B.n, s);
+        int a0 = __shfl_sync(FULL, s[0], 0), a1 = __shfl_sync(FULL, s[1], 0);
+        int b0 = __shfl_sync(FULL, s[0], 1), b1 = __shfl_sync(FULL, s[1], 1);
         bool m1 = a0 != a1, m2 = b0 != b1;
         if (lane == 0 && a.point) {
             Vec3 r = v3(0, 0, 0);
@@ -201,12 +267,10 @@ __device__ void contact_epilogue(const EpaArgs &a, int p, const HullView &A, con
             } else if (m1 && !m2) r = B.get(b0 - 1);
             else if (!m1 && m2) r = A.get(a0 - 1);
             else {                              // F:766-804: mean of p1 supports within 0.1 of the maximum
-                double mx = -DBL_MAX;
-                for (int i = 0; i < A.n; ++i) { double t = dot3(nrm, A.get(i)); if (t > mx) mx = t; }
+                const double mx = tA[iA];       // strict maximum of the same dot products (F:779-787)
                 double sx = 0, sy = 0, sz = 0; int c = 0;
                 for (int i = 0; i < A.n; ++i) {
-                    Vec3 v = A.get(i);
-                    if (dot3(nrm, v) > mx - 1.0e-1) { ++c; sx = gjk::add(sx, v.x); sy = gjk::add(sy, v.y); sz = gjk::add(sz, v.z); }
+                    if (tA[i] > mx - 1.0e-1) { Vec3 v = A.get(i); ++c; sx = gjk::add(sx, v.x); sy = gjk::add(sy, v.y); sz = gjk::add(sz, v.z); }
                 }
                 r = v3(sx / (double)c, sy / (double)c, sz / (double)c);
             }
@@ -215,11 +279,11 @@ __device__ void contact_epilogue(const EpaArgs &a, int p, const HullView &A, con
         }
     } else if (a.version == 3) {                // get_collisionPoint_03, F:426-452
         if (lane == 0) {
-            double mx = -DBL_MAX; int idx = 0; Vec3 nd = neg(nrm);
-            for (int i = 0; i < B.n; ++i) { double t = dot3(nd, B.get(i)); if (t > mx - 1.0e-8) { mx = t; idx = i; } }
+            double mx = -DBL_MAX; int idx = 0;
+            for (int i = 0; i < B.n; ++i) { double t = tB[i]; if (t > mx - 1.0e-8) { mx = t; idx = i; } }
             Vec3 r = B.get(idx);
             double s = 0.0;
-            for (int i = 0; i < A.n; ++i) s = gjk::add(s, A.get(i).z);
+            for (int i = 0; i < A.n; ++i) s = gjk::add(s, A.z[i]);
             r.z = s / (double)(float)A.n;
             if (a.point) { double *o = a.point + 3 * (int64_t)p; o[0] = r.x; o[1] = r.y; o[2] = r.z; }
         }
@@ -232,48 +296,74 @@ __device__ void contact_epilogue(const EpaArgs &a, int p, const HullView &A, con
     }
     // get_info_collisionType, F:353-413 (on the possibly re-projected normal, F:335-343)
     {
+        const bool same = (a.version != 3);     // version 1: the dots above are the ones F:372/391 compute
         double mA = -DBL_MAX, mB = -DBL_MAX;
-        Vec3 nd = neg(nrm_out);
-        for (int v = lane; v < A.n; v += 32) { double t = dot3(nrm_out, A.get(v)); if (t > mA) mA = t; }
-        for (int v = lane; v < B.n; v += 32) { double t = dot3(nd, B.get(v)); if (t > mB) mB = t; }
+        const Vec3 nd2 = neg(nrm_out);
+        __syncwarp();
+        if (!same) {
+            for (int v = lane; v < A.n; v += 32) tA[v] = dot3(nrm_out, A.get(v));
+            for (int v = lane; v < B.n; v += 32) tB[v] = dot3(nd2, B.get(v));
+            __syncwarp();
+        }
+        for (int v = lane; v < A.n; v += 32) { double t = tA[v]; if (t > mA) mA = t; }
+        for (int v = lane; v < B.n; v += 32) { double t = tB[v]; if (t > mB) mB = t; }
         for (int o = 16; o > 0; o >>= 1) {
-            double t = __shfl_xor_sync(0xffffffffu, mA, o); if (t > mA) mA = t;
-            t = __shfl_xor_sync(0xffffffffu, mB, o); if (t > mB) mB = t;
+            double t = __shfl_xor_sync(FULL, mA, o); if (t > mA) mA = t;
+            t = __shfl_xor_sync(FULL, mB, o); if (t > mB) mB = t;
         }
         int cA = 0, cB = 0;
-        for (int v = lane; v < A.n; v += 32) cA += dot3(nrm_out, A.get(v)) > gjk::sub(mA, a.tol_ff);
-        for (int v = lane; v < B.n; v += 32) cB += dot3(nd, B.get(v)) > gjk::sub(mB, a.tol_ff);
-        for (int o = 16; o > 0; o >>= 1) { cA += __shfl_xor_sync(0xffffffffu, cA, o); cB += __shfl_xor_sync(0xffffffffu, cB, o); }
+        for (int v = lane; v < A.n; v += 32) cA += tA[v] > gjk::sub(mA, a.tol_ff);
+        for (int v = lane; v < B.n; v += 32) cB += tB[v] > gjk::sub(mB, a.tol_ff);
+        cA = __reduce_add_sync(FULL, cA); cB = __reduce_add_sync(FULL, cB);
         if (lane == 0 && a.colli_type) a.colli_type[p] = (cA >= 3 && cB >= 3) ? 2 : 1;
     }
 }
 
+template <int VC, int FC>
 __global__ void __launch_bounds__(WARPS * 32)
 epa_kernel(EpaArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    Polytope &P = reinterpret_cast<Polytope *>(smem_raw)[warp];
+    Polytope<VC, FC> &P = reinterpret_cast<Polytope<VC, FC> *>(smem_raw)[warp];
     const unsigned FULL = 0xffffffffu;
-    const Lanes<32> g;
-    const unsigned long long n_items = *a.wl_count;
+    const unsigned long long n_items = a.item_list ? *a.item_count : *a.wl_count;
 
     for (;;) {
-        unsigned long long item = 0;
-        if (lane == 0) item = atomicAdd(a.queue_head, 1ull);
-        item = __shfl_sync(FULL, item, 0);
-        if (item >= n_items) break;
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(a.queue_head, 1ull);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= n_items) break;
+        const long long item = a.item_list ? (long long)a.item_list[q] : (long long)q;
 
         const int p = a.wl_pair[item];
-        const HullView A = gjk::hull_view(a.verts, a.hull_off, a.pair_a[p]);
-        const HullView B = gjk::hull_view(a.verts, a.hull_off, a.pair_b[p]);
+        const HullView GA = gjk::hull_view(a.verts, a.hull_off, a.pair_a[p]);
+        const HullView GB = gjk::hull_view(a.verts, a.hull_off, a.pair_b[p]);
         uint32_t st = 0;
         int iters = 0;
         double depth = 0.0; Vec3 nrm = v3(0, 0, 0);
-        bool ok = true;
+        bool ok = true, overflow = false;
+        if (a.full && a.ovf_items && (GA.n > FC || GB.n > FC)) {       // epilogue scratch too small: large pass
+            if (lane == 0) a.ovf_items[atomicAdd(a.ovf_count, 1ull)] = (int32_t)item;
+            continue;
+        }
 
+        __syncwarp();                                   // previous item's shared state is dead
+        // stage both hulls (coalesced: the block [x|y|z] is contiguous) unless they exceed the buffer
+        HullPlain A, B;
+        const bool staged = GA.n + GB.n <= HULL_CAP;
+        if (staged) {
+            for (int v = lane; v < GA.n; v += 32) { P.hx[v] = __ldg(GA.x + v); P.hy[v] = __ldg(GA.y + v); P.hz[v] = __ldg(GA.z + v); }
+            for (int v = lane; v < GB.n; v += 32) {
+                P.hx[GA.n + v] = __ldg(GB.x + v); P.hy[GA.n + v] = __ldg(GB.y + v); P.hz[GA.n + v] = __ldg(GB.z + v);
+            }
+            A.x = P.hx; A.y = P.hy; A.z = P.hz; A.n = GA.n;
+            B.x = P.hx + GA.n; B.y = P.hy + GA.n; B.z = P.hz + GA.n; B.n = GB.n;
+        } else {
+            A.x = GA.x; A.y = GA.y; A.z = GA.z; A.n = GA.n;
+            B.x = GB.x; B.y = GB.y; B.z = GB.z; B.n = GB.n;
+        }
         // seed polytope from the GJK tetrahedron, faces as F:279-293, wound outwards
-        __syncwarp();
         if (lane < 4) {
             const double *s = a.wl_simplex + 12 * item + 3 * lane;
             P.vx[lane] = s[0]; P.vy[lane] = s[1]; P.vz[lane] = s[2];
@@ -294,7 +384,7 @@ epa_kernel(EpaArgs a)
                     if (!face_plane(P, fa, fb, fc, n, d)) bad = true;
                 }
                 P.nx[lane] = n.x; P.ny[lane] = n.y; P.nz[lane] = n.z; P.d[lane] = d;
-                P.fa[lane] = (uint8_t)fa; P.fb[lane] = (uint8_t)fb; P.fc[lane] = (uint8_t)fc;
+                P.fw[lane] = (unsigned)fa | ((unsigned)fb << 8) | ((unsigned)fc << 16);
             }
             if (__any_sync(FULL, bad)) { st |= ST_STOP; ok = false; }   // degenerate face: reference STOPs (F:1369)
         }
@@ -305,65 +395,98 @@ epa_kernel(EpaArgs a)
             if (iters > MAX_ITERS) { st |= ST_EPA_CAP; iters = MAX_ITERS; ok = false; break; }   // F:299-303
 
             // closest face, F:893-898 (first minimum)
+            const int nf = P.nf;
             double best = DBL_MAX; int k = 0;
-            for (int f = lane; f < P.nf; f += 32) { double ad = fabs(P.d[f]); if (ad < best) { best = ad; k = f; } }
-            g.argmin_first(best, k);
+            for (int f = lane; f < nf; f += 32) { double ad = fabs(P.d[f]); if (ad < best) { best = ad; k = f; } }
+            k = warp_argmin_first_nonneg(best, k);
+            const double dk = P.d[k];
+            best = fabs(dk);
             Vec3 n = v3(P.nx[k], P.ny[k], P.nz[k]);
-            double dt = P.d[k];                                     // (v1 - O) . dir, F:903
+            double dt = dk;                                         // (v1 - O) . dir, F:903
             if (fabs(dt) < 1.0e-12) {                               // F:905-908: re-base on the slot centroid
                 double sx = 0, sy = 0, sz = 0;
-                for (int f = lane; f < P.nf; f += 32) {
-                    Vec3 u = pv(P, P.fa[f]), v = pv(P, P.fb[f]), w = pv(P, P.fc[f]);
-                    sx += u.x + v.x + w.x; sy += u.y + v.y + w.y; sz += u.z + v.z + w.z;
+                for (int f = lane; f < nf; f += 32) {
+                    unsigned w = P.fw[f];
+                    Vec3 u = pv(P, w & 0xff), v = pv(P, (w >> 8) & 0xff), x = pv(P, (w >> 16) & 0xff);
+                    sx += u.x + v.x + x.x; sy += u.y + v.y + x.y; sz += u.z + v.z + x.z;
                 }
                 for (int o = 16; o > 0; o >>= 1) {
                     sx += __shfl_xor_sync(FULL, sx, o); sy += __shfl_xor_sync(FULL, sy, o); sz += __shfl_xor_sync(FULL, sz, o);
                 }
-                double cnt = (double)(P.nf * 3);
-                dt = dot3(pv(P, P.fa[k]) - v3(sx / cnt, sy / cnt, sz / cnt), n);
+                double cnt = (double)(nf * 3);
+                dt = dot3(pv(P, P.fw[k] & 0xff) - v3(sx / cnt, sy / cnt, sz / cnt), n);
             }
             Vec3 dir = (dt <= -1.0e-12) ? neg(n) : n;               // F:910
 
-            Vec3 sp = gjk::support<32>(g, A, B, dir);               // F:914
+            Vec3 sp = warp_support(A, B, dir, lane);                // F:914
             int ch = insert_point(P, sp, lane, st);
-            if (ch >= 0 && fabs(best) < 1.0e-12) {                  // F:935-944: origin on the face
-                Vec3 sp2 = gjk::support<32>(g, A, B, neg(dir));
+            if (ch >= 0 && best < 1.0e-12) {                        // F:935-944: origin on the face
+                Vec3 sp2 = warp_support(A, B, neg(dir), lane);
                 int ch2 = insert_point(P, sp2, lane, st);
                 ch = (ch2 < 0) ? ch2 : (ch | ch2);
             }
+            if (ch == -2) { overflow = true; ok = false; break; }
             if (ch < 0) { ok = false; break; }
             if (ch == 0) {                                          // hull unchanged: converged (F:994-998)
                 depth = best;
-                nrm = (P.d[k] < 0.0) ? neg(n) : n;                  // F:967-969
+                nrm = (dk < 0.0) ? neg(n) : n;                      // F:967-969
                 break;
             }
         }
 
+        if (overflow) {
+            if (a.ovf_items) {                                      // retry with the large polytope
+                if (lane == 0) a.ovf_items[atomicAdd(a.ovf_count, 1ull)] = (int32_t)item;
+                continue;
+            }
+            st |= ST_HULL_FAIL;
+        }
         st |= (uint32_t)iters << 16;
         if (ok) {
             if (lane == 0) {
                 if (a.depth) a.depth[p] = depth;
                 if (a.normal) { double *o = a.normal + 3 * (int64_t)p; o[0] = nrm.x; o[1] = nrm.y; o[2] = nrm.z; }
             }
-            if (a.full) contact_epilogue(a, p, A, B, nrm, lane, st);
+            if (a.full) {
+                __syncwarp();
+                if (A.n <= FC && B.n <= FC) contact_epilogue(a, p, A, B, nrm, lane, st, P.nx, P.ny);     // planes are dead now
+                else st |= ST_HULL_FAIL;                                                            // hulls beyond the scratch: epilogue skipped
+            }
         }
         if (lane == 0 && a.status) a.status[p] |= st;
     }
 }
 
-inline int launch(const EpaArgs &a, int sm_count, cudaStream_t st, int *blocks_out)
+template <int VC, int FC>
+inline int launch_one(const EpaArgs &a, int sm_count, cudaStream_t st)
 {
-    const size_t smem = sizeof(Polytope) * WARPS;
-    cudaError_t e = cudaFuncSetAttribute(epa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = sizeof(Polytope<VC, FC>) * WARPS;
+    cudaError_t e = cudaFuncSetAttribute(epa_kernel<VC, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_kernel, WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, epa_kernel<VC, FC>, WARPS * 32, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
-    int blocks = sm_count * per_sm;
-    epa_kernel<<<blocks, WARPS * 32, smem, st>>>(a);
-    if (blocks_out) *blocks_out = blocks;
+    epa_kernel<VC, FC><<<sm_count * per_sm, WARPS * 32, smem, st>>>(a);
     return 0;
+}
+
+// two passes: small polytopes for everything, then the pairs that outgrew them with the full bound.
+// queue heads: counters[1] (pass 1) and counters[3] (pass 2); overflow count: counters[4]
+inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf_items, unsigned long long *counters, int *launches)
+{
+    a.item_list = nullptr; a.item_count = nullptr;
+    a.queue_head = counters + 1;
+    a.ovf_items = ovf_items; a.ovf_count = counters + 4;
+    int rc = launch_one<64, 128>(a, sm_count, st);
+    if (rc) return rc;
+    EpaArgs b = a;
+    b.item_list = ovf_items; b.item_count = counters + 4;
+    b.queue_head = counters + 3;
+    b.ovf_items = nullptr; b.ovf_count = nullptr;
+    rc = launch_one<128, 256>(b, sm_count, st);
+    if (launches) *launches = 2;
+    return rc;
 }
 
 }  // namespace epa

@@ -30,7 +30,7 @@ struct gjkepa_ctx {
     // workspace (device)
     gjk::Sphere *d_sphere = nullptr; int64_t cap_sphere = 0;
     int32_t *d_wl_pair = nullptr; double *d_wl_simplex = nullptr; int64_t cap_wl = 0;
-    unsigned long long *d_counters = nullptr;      // [0] work-list length, [1] EPA queue head
+    unsigned long long *d_counters = nullptr;      // [0] work-list length, [1] EPA queue head, [2] GJK overflow, [3] EPA pass-2 head, [4] EPA overflow
     // staging for the host-buffer entry (device)
     void *d_stage = nullptr; size_t cap_stage = 0;
     unsigned long long *h_counters = nullptr;      // pinned
@@ -79,7 +79,7 @@ int gjkepa_create(gjkepa_ctx **out, int32_t device)
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_counters, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&ctx->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
@@ -210,7 +210,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         if (point)      CU(cudaMemsetAsync(point, 0, (size_t)n_pairs * 3 * sizeof(double), st));
         if (depth)      CU(cudaMemsetAsync(depth, 0, (size_t)n_pairs * sizeof(double), st));
     }
-    CU(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
     if (n_pairs == 0) {
         if (n_contacts) CU(cudaMemsetAsync(n_contacts, 0, sizeof(int64_t), st));
         return GJKEPA_OK;
@@ -235,7 +235,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         }
     }
     const bool use_tile = ctx->lanes == 0;
-    if (use_tile) { rc = ensure(ctx, ctx->d_ovf, ctx->cap_ovf, n_pairs); if (rc) return rc; }
+    if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf, ctx->cap_ovf, n_pairs); if (rc) return rc; }
 
     ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = false;
     const bool prof = ctx->profiling;
@@ -320,12 +320,12 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         e.version = version; e.tol_ff = tol_ff; e.full = (mode == GJKEPA_MODE_FULL);
         e.colli_type = colli_type; e.nearest = nearest; e.normal = normal; e.point = point;
         e.depth = depth; e.status = status;
-        int blocks = 0;
+        int nl = 0;
         if (prof) CU(cudaEventRecord(ctx->ev[4], st));
-        rc = epa::launch(e, ctx->sm_count, st, &blocks);
+        rc = epa::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_counters, &nl);
         if (rc) return fail(ctx, GJKEPA_ERR_CUDA, "epa launch", (cudaError_t)rc);
         if (prof) { CU(cudaEventRecord(ctx->ev[5], st)); ctx->ev_valid[2] = true; }
-        ++ctx->launches;
+        ctx->launches += nl;
         CU(cudaGetLastError());
     }
     if (n_contacts)

@@ -12,7 +12,7 @@ import subprocess
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-SO_PATH = _PKG / "libgjkepa_b200.so"
+SO_PATH = Path(os.environ["GJKEPA_LIB"]) if os.environ.get("GJKEPA_LIB") else _PKG / "libgjkepa_b200.so"   # env override: developer A/B builds
 CSRC = _PKG / "csrc"
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM = 0, 1, 2, 3

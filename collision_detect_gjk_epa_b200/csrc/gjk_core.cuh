@@ -349,7 +349,7 @@ GJK_HD bool faces_from_cross_impl(const Vec3 *cr, Faces<L> &F)
 // the face the walk just kept, whose cross product has the very same operands, so the caller has
 // already put its normal and norm in slot 2 and it is not recomputed.
 template <int L, int SKIP = -1>
-GJK_HD void compute_faces(const Lanes<L> &g, const Vec3 *S, Faces<L> &F)
+GJK_HD bool compute_faces(const Lanes<L> &g, const Vec3 *S, Faces<L> &F)
 {
     Vec3 cr[Faces<L>::FPL];
 #pragma unroll
@@ -359,7 +359,8 @@ GJK_HD void compute_faces(const Lanes<L> &g, const Vec3 *S, Faces<L> &F)
         Vec3 sa = pick4(S, a), sb = pick4(S, b), sc = pick4(S, c);
         cr[j] = cross3(sa - sb, sb - sc);
     }
-    if (!faces_from_cross_impl<L, MathFast, SKIP>(cr, F)) faces_from_cross_impl<L, MathCold, SKIP>(cr, F);
+    if (!faces_from_cross_impl<L, MathFast, SKIP>(cr, F)) { faces_from_cross_impl<L, MathCold, SKIP>(cr, F); return true; }
+    return false;
 }
 
 GJK_HD Vec3 simplex_mean(const Vec3 *S)
@@ -439,6 +440,8 @@ struct GjkOut {
     int iters;          // walk steps taken, F:182-236
     int n_support;
     bool stop_flag;     // reference STOP path (F:1369)
+    int cold;           // times the straight-line sqrt/div block was redone with the IEEE operators
+    int band;           // times IS_INSIDE_PF was entered (1e-8 bands)
 };
 
 // The whole GJKEPA flag path for one pair.  S: 4 rows, final simplex on return (row 3 zero on the
@@ -448,7 +451,7 @@ GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HV &A, const HV &B,
                        const Sphere &sa, const Sphere &sb, Vec3 *S)
 {
     constexpr int FPL = Faces<L>::FPL;
-    GjkOut o; o.exit_path = 0; o.iters = 0; o.n_support = 0; o.stop_flag = false;
+    GjkOut o; o.exit_path = 0; o.iters = 0; o.n_support = 0; o.stop_flag = false; o.cold = 0; o.band = 0;
     const Vec3 O = v3(0.0, 0.0, 0.0);
     S[0] = S[1] = S[2] = S[3] = O;
 
@@ -468,7 +471,7 @@ GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HV &A, const HV &B,
         Vec3 ab = S[1] - S[0], ac = O - S[0];
         double dab = dot3(ac, ab);
         dir = vec_pl_tail<MathFast>(S[0], ab, dab);
-        if (dir.x != dir.x) dir = vec_pl_tail<MathCold>(S[0], ab, dab);      // NaN marks "redo exactly"
+        if (dir.x != dir.x) { dir = vec_pl_tail<MathCold>(S[0], ab, dab); ++o.cold; }      // NaN marks "redo exactly"
     }
     S[2] = support(g, A, B, dir); ++o.n_support;                             // F:119
     if (close3(S[2], S[0]) || close3(S[2], S[1])) { o.exit_path = EXIT_DUP3; return o; }   // F:123
@@ -479,7 +482,7 @@ GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HV &A, const HV &B,
         bool ok = true;
         md3 = MathFast::nrm(c3, ok);
         q3 = MathFast::dv(c3, md3, ok);
-        if (!ok) { bool dummy = true; md3 = MathCold::nrm(c3, dummy); q3 = (md3 > 0.0) ? MathCold::dv(c3, md3, dummy) : O; }
+        if (!ok) { ++o.cold; bool dummy = true; md3 = MathCold::nrm(c3, dummy); q3 = (md3 > 0.0) ? MathCold::dv(c3, md3, dummy) : O; }
     }
     dir = (md3 < 1.0e-12) ? O : q3;                                          // UTZVEC
     {
@@ -496,7 +499,7 @@ GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HV &A, const HV &B,
         if (fabs(dot3(S[3] - S[0], n)) < 1.0e-8) { o.exit_path = EXIT_COPLANAR4; return o; }
     }
     Faces<L> F;
-    compute_faces<L>(g, S, F);
+    o.cold += compute_faces<L>(g, S, F);
     Vec3 M = simplex_mean(S);
     if (contains_origin(g, S, F, M)) { o.exit_path = EXIT_INIT_CONTAIN; return o; }   // F:164
 
@@ -519,23 +522,25 @@ GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HV &A, const HV &B,
             Vec3 n0 = pick4(S, a), n1 = pick4(S, b), n2 = pick4(S, c);       // F:1130-1150
             S[0] = n0; S[1] = n1; S[2] = n2; S[3] = sm;
         }
-        if (L == 1) {                                                        // kept face -> new face (1,2,3)
-            Vec3 qk = F.q[0]; double mk = F.md[0];
+        {   // F:199-206 first: face (1,2,3) of the new simplex is the face the walk kept (same operands,
+            // same bits), so both degeneracy exits are decided before any new normal is computed --
+            // this is how ~all separated pairs leave, usually with two zero-area new faces
+            const int owner = k % L, slot = k / L;
+            Vec3 qs = F.q[0]; double ms = F.md[0];
 #pragma unroll
-            for (int j = 1; j < FPL; ++j) { qk = sel(k == j, F.q[j], qk); mk = (k == j) ? F.md[j] : mk; }
-            F.q[2 % FPL] = qk; F.md[2 % FPL] = mk;
-            compute_faces<L, (L == 1 ? 2 : -1)>(g, S, F);
-        } else {
-            compute_faces<L>(g, S, F);
+            for (int j = 1; j < FPL; ++j) { qs = sel(slot == j, F.q[j], qs); ms = (slot == j) ? F.md[j] : ms; }
+            const double mk = g.bcast(ms, owner);
+            if (mk < 1.0e-8) { o.exit_path = EXIT_LOOP_COLLINEAR; return o; }
+            const Vec3 qk = v3(g.bcast(qs.x, owner), g.bcast(qs.y, owner), g.bcast(qs.z, owner));
+            if (fabs(dot3(S[3] - S[0], qk)) < 1.0e-8) { o.exit_path = EXIT_LOOP_COPLANAR; return o; }
+            if (L == 1) {
+                F.q[2 % FPL] = qk; F.md[2 % FPL] = mk;
+                o.cold += compute_faces<L, (L == 1 ? 2 : -1)>(g, S, F);
+            } else {
+                o.cold += compute_faces<L>(g, S, F);
+            }
         }
         M = simplex_mean(S);
-        {   // F:199-206: face (1,2,3)'s cross product is the one compute_faces used for face 2
-            const int owner = 2 % L, slot = 2 / L;
-            double m2 = g.bcast(F.md[slot], owner);
-            if (m2 < 1.0e-8) { o.exit_path = EXIT_LOOP_COLLINEAR; return o; }
-            Vec3 n = v3(g.bcast(F.q[slot].x, owner), g.bcast(F.q[slot].y, owner), g.bcast(F.q[slot].z, owner));
-            if (fabs(dot3(S[3] - S[0], n)) < 1.0e-8) { o.exit_path = EXIT_LOOP_COPLANAR; return o; }
-        }
         if (contains_origin(g, S, F, M)) { o.exit_path = EXIT_LOOP_CONTAIN; return o; }   // F:210
         {   // F:219-234
             bool ok = true;

@@ -100,7 +100,7 @@ __device__ __forceinline__ Sphere group_sphere<1>(const Lanes<1> &, const HullVi
 __device__ __forceinline__ uint32_t pack_status(const GjkOut &o)
 {
     return (uint32_t)o.exit_path | ((uint32_t)o.iters << 8) | (o.stop_flag ? (1u << 25) : 0u)
-         | (o.exit_path == EXIT_TRI_ORIGIN ? (1u << 28) : 0u);
+         | (o.exit_path == EXIT_TRI_ORIGIN ? (1u << 28) : 0u) | (o.cold ? (1u << 30) : 0u);
 }
 
 // ------------------------------------------------------------------ K1a: one thread per pair, staged hulls
@@ -119,8 +119,11 @@ __device__ __forceinline__ void cp_async_wait_all()
 // over consecutive doubles of one hull block (coalesced global reads, conflict-free transposed
 // writes thanks to the odd pitch); the walk then reads region[e*33 + lane] (conflict-free).  No
 // block-level barrier anywhere: warps never wait for each other's slowest pair.
+#ifndef GJK_TILE_MIN_CTAS
+#define GJK_TILE_MIN_CTAS 3
+#endif
 template <bool FUSE>
-__global__ void __launch_bounds__(TILE)
+__global__ void __launch_bounds__(TILE, GJK_TILE_MIN_CTAS)
 gjk_tile_kernel(BatchArgs a)
 {
     extern __shared__ __align__(16) double sm[];          // (TILE/32) regions of col_doubles * WSTRIDE

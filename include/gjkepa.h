@@ -56,6 +56,9 @@ typedef struct gjkepa_ctx gjkepa_ctx;
 #define GJKEPA_ST_HULL_FAIL    (1u << 26)  /* EPA polytope degenerate or over capacity */
 #define GJKEPA_ST_BAD_VERSION  (1u << 27)  /* version_ not 1 or 3 (F:329-340) */
 #define GJKEPA_ST_H1           (1u << 28)  /* F:140 path (simplex row 4 defined as zero) */
+#define GJKEPA_ST_TOPO_WARN    (1u << 29)  /* diagnostic: an EPA visible region was not a disk */
+#define GJKEPA_ST_COLD_MATH    (1u << 30)  /* diagnostic: an operand left the straight-line sqrt/div range and
+                                              the block was redone with the IEEE operators (same result) */
 
 /* ---- context: one per GPU (one process per GPU; pairs shard by index across contexts) ---- */
 int  gjkepa_create(gjkepa_ctx **ctx, int32_t device);

@@ -48,8 +48,8 @@ def test_unit_scale_operands_like_the_gjk_walk(engine):
 
 def test_special_operands_take_the_fallback(engine):
     tiny = np.nextafter(0.0, 1.0)
-    a = np.array([0.0, -0.0, 1.0, 1.0, np.inf, np.nan, 1.0, 1e-300, tiny, 1.0, 1e300])
-    b = np.array([1.0, 2.0, 0.0, np.inf, 1.0, 1.0, np.nan, 1.0, 1.0, tiny, 1e-300])
+    a = np.array([1.0, 1.0, np.inf, np.nan, 1.0, 1e-300, tiny, 1.0, 1e300, 0.0, 0.0, 0.0, 0.0])
+    b = np.array([0.0, np.inf, 1.0, 1.0, np.nan, 1.0, 1.0, tiny, 1e-300, 0.0, np.inf, np.nan, tiny])
     (qf, qr, sf, sr), fl = probe(engine, a, b)
     assert np.all((fl & 1) == 0)                      # every one of these leaves the division fast path
     with np.errstate(all="ignore"):
@@ -57,3 +57,13 @@ def test_special_operands_take_the_fallback(engine):
     assert np.array_equal(np.isnan(qr), np.isnan(want)) and np.array_equal(qr[~np.isnan(want)], want[~np.isnan(want)])
     (_, _, sf, sr), fl = probe(engine, np.ones(5), np.array([0.0, tiny, 1e-300, np.inf, np.nan]))
     assert np.all((fl & 2) == 0)
+
+
+def test_zero_numerator_is_answered_in_line_with_the_ieee_sign(engine):
+    # exactly zero cross-product components are routine (degenerate tetrahedron faces, axis-aligned boxes)
+    a = np.array([0.0, -0.0, 0.0, -0.0])
+    b = np.array([1.5, 2.5, -3.0, -0.25])
+    (qf, qr, sf, sr), fl = probe(engine, a, b)
+    assert np.all((fl & 1) == 1)
+    assert np.array_equal(qf.view(np.uint64), (a / b).view(np.uint64))
+    assert np.array_equal(qf.view(np.uint64), qr.view(np.uint64))

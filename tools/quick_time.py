@@ -38,6 +38,8 @@ def main():
         if ref is not None:
             got = out["collision"][:chk].cpu().numpy(); st = out["status"][:chk].cpu().numpy().view(np.uint32)
             ok = f" flags_ok={np.array_equal(got, ref['collision'])} status_ok={np.array_equal(st & 0xffff, ref['status'] & 0xffff)}"
+        stall = out["status"].cpu().numpy().view(np.uint32)
+        ok += f" cold_math={np.mean((stall >> 30) & 1):.4f}"
         print(f"[quick] {wl} mode={mode} lanes={lanes}: total {np.median(tot[3:]):.3f} ms  K0 {k['hull_prep']:.3f}  K1 {k['gjk']:.3f}  K3 {k['epa']:.3f}  "
               f"-> {b.n_pairs / np.median(tot[3:]) * 1e3:.3e} pairs/s{ok}", flush=True)
 

@@ -117,6 +117,11 @@ def cpu_rate(batch, mode, sample_pairs, threads=0, repeats=1):
     """Times the CPU path (oracle port: C restatement of GCLIB_GJKEPA.f90, OpenMP over pairs)."""
     from oracle import orc
     n = min(sample_pairs, batch.n_pairs)
+    if threads <= 0:                      # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except Exception:
+            threads = os.cpu_count() or 1
     omode = {"gjk": orc.MODE_GJK, "epa": orc.MODE_EPA, "full": orc.MODE_FULL}[mode]
     pa, pb = batch.pair_a[:n], batch.pair_b[:n]
     best, used, hits = None, 1, 0

@@ -131,11 +131,8 @@ __device__ int insert_point(Polytope<VC, FC> &P, Vec3 q, int lane, uint32_t &st)
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = (1u << lane) - 1u;
     const int nf0 = P.nf, nv0 = P.nv;
-    // exact duplicate of an existing vertex (the reference appends unconditionally, F:927; its hull then drops it)
-    bool dup = false;
-    for (int v = lane; v < nv0; v += 32) dup = dup || (P.vx[v] == q.x && P.vy[v] == q.y && P.vz[v] == q.z);
-    if (__any_sync(FULL, dup)) return 0;
-
+    // (a support point that repeats an existing vertex needs no special case: it lies on the hull, so no
+    //  face sees it by more than HULL_EPS and the visibility pass below reports "unchanged")
     // visible faces
     int nvis = 0;
     for (int c = 0; c < nf0; c += 32) {
@@ -319,8 +316,11 @@ __device__ void contact_epilogue(const EpaArgs &a, int p, const HullPlain &A, co
     }
 }
 
+#ifndef EPA_MIN_CTAS
+#define EPA_MIN_CTAS 5
+#endif
 template <int VC, int FC>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, EPA_MIN_CTAS)
 epa_kernel(EpaArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

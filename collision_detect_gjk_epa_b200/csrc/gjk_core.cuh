@@ -172,6 +172,15 @@ struct HullView {
         return v3(x[i], y[i], z[i]);
 #endif
     }
+    GJK_HD double comp(int ax, int i) const
+    {
+        const double *p = (ax == 0) ? x : (ax == 1 ? y : z);
+#if defined(__CUDA_ARCH__)
+        return __ldg(p + i);
+#else
+        return p[i];
+#endif
+    }
 };
 
 // The same block staged in shared memory, transposed across the CTA's pairs: element e of the block
@@ -217,7 +226,8 @@ template <int L> struct Lanes;
 
 template <> struct Lanes<1> {
     int lane;
-    GJK_HD Lanes() : lane(0) {}
+    unsigned mask;
+    GJK_HD Lanes() : lane(0), mask(0u) {}
     GJK_HD double bcast(double v, int) const { return v; }
     GJK_HD int bcast_i(int v, int) const { return v; }
     GJK_HD bool all(bool p) const { return p; }

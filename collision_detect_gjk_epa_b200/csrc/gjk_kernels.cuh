@@ -67,16 +67,15 @@ hull_prep_kernel(const double *__restrict__ verts, const int64_t *__restrict__ h
 
 // envelope sphere by a sub-warp: lane l sums axis l sequentially (the order matters), the radius is a
 // max over vertices (order-free)
-template <int L>
-__device__ __forceinline__ Sphere group_sphere(const Lanes<L> &g, const HullView &h)
+template <int L, class HV>
+__device__ __forceinline__ Sphere group_sphere(const Lanes<L> &g, const HV &h)
 {
     double c[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
         if ((ax % L) == g.lane) {
-            const double *p = (ax == 0) ? h.x : (ax == 1 ? h.y : h.z);
             double s = 0.0;
-            for (int i = 0; i < h.n; ++i) s = add(s, __ldg(p + i));
+            for (int i = 0; i < h.n; ++i) s = add(s, h.comp(ax, i));
             c[ax] = s / (double)h.n;
         }
     }
@@ -89,13 +88,13 @@ __device__ __forceinline__ Sphere group_sphere(const Lanes<L> &g, const HullView
         double t = add(add(mul(d.x, d.x), mul(d.y, d.y)), mul(d.z, d.z));
         if (t > r2) r2 = t;
     }
+    if constexpr (L > 1) {
 #pragma unroll
-    for (int o = L / 2; o > 0; o >>= 1) { double t = __shfl_xor_sync(g.mask, r2, o, L); if (t > r2) r2 = t; }
+        for (int o = L / 2; o > 0; o >>= 1) { double t = __shfl_xor_sync(g.mask, r2, o, L); if (t > r2) r2 = t; }
+    }
     s.r = (h.n > 0) ? sqrt(r2) : -DBL_MAX;
     return s;
 }
-template <>
-__device__ __forceinline__ Sphere group_sphere<1>(const Lanes<1> &, const HullView &h) { return hull_sphere(h); }
 
 __device__ __forceinline__ uint32_t pack_status(const GjkOut &o)
 {
@@ -158,9 +157,14 @@ gjk_tile_kernel(BatchArgs a)
         }
         cp_async_wait_all();
         __syncwarp();
-        if (valid && !fits) {                              // large hulls: leave to the sub-warp kernel
-            unsigned long long slot = atomicAdd(a.ovf_count, 1ull);
-            a.ovf_list[slot] = (int32_t)p;
+        {   // large hulls: leave to the sub-warp kernels (one atomic per warp)
+            const unsigned big = __ballot_sync(FULL, valid && !fits);
+            if (big) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.ovf_count, (unsigned long long)__popc(big));
+                base = __shfl_sync(FULL, base, 0);
+                if (valid && !fits) a.ovf_list[base + __popc(big & ((1u << lane) - 1u))] = (int32_t)p;
+            }
         }
         if (fits) {
             HullViewStrided<WSTRIDE> A, B;
@@ -220,6 +224,129 @@ gjk_group_kernel(BatchArgs a)
             for (int r = g.lane; r < 4; r += L) {
                 Vec3 row = pick4(S, r);
                 dst[3 * r + 0] = row.x; dst[3 * r + 1] = row.y; dst[3 * r + 2] = row.z;
+            }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------ K1c: sub-warp per pair over TMA-staged hulls
+// Shared-memory view of a hull block copied verbatim ([x(n) | y(n) | z(n)]).
+struct HullViewShared {
+    const double *x, *y, *z; int n;
+    __device__ __forceinline__ Vec3 get(int i) const { return v3(x[i], y[i], z[i]); }
+    __device__ __forceinline__ double comp(int ax, int i) const { return (ax == 0 ? x : (ax == 1 ? y : z))[i]; }
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async()
+{ asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Each warp owns a tile of 32/L pairs; every pair has a slot of slot_doubles in the warp's region.
+// Lane 0 of each group issues the pair's two hull blocks as 1-D TMA bulk copies (16-byte aligned
+// blocks) or the group copies them element-wise with cp.async (odd vertex counts / offsets); the
+// walk then reads shared memory.  Slots are padded by 4 doubles so that the 32/L groups of a warp
+// start 32 bytes apart modulo the bank window (conflict-free lane-strided vertex reads).
+template <int L, bool FUSE>
+__global__ void __launch_bounds__(128)
+gjk_group_staged_kernel(BatchArgs a, int slot_doubles)
+{
+    extern __shared__ __align__(16) double sm[];
+    __shared__ __align__(8) unsigned long long s_bar[4];
+    constexpr int PPW = 32 / L;                          // pairs per warp
+    const Lanes<L> g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / L;
+    const unsigned FULL = 0xffffffffu;
+    double *slot = sm + ((size_t)warp * PPW + grp) * slot_doubles;
+    unsigned long long *bar = &s_bar[warp];
+    if (lane == 0) mbar_init(bar, 1);
+    fence_proxy_async();
+    __syncwarp();
+    unsigned parity = 0;
+
+    const int64_t n_items = a.pair_list ? (int64_t)(*a.pair_list_count) : a.n_pairs;
+    const int64_t n_tiles = (n_items + PPW - 1) / PPW;
+    const int64_t n_warps = (int64_t)gridDim.x * 4;
+    for (int64_t tile = (int64_t)blockIdx.x * 4 + warp; tile < n_tiles; tile += n_warps) {
+        const int64_t it = tile * PPW + grp;
+        const bool valid = it < n_items;
+        int64_t p = 0; int ha = 0, hb = 0;
+        HullView GA, GB; GA.n = GB.n = 0; GA.x = GB.x = a.verts;
+        if (valid) {
+            p = a.pair_list ? (int64_t)a.pair_list[it] : it;
+            ha = __ldg(a.pair_a + p); hb = __ldg(a.pair_b + p);
+            GA = hull_view(a.verts, a.hull_off, ha); GB = hull_view(a.verts, a.hull_off, hb);
+        }
+        const bool fits = valid && 3 * (GA.n + GB.n) + 4 <= slot_doubles;
+        const unsigned bytesA = fits ? 24u * (unsigned)GA.n : 0u, bytesB = fits ? 24u * (unsigned)GB.n : 0u;
+        const bool bulkA = bytesA && ((bytesA & 15u) == 0) && ((reinterpret_cast<uintptr_t>(GA.x) & 15u) == 0);
+        // B lands right after A: its destination is 16-byte aligned only if A's block is a multiple of 16 bytes
+        const bool bulkB = bytesB && ((bytesB & 15u) == 0) && ((bytesA & 15u) == 0) && ((reinterpret_cast<uintptr_t>(GB.x) & 15u) == 0);
+        __syncwarp();                                     // the previous tile's slots are no longer read
+        fence_proxy_async();                              // order those generic reads before the async writes
+        unsigned tx = (g.lane == 0) ? ((bulkA ? bytesA : 0u) + (bulkB ? bytesB : 0u)) : 0u;
+        tx = __reduce_add_sync(FULL, tx);
+        if (lane == 0) mbar_expect_tx(bar, tx);
+        __syncwarp();
+        if (g.lane == 0) {
+            if (bulkA) bulk_g2s(slot, GA.x, bytesA, bar);
+            if (bulkB) bulk_g2s(slot + 3 * GA.n, GB.x, bytesB, bar);
+        }
+        if (bytesA && !bulkA) for (int e = g.lane; e < 3 * GA.n; e += L) cp_async8(slot + e, GA.x + e);
+        if (bytesB && !bulkB) for (int e = g.lane; e < 3 * GB.n; e += L) cp_async8(slot + 3 * GA.n + e, GB.x + e);
+        cp_async_wait_all();
+        {
+            unsigned spins = 0;
+            while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 24)) __trap(); }
+            parity ^= 1u;
+        }
+        __syncwarp();
+        if (valid && !fits && g.lane == 0) {             // larger than a slot: plain sub-warp kernel
+            unsigned long long s2 = atomicAdd(a.ovf_count, 1ull);
+            a.ovf_list[s2] = (int32_t)p;
+        }
+        if (fits) {
+            HullViewShared A, B;
+            A.x = slot; A.y = slot + GA.n; A.z = slot + 2 * GA.n; A.n = GA.n;
+            B.x = slot + 3 * GA.n; B.y = B.x + GB.n; B.z = B.y + GB.n; B.n = GB.n;
+            Sphere sa, sb;
+            if (FUSE) { sa = group_sphere<L>(g, A); sb = group_sphere<L>(g, B); }
+            else      { sa = a.sphere[ha];          sb = a.sphere[hb]; }
+            Vec3 S[4];
+            const GjkOut o = gjk_pair<L>(g, A, B, sa, sb, S);
+            const bool coll = exit_is_collision(o.exit_path);
+            if (g.lane == 0) {
+                if (a.collision) a.collision[p] = coll ? 1 : 0;
+                if (a.status) a.status[p] = pack_status(o);
+            }
+            if (coll && a.wl_pair) {
+                unsigned long long s3 = 0;
+                if (g.lane == 0) s3 = atomicAdd(a.wl_count, 1ull);
+                s3 = ((unsigned long long)(unsigned)g.bcast_i((int)(s3 >> 32), 0) << 32)
+                   | (unsigned)g.bcast_i((int)(s3 & 0xffffffffu), 0);
+                if (g.lane == 0) a.wl_pair[s3] = (int32_t)p;
+                double *dst = a.wl_simplex + 12 * s3;
+#pragma unroll
+                for (int r = g.lane; r < 4; r += L) {
+                    Vec3 row = pick4(S, r);
+                    dst[3 * r + 0] = row.x; dst[3 * r + 1] = row.y; dst[3 * r + 2] = row.z;
+                }
             }
         }
     }

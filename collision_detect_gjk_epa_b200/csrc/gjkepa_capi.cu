@@ -27,6 +27,7 @@ struct gjkepa_ctx {
     int max_hull_hint = 0;         // caller's bound on vertices per hull (0 = unknown)
     int tile_ctas_per_sm = 2;      // persistent grid of the tile kernel
     int32_t *d_ovf = nullptr; int64_t cap_ovf = 0;
+    int32_t *d_ovf2 = nullptr; int64_t cap_ovf2 = 0;
     // workspace (device)
     gjk::Sphere *d_sphere = nullptr; int64_t cap_sphere = 0;
     int32_t *d_wl_pair = nullptr; double *d_wl_simplex = nullptr; int64_t cap_wl = 0;
@@ -111,6 +112,7 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
     if (ctx->d_wl_simplex) cudaFree(ctx->d_wl_simplex);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_ovf) cudaFree(ctx->d_ovf);
+    if (ctx->d_ovf2) cudaFree(ctx->d_ovf2);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -236,6 +238,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     }
     const bool use_tile = ctx->lanes == 0;
     if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf, ctx->cap_ovf, n_pairs); if (rc) return rc; }
+    if (use_tile) { rc = ensure(ctx, ctx->d_ovf2, ctx->cap_ovf2, n_pairs); if (rc) return rc; }
 
     ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = false;
     const bool prof = ctx->profiling;
@@ -281,14 +284,34 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
             gjk::gjk_tile_kernel<false><<<(unsigned)blocks, gjk::TILE, smem, st>>>(a);
         }
         ++ctx->launches;
-        // K1b over the overflow list (exits at once when the list is empty)
-        if (ctx->max_hull_hint == 0 || ctx->max_hull_hint > 16) {
+        // K1c: hulls too large for a column -> 4-lane sub-warps over TMA-staged slots; K1b: anything larger still
+        const int hint = ctx->max_hull_hint;
+        if (hint == 0 || hint > 16) {
+            const int cap_v = (hint > 0 && hint < 64) ? hint : 64;
+            const int slot_doubles = ((3 * 2 * cap_v + 15) / 16) * 16 + 4;
+            const size_t smem_c = (size_t)slot_doubles * 8 /*pairs per warp*/ * 4 /*warps*/ * sizeof(double);
             gjk::BatchArgs b = a;
             b.pair_list = ctx->d_ovf; b.pair_list_count = ctx->d_counters + 2;
-            const int blocks_b = ctx->sm_count * 4;
-            if (fuse) gjk::gjk_group_kernel<4, true><<<blocks_b, 128, 0, st>>>(b);
-            else      gjk::gjk_group_kernel<4, false><<<blocks_b, 128, 0, st>>>(b);
+            b.ovf_list = ctx->d_ovf2; b.ovf_count = ctx->d_counters + 5;
+            int per_sm = 1;
+            if (fuse) {
+                CU(cudaFuncSetAttribute(gjk::gjk_group_staged_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_group_staged_kernel<4, true>, 128, smem_c));
+                gjk::gjk_group_staged_kernel<4, true><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(b, slot_doubles);
+            } else {
+                CU(cudaFuncSetAttribute(gjk::gjk_group_staged_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_group_staged_kernel<4, false>, 128, smem_c));
+                gjk::gjk_group_staged_kernel<4, false><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(b, slot_doubles);
+            }
             ++ctx->launches;
+            if (hint == 0 || hint > 64) {
+                gjk::BatchArgs c = a;
+                c.pair_list = ctx->d_ovf2; c.pair_list_count = ctx->d_counters + 5;
+                const int blocks_c = ctx->sm_count * 4;
+                if (fuse) gjk::gjk_group_kernel<4, true><<<blocks_c, 128, 0, st>>>(c);
+                else      gjk::gjk_group_kernel<4, false><<<blocks_c, 128, 0, st>>>(c);
+                ++ctx->launches;
+            }
         }
     } else {
         const int L = ctx->lanes;

@@ -380,53 +380,6 @@ GJK_HD Vec3 simplex_mean(const Vec3 *S)
               add(add(add(S[0].z, S[1].z), S[2].z), S[3].z) / 4.0);
 }
 
-// isPointInSimplex(O, S), F:1217-1265, from precomputed face normals
-template <int L>
-GJK_HD bool contains_origin(const Lanes<L> &g, const Vec3 *S, const Faces<L> &F, Vec3 M)
-{
-    bool band_hit = false, all_pos = true;
-#pragma unroll
-    for (int j = 0; j < Faces<L>::FPL; ++j) {
-        int f = g.lane + j * L;
-        Vec3 ref = pick4(S, f);                                   // simplex_(i,:), F:1240
-        Vec3 n = F.q[j];
-        if (dot3(n, ref - M) < 0.0) n = neg(n);
-        double dist = dot3(ref, n);                               // (simplex_(i,:) - O) . nml(i,:)
-        all_pos = all_pos && (dist > 0.0);
-        if (fabs(dist) < 1.0e-8) {                                // F:1248
-            int a, b, c;
-            face_rows(f, a, b, c);
-            if (inside_pf3(pick4(S, a), pick4(S, b), pick4(S, c), v3(0.0, 0.0, 0.0))) band_hit = true;
-        }
-    }
-    return g.any(band_hit) || g.all(all_pos);
-}
-
-// face pick of update_simplex_GJK, F:1093-1124: returns k and the search direction
-template <int L>
-GJK_HD int pick_face(const Lanes<L> &g, const Vec3 *S, const Faces<L> &F, Vec3 M, Vec3 &dir)
-{
-    Vec3 nu[Faces<L>::FPL];
-    double wbest = 0.0; int fbest = 0;
-#pragma unroll
-    for (int j = 0; j < Faces<L>::FPL; ++j) {
-        int f = g.lane + j * L;
-        Vec3 ref = (f == 3) ? S[1] : S[0];
-        Vec3 n = F.q[j];
-        if (dot3(n, ref - M) < 0.0) n = neg(n);
-        nu[j] = n;
-        double w = dot3(neg(n), ref);                             // DOT(-nml, simplex_(ref,:) - O)
-        if (j == 0 || w > wbest) { wbest = w; fbest = f; }        // MAXLOC: first maximum
-    }
-    g.argmax_first(wbest, fbest);
-    int k = fbest, slot = k / L;
-    Vec3 mine = nu[0];
-#pragma unroll
-    for (int j = 1; j < Faces<L>::FPL; ++j) mine = sel(slot == j, nu[j], mine);
-    dir = v3(g.bcast(mine.x, k % L), g.bcast(mine.y, k % L), g.bcast(mine.z, k % L));
-    return k;
-}
-
 // tail of VEC_PL(O, (A, B)), F:1436-1438: D = A + (AC.AB / |AB|) * UTZVEC(AB); returns UTZVEC(D - O).
 // With MathFast a NaN x-component tells the caller to redo the block with MathExact.
 template <class M>
@@ -454,114 +407,204 @@ struct GjkOut {
     int band;           // times IS_INSIDE_PF was entered (1e-8 bands)
 };
 
+// =====================================================================================================
+// The flag path in two stages.
+//
+//   gjk_init     sphere test, line and triangle of the initial tetrahedron (F:76-151).  Every pair does
+//                the same amount of work here, so a warp of 32 pairs runs it in lockstep.
+//   walk_round   ONE support query plus everything that follows it: the fourth vertex of the initial
+//                tetrahedron (F:154-170, "first" round) or one step of the tetrahedron walk
+//                (F:186-234).  Both are the same computation -- append the support point to a kept
+//                triangle, test the degenerate cases against that triangle's normal, compute the three
+//                new face normals, test containment, choose the next face -- so they share one
+//                instruction stream: one support site and one normal-computation site in the whole
+//                walk (the instruction cache, not the FP64 pipe, bounded the monolithic form).
+//
+// State carried between rounds (struct Walk): the simplex, the kept face's unit normal and |cross| (the
+// next query direction IS that normal, up to the flip bit), and what the stall test F:219-234 needs.
+// simplex_last_1 is the simplex before the update; simplex_last_2 is rebuilt, in the rare case row 4
+// already matches, from the vertex the previous update dropped (D1) and the face it kept (k1).
+// =====================================================================================================
+enum : unsigned { WF_FLIP = 1u, WF_FIRST = 2u, WF_NZ = 4u, WF_HAVE2 = 8u, WF_COLD = 16u, WF_STOP = 32u };
+
+struct Walk {
+    Vec3 S[4];          // simplex rows (same in every lane of the group)
+    Vec3 qk;            // UTZVEC of the kept face's cross product, unflipped; query direction = +-qk
+    double mk;          // |cross| of the kept face
+    Vec3 D1;            // first round: UNINML's raw quotient (F:1392); later: vertex dropped by the previous update
+    int k, k1;          // face kept by the pending update / by the previous one
+    int iters;          // reference `iter`
+    int n_support;
+    unsigned fl;
+};
+
+// full stall test F:219-234 for rows 1..3 (row 4 was matched by the caller).  Cold.
+GJK_HD_NOINLINE bool stall_rows(Vec3 p0, Vec3 p1, Vec3 p2, Vec3 n0, Vec3 n1, Vec3 n2, Vec3 D1, int k1, bool have2)
+{
+    const Vec3 O = v3(0.0, 0.0, 0.0);
+    Vec3 l0 = O, l1 = O, l2 = O;                 // rows 0..2 of simplex_last_2 (zeros before the second iteration, F:178)
+    if (have2) {                                 // previous update: last_2(a,b,c) -> last_1(0,1,2), last_2(d) dropped
+        l0 = (k1 == 3) ? D1 : p0;                // row 0 is a of faces 0,1,2
+        l1 = (k1 == 0) ? D1 : ((k1 == 3) ? p0 : p1);     // row 1: dropped by face 0; a of face 3; b of faces 1,2
+        l2 = (k1 == 1) ? D1 : ((k1 == 2) ? p2 : p1);     // row 2: dropped by face 1; c of face 2; b of faces 0,3
+    }
+    return (close3(n0, p0) || close3(n0, l0)) && (close3(n1, p1) || close3(n1, l1)) && (close3(n2, p2) || close3(n2, l2));
+}
+
+// F:219-234 on the rows as they are before the update (p = simplex_last_1, n/sp = the new simplex).  Row 4
+// is tested first: it is the new support point, which differs from the two before it unless the walk
+// really cycles, so the other rows (and the rebuilt simplex_last_2) are almost never looked at.
+GJK_HD bool stall_test(Vec3 p0, Vec3 p1, Vec3 p2, Vec3 p3, Vec3 n0, Vec3 n1, Vec3 n2, Vec3 sp, Vec3 D1, int k1, bool have2)
+{
+    const Vec3 l23 = have2 ? sel(k1 == 2, D1, p2) : v3(0.0, 0.0, 0.0);
+    if (!(close3(sp, p3) || close3(sp, l23))) return false;
+    return stall_rows(p0, p1, p2, n0, n1, n2, D1, k1, have2);
+}
+
+// Initial line and triangle.  Returns the exit path, or 0 with `w` ready for the first walk_round.
+template <int L, class HV>
+GJK_HD int gjk_init(const Lanes<L> &g, const HV &A, const HV &B, const Sphere &sa, const Sphere &sb, Walk &w)
+{
+    const Vec3 O = v3(0.0, 0.0, 0.0);
+    w.S[0] = w.S[1] = w.S[2] = w.S[3] = O;
+    w.qk = O; w.mk = 0.0; w.D1 = O; w.k = 2; w.k1 = 2; w.iters = 0; w.n_support = 0; w.fl = WF_FIRST;
+
+    if (!sphere_hit(sa, sb)) return EXIT_SPHERE;                              // F:76-77
+    int it = 0;
+    for (;;) {
+        ++it;
+        if (it > 99) return EXIT_INIT_CAP;                                    // F:86
+        support_both(g, A, B, dir_table(it - 1), w.S[0], w.S[1]);            // F:94-103
+        w.n_support += 2;
+        if (!close3(w.S[0], w.S[1])) break;                                  // F:106
+    }
+    Vec3 dir;
+    {   // VEC_PL(O, S0, S1), F:1431-1438 (quirk Q4: points from O to its foot on the line)
+        Vec3 ab = w.S[1] - w.S[0], ac = O - w.S[0];
+        double dab = dot3(ac, ab);
+        dir = vec_pl_tail<MathFast>(w.S[0], ab, dab);
+        if (dir.x != dir.x) { dir = vec_pl_tail<MathCold>(w.S[0], ab, dab); w.fl |= WF_COLD; }   // NaN marks "redo exactly"
+    }
+    w.S[2] = support(g, A, B, dir); ++w.n_support;                           // F:119
+    if (close3(w.S[2], w.S[0]) || close3(w.S[2], w.S[1])) return EXIT_DUP3;  // F:123
+
+    Vec3 c3 = cross3(w.S[1] - w.S[0], w.S[2] - w.S[1]);                      // F:132-135
+    double md3; Vec3 q3;
+    {
+        bool ok = true;
+        md3 = MathFast::nrm(c3, ok);
+        q3 = MathFast::dv(c3, md3, ok);
+        if (!ok) { w.fl |= WF_COLD; bool dummy = true; md3 = MathCold::nrm(c3, dummy); q3 = (md3 > 0.0) ? MathCold::dv(c3, md3, dummy) : O; }
+    }
+    dir = (md3 < 1.0e-12) ? O : q3;                                          // UTZVEC
+    {
+        Vec3 vo = O - w.S[2];
+        double dt = dot3(vo, dir);
+        if (fabs(dt) < 1.0e-8 && inside_pf3(w.S[0], w.S[1], w.S[2], O)) return EXIT_TRI_ORIGIN;   // F:140
+        if (dt < 0.0) w.fl |= WF_FLIP;                                       // F:151
+    }
+    // the triangle is face (1,2,3) of the tetrahedron to come: (S1-S2)x(S2-S3) has the operands of c3 with
+    // both factors negated, i.e. the same products -- its normal is not computed again
+    w.qk = dir; w.mk = md3;
+    w.D1 = q3;                                                               // UNINML's own zero rule needs the raw quotient, F:1392
+    if (fabs(c3.x) > 1.0e-12 || fabs(c3.y) > 1.0e-12 || fabs(c3.z) > 1.0e-12) w.fl |= WF_NZ;
+    return 0;
+}
+
+// One support query and the tetrahedron step that consumes it.  Returns the exit path or 0.
+template <int L, class HV>
+GJK_HD int walk_round(const Lanes<L> &g, const HV &A, const HV &B, Walk &w)
+{
+    constexpr int FPL = Faces<L>::FPL;
+    const Vec3 O = v3(0.0, 0.0, 0.0);
+    const bool first = (w.fl & WF_FIRST) != 0u;
+    const int k = w.k;
+    const Vec3 sp = support(g, A, B, (w.fl & WF_FLIP) ? neg(w.qk) : w.qk);   // F:154 / F:1127
+    ++w.n_support;
+
+    const Vec3 p0 = w.S[0], p1 = w.S[1], p2 = w.S[2], p3 = w.S[3];
+    const Vec3 n0 = sel(k == 3, p1, p0);                                    // F:1130-1150: rows (a,b,c) of the kept face
+    const Vec3 n1 = sel(k == 0 || k == 3, p2, p1);
+    const Vec3 n2 = sel(k == 2, p2, p3);
+    const Vec3 dropped = sel(k == 0, p1, sel(k == 1, p2, sel(k == 2, p3, p0)));
+    const bool stall = !first && stall_test(p0, p1, p2, p3, n0, n1, n2, sp, w.D1, w.k1, (w.fl & WF_HAVE2) != 0u);
+    w.S[0] = n0; w.S[1] = n1; w.S[2] = n2; w.S[3] = sp;
+
+    {   // degenerate cases, against the kept triangle: F:157 (DIST_PF_SIGN with UNINML's zero rule) / F:199-206
+        const Vec3 nrm = first ? (((w.fl & WF_NZ) != 0u) ? w.D1 : O) : w.qk;
+        const bool degen = first ? (fabs(nrm.x) < 1.0e-12 && fabs(nrm.y) < 1.0e-12 && fabs(nrm.z) < 1.0e-12) : (w.mk < 1.0e-8);
+        if (degen) { if (first) w.fl |= WF_STOP; return first ? EXIT_STOP : EXIT_LOOP_COLLINEAR; }
+        if (fabs(dot3(sp - n0, nrm)) < 1.0e-8) return first ? EXIT_COPLANAR4 : EXIT_LOOP_COPLANAR;
+    }
+
+    Faces<L> F;
+    if (L == 1) {
+        F.q[2 % FPL] = w.qk; F.md[2 % FPL] = w.mk;
+        if (compute_faces<L, (L == 1 ? 2 : -1)>(g, w.S, F)) w.fl |= WF_COLD;
+    } else {
+        if (compute_faces<L>(g, w.S, F)) w.fl |= WF_COLD;
+    }
+    const Vec3 M = simplex_mean(w.S);
+
+    // containment (isPointInSimplex F:1236-1262) and the next face (update_simplex_GJK F:1093-1124) from the
+    // same normals: a flipped normal only changes the sign of its dot products, bit for bit
+    bool band_hit = false, all_pos = true;
+    double wbest = 0.0; int fbest = 0; Vec3 qbest = O; double mbest = 0.0; bool flbest = false;
+#pragma unroll
+    for (int j = 0; j < FPL; ++j) {
+        const int f = g.lane + j * L;
+        const Vec3 q = F.q[j];
+        const Vec3 refc = pick4(w.S, f);                                    // simplex_(i,:), F:1240
+        const double sc = dot3(q, refc - M);
+        const double uc = dot3(refc, q);
+        const double dist = (sc < 0.0) ? -uc : uc;                          // (simplex_(i,:) - O) . nml(i,:)
+        all_pos = all_pos && (dist > 0.0);
+        if (fabs(uc) < 1.0e-8) {                                            // F:1248
+            int a, b, c;
+            face_rows(f, a, b, c);
+            if (inside_pf3(pick4(w.S, a), pick4(w.S, b), pick4(w.S, c), O)) band_hit = true;
+        }
+        double sk, uk;
+        if (L == 1 && j == 0) { sk = sc; uk = uc; }                         // face (1,3,4): both tests refer to row 1
+        else {
+            const Vec3 refp = (f == 3) ? w.S[1] : w.S[0];
+            sk = dot3(q, refp - M);
+            uk = dot3(q, refp);
+        }
+        const bool flp = sk < 0.0;
+        const double wv = flp ? uk : -uk;                                   // DOT(-nml, simplex_(ref,:) - O)
+        if (j == 0 || wv > wbest) { wbest = wv; fbest = f; qbest = q; mbest = F.md[j]; flbest = flp; }   // MAXLOC: first maximum
+    }
+    if (g.any(band_hit) || g.all(all_pos)) return first ? EXIT_INIT_CONTAIN : EXIT_LOOP_CONTAIN;   // F:164 / F:210
+    if (stall) return EXIT_LOOP_STALL;
+
+    // next iteration, F:186-194
+    if (w.iters + 1 > 50) { w.iters = 50; return EXIT_LOOP_CAP; }
+    ++w.iters;
+    g.argmax_first(wbest, fbest);
+    const int owner = fbest % L;
+    w.qk = v3(g.bcast(qbest.x, owner), g.bcast(qbest.y, owner), g.bcast(qbest.z, owner));
+    w.mk = g.bcast(mbest, owner);
+    const bool fl = g.bcast_i(flbest ? 1 : 0, owner) != 0;
+    w.k1 = k; w.D1 = dropped; w.k = fbest;
+    w.fl = (w.fl & (WF_COLD)) | (fl ? WF_FLIP : 0u) | (first ? 0u : WF_HAVE2);
+    return 0;
+}
+
 // The whole GJKEPA flag path for one pair.  S: 4 rows, final simplex on return (row 3 zero on the
 // F:140 path, hazard H1).  All lanes of the group return the same values.
 template <int L, class HV>
 GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HV &A, const HV &B,
                        const Sphere &sa, const Sphere &sb, Vec3 *S)
 {
-    constexpr int FPL = Faces<L>::FPL;
-    GjkOut o; o.exit_path = 0; o.iters = 0; o.n_support = 0; o.stop_flag = false; o.cold = 0; o.band = 0;
-    const Vec3 O = v3(0.0, 0.0, 0.0);
-    S[0] = S[1] = S[2] = S[3] = O;
-
-    if (!sphere_hit(sa, sb)) { o.exit_path = EXIT_SPHERE; return o; }          // F:76-77
-
-    // ---- initial tetrahedron, F:82-170 ----
-    int it = 0;
-    for (;;) {
-        ++it;
-        if (it > 99) { o.exit_path = EXIT_INIT_CAP; return o; }               // F:86
-        support_both(g, A, B, dir_table(it - 1), S[0], S[1]);                // F:94-103
-        o.n_support += 2;
-        if (!close3(S[0], S[1])) break;                                      // F:106
-    }
-    Vec3 dir;
-    {   // VEC_PL(O, S0, S1), F:1431-1438 (quirk Q4: points from O to its foot on the line)
-        Vec3 ab = S[1] - S[0], ac = O - S[0];
-        double dab = dot3(ac, ab);
-        dir = vec_pl_tail<MathFast>(S[0], ab, dab);
-        if (dir.x != dir.x) { dir = vec_pl_tail<MathCold>(S[0], ab, dab); ++o.cold; }      // NaN marks "redo exactly"
-    }
-    S[2] = support(g, A, B, dir); ++o.n_support;                             // F:119
-    if (close3(S[2], S[0]) || close3(S[2], S[1])) { o.exit_path = EXIT_DUP3; return o; }   // F:123
-
-    Vec3 c3 = cross3(S[1] - S[0], S[2] - S[1]);                              // F:132-135
-    double md3; Vec3 q3;
-    {
-        bool ok = true;
-        md3 = MathFast::nrm(c3, ok);
-        q3 = MathFast::dv(c3, md3, ok);
-        if (!ok) { ++o.cold; bool dummy = true; md3 = MathCold::nrm(c3, dummy); q3 = (md3 > 0.0) ? MathCold::dv(c3, md3, dummy) : O; }
-    }
-    dir = (md3 < 1.0e-12) ? O : q3;                                          // UTZVEC
-    {
-        Vec3 vo = O - S[2];
-        double dt = dot3(vo, dir);
-        if (fabs(dt) < 1.0e-8 && inside_pf3(S[0], S[1], S[2], O)) { o.exit_path = EXIT_TRI_ORIGIN; return o; }   // F:140
-        if (dt < 0.0) dir = neg(dir);                                        // F:151
-    }
-    S[3] = support(g, A, B, dir); ++o.n_support;                             // F:154
-    {   // DIST_PF_SIGN(S3, (S0,S1,S2)), F:157, with UNINML's own zero rule (F:1392)
-        bool nz = fabs(c3.x) > 1.0e-12 || fabs(c3.y) > 1.0e-12 || fabs(c3.z) > 1.0e-12;
-        Vec3 n = nz ? q3 : O;
-        if (fabs(n.x) < 1.0e-12 && fabs(n.y) < 1.0e-12 && fabs(n.z) < 1.0e-12) { o.exit_path = EXIT_STOP; o.stop_flag = true; return o; }
-        if (fabs(dot3(S[3] - S[0], n)) < 1.0e-8) { o.exit_path = EXIT_COPLANAR4; return o; }
-    }
-    Faces<L> F;
-    o.cold += compute_faces<L>(g, S, F);
-    Vec3 M = simplex_mean(S);
-    if (contains_origin(g, S, F, M)) { o.exit_path = EXIT_INIT_CONTAIN; return o; }   // F:164
-
-    // ---- tetrahedron walk, F:178-236 ----
-    Vec3 last1[FPL], last2[FPL];                  // rows lane + j*L of simplex_last_1 / _2
-#pragma unroll
-    for (int j = 0; j < FPL; ++j) { last1[j] = O; last2[j] = O; }
-
-    for (int iter = 1; ; ++iter) {
-        if (iter > 50) { o.iters = 50; o.exit_path = EXIT_LOOP_CAP; return o; }       // F:186
-        o.iters = iter;
-#pragma unroll
-        for (int j = 0; j < FPL; ++j) { last2[j] = last1[j]; last1[j] = pick4(S, g.lane + j * L); }   // F:193-194
-
-        int k = pick_face(g, S, F, M, dir);                                  // F:1093-1124
-        Vec3 sm = support(g, A, B, dir); ++o.n_support;                      // F:1127
-        {
-            int a, b, c;
-            face_rows(k, a, b, c);
-            Vec3 n0 = pick4(S, a), n1 = pick4(S, b), n2 = pick4(S, c);       // F:1130-1150
-            S[0] = n0; S[1] = n1; S[2] = n2; S[3] = sm;
-        }
-        {   // F:199-206 first: face (1,2,3) of the new simplex is the face the walk kept (same operands,
-            // same bits), so both degeneracy exits are decided before any new normal is computed --
-            // this is how ~all separated pairs leave, usually with two zero-area new faces
-            const int owner = k % L, slot = k / L;
-            Vec3 qs = F.q[0]; double ms = F.md[0];
-#pragma unroll
-            for (int j = 1; j < FPL; ++j) { qs = sel(slot == j, F.q[j], qs); ms = (slot == j) ? F.md[j] : ms; }
-            const double mk = g.bcast(ms, owner);
-            if (mk < 1.0e-8) { o.exit_path = EXIT_LOOP_COLLINEAR; return o; }
-            const Vec3 qk = v3(g.bcast(qs.x, owner), g.bcast(qs.y, owner), g.bcast(qs.z, owner));
-            if (fabs(dot3(S[3] - S[0], qk)) < 1.0e-8) { o.exit_path = EXIT_LOOP_COPLANAR; return o; }
-            if (L == 1) {
-                F.q[2 % FPL] = qk; F.md[2 % FPL] = mk;
-                o.cold += compute_faces<L, (L == 1 ? 2 : -1)>(g, S, F);
-            } else {
-                o.cold += compute_faces<L>(g, S, F);
-            }
-        }
-        M = simplex_mean(S);
-        if (contains_origin(g, S, F, M)) { o.exit_path = EXIT_LOOP_CONTAIN; return o; }   // F:210
-        {   // F:219-234
-            bool ok = true;
-#pragma unroll
-            for (int j = 0; j < FPL; ++j) {
-                Vec3 r = pick4(S, g.lane + j * L);
-                ok = ok && (close3(r, last1[j]) || close3(r, last2[j]));
-            }
-            if (g.all(ok)) { o.exit_path = EXIT_LOOP_STALL; return o; }
-        }
-    }
+    Walk w;
+    int e = gjk_init<L>(g, A, B, sa, sb, w);
+    while (e == 0) e = walk_round<L>(g, A, B, w);
+    GjkOut o;
+    o.exit_path = e; o.iters = w.iters; o.n_support = w.n_support;
+    o.stop_flag = (w.fl & WF_STOP) != 0u; o.cold = (w.fl & WF_COLD) ? 1 : 0; o.band = 0;
+    S[0] = w.S[0]; S[1] = w.S[1]; S[2] = w.S[2]; S[3] = w.S[3];
+    return o;
 }
 
 }  // namespace gjk

@@ -26,3 +26,18 @@ extern "C" void hostsim_gjk_batch(const double *verts, const int64_t *hull_off, 
         if (simplex) std::memcpy(simplex + 12 * i, S, 12 * sizeof(double));
     }
 }
+
+// Unit hook for the stall test F:219-234: the product keeps only the vertex the previous update dropped
+// and the face it kept; the test harness passes explicit simplex_last_1 / simplex_last_2 arrays as the
+// reference holds them and compares the two answers.
+extern "C" int hostsim_stall(const double *last1, const double *last2, int have2, int k1, int k, const double *sp_)
+{
+    using namespace gjk;
+    Vec3 p[4], l2[4];
+    for (int i = 0; i < 4; ++i) { p[i] = v3(last1[3 * i], last1[3 * i + 1], last1[3 * i + 2]); l2[i] = v3(last2[3 * i], last2[3 * i + 1], last2[3 * i + 2]); }
+    int a1, b1, c1; face_rows(k1, a1, b1, c1);
+    const int d1 = 6 - a1 - b1 - c1;
+    int a, b, c; face_rows(k, a, b, c);
+    Vec3 sp = v3(sp_[0], sp_[1], sp_[2]);
+    return stall_test(p[0], p[1], p[2], p[3], p[a], p[b], p[c], sp, l2[d1], k1, have2 != 0) ? 1 : 0;
+}

@@ -50,3 +50,40 @@ def test_core_golden_fixture(golden, host_sim, W):
     col, st, ns, sx = run_sim(host_sim, b)
     assert np.array_equal(col, g["collision"]) and np.array_equal(st & 0xff, g["exit_path"])
     assert np.array_equal((st >> 8) & 0xff, g["gjk_iters"])
+
+
+def test_stall_test_equals_the_reference_form(host_sim):
+    """F:219-234 with explicit simplex_last_1/_2 arrays (as the reference keeps them) against the product's
+    form, which rebuilds simplex_last_2 from the previously dropped vertex.  No synthetic workload reaches
+    this exit, so the cases are constructed: consistent walk histories with rows forced to coincide."""
+    rng = np.random.default_rng(5)
+    rows = {0: (0, 2, 3), 1: (0, 1, 3), 2: (0, 1, 2), 3: (1, 2, 3)}
+    host_sim.hostsim_stall.restype = C.c_int
+    P = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    n_true = 0
+    for trial in range(20000):
+        have2 = trial % 5 != 0
+        pool = rng.normal(size=(3, 3))                                  # few distinct points -> many coincidences
+        pick = lambda: pool[rng.integers(0, 3)] + (rng.random(3) < 0.3) * rng.choice([0.0, 5e-9, 2e-8], size=3)
+        last2 = np.array([pick() for _ in range(4)]) if have2 else np.zeros((4, 3))
+        k1 = int(rng.integers(0, 4))
+        last1 = np.zeros((4, 3))
+        if have2:
+            a1, b1, c1 = rows[k1]
+            last1[0], last1[1], last1[2] = last2[a1], last2[b1], last2[c1]
+            last1[3] = pick()
+        else:
+            last1 = np.array([pick() for _ in range(4)])
+            if trial % 3 == 0:
+                last1[:] = rng.choice([0.0, 3e-9], size=(4, 3))          # rows close to the zero history
+        k = int(rng.integers(0, 4))
+        a, b, c = rows[k]
+        sp = pick() if trial % 4 else last1[3] + rng.choice([0.0, 4e-9, 2e-8], size=3)
+        new = np.array([last1[a], last1[b], last1[c], sp])
+        close = lambda u, v: bool(np.all(np.abs(u - v) < 1e-8))
+        want = all(close(new[i], last1[i]) or close(new[i], last2[i]) for i in range(4))
+        got = host_sim.hostsim_stall(P(np.ascontiguousarray(last1)), P(np.ascontiguousarray(last2)), int(have2), k1, k,
+                                     P(np.ascontiguousarray(sp)))
+        assert bool(got) == want, (trial, k1, k, have2)
+        n_true += want
+    assert n_true > 200                                                  # the constructed cases do reach the exit

@@ -21,7 +21,7 @@ MODE_GJK, MODE_EPA, MODE_FULL = 0, 1, 2
 # every symbol include/gjkepa.h declares
 SYMBOLS = [
     "gjkepa_create", "gjkepa_destroy", "gjkepa_set_stream", "gjkepa_use_own_stream", "gjkepa_last_error",
-    "gjkepa_launch_count", "gjkepa_set_lanes", "gjkepa_set_max_hull_vertices", "gjkepa_set_profiling", "gjkepa_kernel_ms", "gjkepa_pair_f64", "gjkepa_batch_f64",
+    "gjkepa_launch_count", "gjkepa_set_lanes", "gjkepa_set_max_hull_vertices", "gjkepa_set_tuning", "gjkepa_set_profiling", "gjkepa_kernel_ms", "gjkepa_pair_f64", "gjkepa_batch_f64",
     "gjkepa_batch_device_f64", "gjkepa_sync", "gjkepa_debug_fp64",
 ]
 
@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
     L.gjkepa_set_lanes.restype = C.c_int
     L.gjkepa_set_max_hull_vertices.argtypes = [vp, C.c_int32]
     L.gjkepa_set_max_hull_vertices.restype = C.c_int
+    L.gjkepa_set_tuning.argtypes = [vp, C.c_int32, C.c_int32]
+    L.gjkepa_set_tuning.restype = C.c_int
     L.gjkepa_set_profiling.argtypes = [vp, C.c_int32]
     L.gjkepa_set_profiling.restype = C.c_int
     L.gjkepa_kernel_ms.argtypes = [vp, dp]

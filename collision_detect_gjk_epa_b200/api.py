@@ -73,6 +73,12 @@ class Engine:
     def set_max_hull_vertices(self, n: int):
         self._check(self._L.gjkepa_set_max_hull_vertices(self._h, int(n)), "gjkepa_set_max_hull_vertices")
 
+    TUNE_WALK_REFILL, TUNE_SINGLE_KERNEL = 1, 2
+
+    def set_tuning(self, key: int, value: int):
+        """GJKEPA_TUNE_* knobs of include/gjkepa.h (walk re-pack threshold, single-kernel A/B switch)."""
+        self._check(self._L.gjkepa_set_tuning(self._h, int(key), int(value)), "gjkepa_set_tuning")
+
     def set_stream(self, cuda_stream: int):
         self._check(self._L.gjkepa_set_stream(self._h, C.c_void_p(int(cuda_stream))), "gjkepa_set_stream")
 

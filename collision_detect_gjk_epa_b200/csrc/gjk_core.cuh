@@ -70,7 +70,16 @@ struct Vec3 { double x, y, z; };
 
 GJK_HD Vec3 v3(double x, double y, double z) { Vec3 r; r.x = x; r.y = y; r.z = z; return r; }
 GJK_HD Vec3 operator-(Vec3 a, Vec3 b) { return v3(sub(a.x, b.x), sub(a.y, b.y), sub(a.z, b.z)); }
-GJK_HD Vec3 neg(Vec3 a) { return v3(-a.x, -a.y, -a.z); }
+// sign flip on the integer pipe: the FP64 pipe is the scarce unit (a DADD with -0 would do the same bits)
+GJK_HD double negd(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000u, __double2loint(x));
+#else
+    return -x;
+#endif
+}
+GJK_HD Vec3 neg(Vec3 a) { return v3(negd(a.x), negd(a.y), negd(a.z)); }
 GJK_HD double dot3(Vec3 a, Vec3 b)
 {   // DOT_PRODUCT: ((a1*b1) + a2*b2) + a3*b3   (the leading 0+ only affects the sign of zero)
     return add(add(mul(a.x, b.x), mul(a.y, b.y)), mul(a.z, b.z));
@@ -274,14 +283,32 @@ template <int L> struct Lanes {
 };
 #endif
 
+// Scans of one hull by lanes lane0, lane0+step, ...: first arg-max (and first arg-min) of d.v.  Views with
+// a vectorised layout overload these (found by argument-dependent lookup at instantiation).
+template <class HV>
+GJK_HD void scan_argmax(const HV &h, Vec3 d, int lane0, int step, double &best, int &idx)
+{
+    best = -DBL_MAX; idx = 0;
+    for (int v = lane0; v < h.n; v += step) { double t = dot3(d, h.get(v)); if (t > best) { best = t; idx = v; } }
+}
+template <class HV>
+GJK_HD void scan_minmax(const HV &h, Vec3 d, int lane0, int step, double &hi, int &ihi, double &lo, int &ilo)
+{
+    hi = -DBL_MAX; lo = DBL_MAX; ihi = 0; ilo = 0;
+    for (int v = lane0; v < h.n; v += step) {
+        double t = dot3(d, h.get(v));
+        if (t > hi) { hi = t; ihi = v; }
+        if (t < lo) { lo = t; ilo = v; }
+    }
+}
+
 // support_mapping, F:1030-1062: p1(first argmax d.p1) - p2(first argmax (-d).p2)
 template <int L, class HV>
 GJK_HD Vec3 support(const Lanes<L> &g, const HV &A, const HV &B, Vec3 d)
 {
-    double bA = -DBL_MAX, bB = -DBL_MAX; int iA = 0, iB = 0;
-    for (int v = g.lane; v < A.n; v += L) { double t = dot3(d, A.get(v)); if (t > bA) { bA = t; iA = v; } }
-    Vec3 nd = neg(d);
-    for (int v = g.lane; v < B.n; v += L) { double t = dot3(nd, B.get(v)); if (t > bB) { bB = t; iB = v; } }
+    double bA, bB; int iA, iB;
+    scan_argmax(A, d, g.lane, L, bA, iA);
+    scan_argmax(B, neg(d), g.lane, L, bB, iB);
     g.argmax_first(bA, iA);
     g.argmax_first(bB, iB);
     return A.get(iA) - B.get(iB);
@@ -292,18 +319,9 @@ GJK_HD Vec3 support(const Lanes<L> &g, const HV &A, const HV &B, Vec3 d)
 template <int L, class HV>
 GJK_HD void support_both(const Lanes<L> &g, const HV &A, const HV &B, Vec3 d, Vec3 &sp, Vec3 &sm)
 {
-    double hiA = -DBL_MAX, loA = DBL_MAX, hiB = -DBL_MAX, loB = DBL_MAX;
-    int ihA = 0, ilA = 0, ihB = 0, ilB = 0;
-    for (int v = g.lane; v < A.n; v += L) {
-        double t = dot3(d, A.get(v));
-        if (t > hiA) { hiA = t; ihA = v; }
-        if (t < loA) { loA = t; ilA = v; }
-    }
-    for (int v = g.lane; v < B.n; v += L) {
-        double t = dot3(d, B.get(v));
-        if (t > hiB) { hiB = t; ihB = v; }
-        if (t < loB) { loB = t; ilB = v; }
-    }
+    double hiA, loA, hiB, loB; int ihA, ilA, ihB, ilB;
+    scan_minmax(A, d, g.lane, L, hiA, ihA, loA, ilA);
+    scan_minmax(B, d, g.lane, L, hiB, ihB, loB, ilB);
     g.argmax_first(hiA, ihA); g.argmin_first(loA, ilA);
     g.argmax_first(hiB, ihB); g.argmin_first(loB, ilB);
     sp = A.get(ihA) - B.get(ilB);      // direction +d
@@ -410,38 +428,47 @@ struct GjkOut {
 // =====================================================================================================
 // The flag path in two stages.
 //
-//   gjk_init     sphere test, line and triangle of the initial tetrahedron (F:76-151).  Every pair does
-//                the same amount of work here, so a warp of 32 pairs runs it in lockstep.
-//   walk_round   ONE support query plus everything that follows it: the fourth vertex of the initial
-//                tetrahedron (F:154-170, "first" round) or one step of the tetrahedron walk
-//                (F:186-234).  Both are the same computation -- append the support point to a kept
-//                triangle, test the degenerate cases against that triangle's normal, compute the three
-//                new face normals, test containment, choose the next face -- so they share one
-//                instruction stream: one support site and one normal-computation site in the whole
-//                walk (the instruction cache, not the FP64 pipe, bounded the monolithic form).
+//   gjk_init     sphere test and the whole initial tetrahedron: line, triangle, fourth vertex and its
+//                degenerate cases (F:76-157).  Every pair does the same amount of work here, so a warp of
+//                32 pairs runs it in lockstep.
+//   walk_round   one turn of the tetrahedron loop, cut where the loop is cheapest to leave:
+//                    face normals of the current tetrahedron -> containment test  (F:164 / F:210, exit)
+//                    -> stall / iteration cap (F:219-234, F:186)                   (exit)
+//                    -> next face and direction (F:1093-1124) -> support (F:1127) -> new tetrahedron
+//                    -> collinear / coplanar tests against the kept face (F:199-206, exit)
+//                The containment test of the INITIAL tetrahedron and of every later one are the same
+//                computation, so the whole walk has one support site and one normal-computation site
+//                (the instruction cache, not the FP64 pipe, bounded the monolithic form), and the exit
+//                separated pairs take -- F:203, ~all of them -- falls at the END of a round.
 //
-// State carried between rounds (struct Walk): the simplex, the kept face's unit normal and |cross| (the
-// next query direction IS that normal, up to the flip bit), and what the stall test F:219-234 needs.
-// simplex_last_1 is the simplex before the update; simplex_last_2 is rebuilt, in the rare case row 4
-// already matches, from the vertex the previous update dropped (D1) and the face it kept (k1).
+// State carried between rounds (struct Walk): the simplex, the unit normal and |cross| of its face
+// (1,2,3) -- the face the last update kept, whose cross product has the operands of the new simplex's
+// face (1,2,3), so it is never recomputed -- and what the stall test F:219-234 needs: simplex_last_1 is
+// the simplex before the update; simplex_last_2 is rebuilt, in the rare case row 4 already matches, from
+// the vertex the previous update dropped (D1) and the face it kept (k1).
 // =====================================================================================================
-enum : unsigned { WF_FLIP = 1u, WF_FIRST = 2u, WF_NZ = 4u, WF_HAVE2 = 8u, WF_COLD = 16u, WF_STOP = 32u };
+enum : unsigned { WF_FIRST = 2u, WF_HAVE2 = 8u, WF_COLD = 16u, WF_STOP = 32u, WF_STALL = 64u };
 
 struct Walk {
     Vec3 S[4];          // simplex rows (same in every lane of the group)
-    Vec3 qk;            // UTZVEC of the kept face's cross product, unflipped; query direction = +-qk
-    double mk;          // |cross| of the kept face
-    Vec3 D1;            // first round: UNINML's raw quotient (F:1392); later: vertex dropped by the previous update
-    int k, k1;          // face kept by the pending update / by the previous one
+    Vec3 qk;            // UTZVEC of face (1,2,3)'s cross product, unflipped
+    double mk;          // |cross| of face (1,2,3)
+    Vec3 D1;            // vertex dropped by the previous update
+    int k1;             // face kept by the previous update
     int iters;          // reference `iter`
     int n_support;
     unsigned fl;
+#if defined(GJK_SHADOW_HISTORY) && !defined(__CUDA_ARCH__)
+    Vec3 sh1[4], sh2[4];    // test builds: simplex_last_1 / _2 kept explicitly, as the reference does (F:193-194)
+#endif
 };
 
-// full stall test F:219-234 for rows 1..3 (row 4 was matched by the caller).  Cold.
-GJK_HD_NOINLINE bool stall_rows(Vec3 p0, Vec3 p1, Vec3 p2, Vec3 n0, Vec3 n1, Vec3 n2, Vec3 D1, int k1, bool have2)
+// F:219-234 for rows 1..3 once row 4 has matched: p = simplex_last_1 (the simplex before the update that
+// keeps face k and appends the support point), simplex_last_2 rebuilt from D1/k1.  Cold.
+GJK_HD_NOINLINE bool stall_rows(Vec3 p0, Vec3 p1, Vec3 p2, Vec3 p3, int k, Vec3 D1, int k1, bool have2)
 {
     const Vec3 O = v3(0.0, 0.0, 0.0);
+    const Vec3 n0 = sel(k == 3, p1, p0), n1 = sel(k == 0 || k == 3, p2, p1), n2 = sel(k == 2, p2, p3);
     Vec3 l0 = O, l1 = O, l2 = O;                 // rows 0..2 of simplex_last_2 (zeros before the second iteration, F:178)
     if (have2) {                                 // previous update: last_2(a,b,c) -> last_1(0,1,2), last_2(d) dropped
         l0 = (k1 == 3) ? D1 : p0;                // row 0 is a of faces 0,1,2
@@ -451,23 +478,52 @@ GJK_HD_NOINLINE bool stall_rows(Vec3 p0, Vec3 p1, Vec3 p2, Vec3 n0, Vec3 n1, Vec
     return (close3(n0, p0) || close3(n0, l0)) && (close3(n1, p1) || close3(n1, l1)) && (close3(n2, p2) || close3(n2, l2));
 }
 
-// F:219-234 on the rows as they are before the update (p = simplex_last_1, n/sp = the new simplex).  Row 4
-// is tested first: it is the new support point, which differs from the two before it unless the walk
-// really cycles, so the other rows (and the rebuilt simplex_last_2) are almost never looked at.
-GJK_HD bool stall_test(Vec3 p0, Vec3 p1, Vec3 p2, Vec3 p3, Vec3 n0, Vec3 n1, Vec3 n2, Vec3 sp, Vec3 D1, int k1, bool have2)
+// F:219-234 on the rows as they are before the update.  Row 4 is tested first: it is the new support
+// point, which differs from the two before it unless the walk really cycles, so the other rows (and the
+// rebuilt simplex_last_2) are almost never looked at.
+GJK_HD bool stall_test(Vec3 p0, Vec3 p1, Vec3 p2, Vec3 p3, int k, Vec3 sp, Vec3 D1, int k1, bool have2)
 {
     const Vec3 l23 = have2 ? sel(k1 == 2, D1, p2) : v3(0.0, 0.0, 0.0);
     if (!(close3(sp, p3) || close3(sp, l23))) return false;
-    return stall_rows(p0, p1, p2, n0, n1, n2, D1, k1, have2);
+    return stall_rows(p0, p1, p2, p3, k, D1, k1, have2);
 }
 
-// Initial line and triangle.  Returns the exit path, or 0 with `w` ready for the first walk_round.
+#if defined(GJK_SHADOW_HISTORY) && !defined(__CUDA_ARCH__)
+// Test builds: keep simplex_last_1/_2 as explicit arrays and compare, at every walk iteration, (a) the rows
+// rebuilt from D1/k1 with simplex_last_2 and (b) the two-level stall test with the reference's four-row form.
+static long long g_shadow_checks = 0, g_shadow_mismatch = 0;
+inline bool same3(Vec3 a, Vec3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+inline void shadow_history_check(Walk &w, int k, Vec3 sp, bool have2)
+{
+    const Vec3 O = v3(0.0, 0.0, 0.0);
+    if (w.fl & WF_FIRST) { for (int i = 0; i < 4; ++i) w.sh1[i] = w.sh2[i] = O; }     // F:178-179
+    for (int i = 0; i < 4; ++i) { w.sh2[i] = w.sh1[i]; w.sh1[i] = w.S[i]; }           // F:193-194
+    ++g_shadow_checks;
+    const Vec3 p0 = w.S[0], p1 = w.S[1], p2 = w.S[2];
+    Vec3 l0 = O, l1 = O, l2 = O, l3 = O;
+    if (have2) {
+        const int k1 = w.k1; const Vec3 D1 = w.D1;
+        l0 = (k1 == 3) ? D1 : p0;
+        l1 = (k1 == 0) ? D1 : ((k1 == 3) ? p0 : p1);
+        l2 = (k1 == 1) ? D1 : ((k1 == 2) ? p2 : p1);
+        l3 = (k1 == 2) ? D1 : p2;
+    }
+    if (!(same3(l0, w.sh2[0]) && same3(l1, w.sh2[1]) && same3(l2, w.sh2[2]) && same3(l3, w.sh2[3]))) ++g_shadow_mismatch;
+    int a, b, c; face_rows(k, a, b, c);
+    const Vec3 nw[4] = { w.S[a], w.S[b], w.S[c], sp };
+    bool ref = true;
+    for (int i = 0; i < 4; ++i) ref = ref && (close3(nw[i], w.sh1[i]) || close3(nw[i], w.sh2[i]));
+    if (ref != stall_test(w.S[0], w.S[1], w.S[2], w.S[3], k, sp, w.D1, w.k1, have2)) ++g_shadow_mismatch;
+}
+#endif
+
+// Initial tetrahedron.  Returns the exit path, or 0 with `w` ready for the first walk_round.
 template <int L, class HV>
 GJK_HD int gjk_init(const Lanes<L> &g, const HV &A, const HV &B, const Sphere &sa, const Sphere &sb, Walk &w)
 {
     const Vec3 O = v3(0.0, 0.0, 0.0);
     w.S[0] = w.S[1] = w.S[2] = w.S[3] = O;
-    w.qk = O; w.mk = 0.0; w.D1 = O; w.k = 2; w.k1 = 2; w.iters = 0; w.n_support = 0; w.fl = WF_FIRST;
+    w.qk = O; w.mk = 0.0; w.D1 = O; w.k1 = 2; w.iters = 0; w.n_support = 0; w.fl = WF_FIRST;
 
     if (!sphere_hit(sa, sb)) return EXIT_SPHERE;                              // F:76-77
     int it = 0;
@@ -497,52 +553,56 @@ GJK_HD int gjk_init(const Lanes<L> &g, const HV &A, const HV &B, const Sphere &s
         if (!ok) { w.fl |= WF_COLD; bool dummy = true; md3 = MathCold::nrm(c3, dummy); q3 = (md3 > 0.0) ? MathCold::dv(c3, md3, dummy) : O; }
     }
     dir = (md3 < 1.0e-12) ? O : q3;                                          // UTZVEC
+    // the triangle is face (1,2,3) of the tetrahedron to come: (S1-S2)x(S2-S3) has the operands of c3 with
+    // both factors negated, i.e. the same products -- its normal is not computed again
+    w.qk = dir; w.mk = md3;
     {
         Vec3 vo = O - w.S[2];
         double dt = dot3(vo, dir);
         if (fabs(dt) < 1.0e-8 && inside_pf3(w.S[0], w.S[1], w.S[2], O)) return EXIT_TRI_ORIGIN;   // F:140
-        if (dt < 0.0) w.fl |= WF_FLIP;                                       // F:151
+        if (dt < 0.0) dir = neg(dir);                                        // F:151
     }
-    // the triangle is face (1,2,3) of the tetrahedron to come: (S1-S2)x(S2-S3) has the operands of c3 with
-    // both factors negated, i.e. the same products -- its normal is not computed again
-    w.qk = dir; w.mk = md3;
-    w.D1 = q3;                                                               // UNINML's own zero rule needs the raw quotient, F:1392
-    if (fabs(c3.x) > 1.0e-12 || fabs(c3.y) > 1.0e-12 || fabs(c3.z) > 1.0e-12) w.fl |= WF_NZ;
+    w.S[3] = support(g, A, B, dir); ++w.n_support;                           // F:154
+    {   // DIST_PF_SIGN(S3, (S0,S1,S2)), F:157, with UNINML's own zero rule (F:1392)
+        bool nz = fabs(c3.x) > 1.0e-12 || fabs(c3.y) > 1.0e-12 || fabs(c3.z) > 1.0e-12;
+        Vec3 n = nz ? q3 : O;
+        if (fabs(n.x) < 1.0e-12 && fabs(n.y) < 1.0e-12 && fabs(n.z) < 1.0e-12) { w.fl |= WF_STOP; return EXIT_STOP; }
+        if (fabs(dot3(w.S[3] - w.S[0], n)) < 1.0e-8) return EXIT_COPLANAR4;
+    }
     return 0;
 }
 
-// One support query and the tetrahedron step that consumes it.  Returns the exit path or 0.
-template <int L, class HV>
-GJK_HD int walk_round(const Lanes<L> &g, const HV &A, const HV &B, Walk &w)
+// One turn of the tetrahedron loop in two halves (see the header of this section).
+//
+// Both halves are straight-line for the caller: neither skips work on an exit, they only report it.  A
+// kernel that keeps several pairs per warp runs them on every lane, finished or not (`live` = false just
+// gates the cold out-of-line paths and means "results ignored"), so no branch has to merge two versions
+// of the walk state -- with early returns ptxas materialised the whole simplex in a second register set at
+// every exit (30 % of the walk kernel's instructions were register moves, ncu).
+struct Pick { int k; Vec3 qk; double mk; bool flip; };
+
+// first half: face normals, containment, stall flag, iteration cap; chooses the next face.  Returns the exit
+// path or 0; the simplex is not modified.
+template <int L>
+GJK_HD int walk_test(const Lanes<L> &g, Walk &w, Pick &pk, bool live)
 {
     constexpr int FPL = Faces<L>::FPL;
     const Vec3 O = v3(0.0, 0.0, 0.0);
     const bool first = (w.fl & WF_FIRST) != 0u;
-    const int k = w.k;
-    const Vec3 sp = support(g, A, B, (w.fl & WF_FLIP) ? neg(w.qk) : w.qk);   // F:154 / F:1127
-    ++w.n_support;
-
-    const Vec3 p0 = w.S[0], p1 = w.S[1], p2 = w.S[2], p3 = w.S[3];
-    const Vec3 n0 = sel(k == 3, p1, p0);                                    // F:1130-1150: rows (a,b,c) of the kept face
-    const Vec3 n1 = sel(k == 0 || k == 3, p2, p1);
-    const Vec3 n2 = sel(k == 2, p2, p3);
-    const Vec3 dropped = sel(k == 0, p1, sel(k == 1, p2, sel(k == 2, p3, p0)));
-    const bool stall = !first && stall_test(p0, p1, p2, p3, n0, n1, n2, sp, w.D1, w.k1, (w.fl & WF_HAVE2) != 0u);
-    w.S[0] = n0; w.S[1] = n1; w.S[2] = n2; w.S[3] = sp;
-
-    {   // degenerate cases, against the kept triangle: F:157 (DIST_PF_SIGN with UNINML's zero rule) / F:199-206
-        const Vec3 nrm = first ? (((w.fl & WF_NZ) != 0u) ? w.D1 : O) : w.qk;
-        const bool degen = first ? (fabs(nrm.x) < 1.0e-12 && fabs(nrm.y) < 1.0e-12 && fabs(nrm.z) < 1.0e-12) : (w.mk < 1.0e-8);
-        if (degen) { if (first) w.fl |= WF_STOP; return first ? EXIT_STOP : EXIT_LOOP_COLLINEAR; }
-        if (fabs(dot3(sp - n0, nrm)) < 1.0e-8) return first ? EXIT_COPLANAR4 : EXIT_LOOP_COPLANAR;
-    }
 
     Faces<L> F;
-    if (L == 1) {
-        F.q[2 % FPL] = w.qk; F.md[2 % FPL] = w.mk;
-        if (compute_faces<L, (L == 1 ? 2 : -1)>(g, w.S, F)) w.fl |= WF_COLD;
-    } else {
-        if (compute_faces<L>(g, w.S, F)) w.fl |= WF_COLD;
+    {
+        Vec3 cr[FPL];
+#pragma unroll
+        for (int j = 0; j < FPL; ++j) if (!(L == 1 && j == 2)) {
+            int f = g.lane + j * L, a, b, c;
+            face_rows(f, a, b, c);
+            Vec3 sa = pick4(w.S, a), sb = pick4(w.S, b), sc = pick4(w.S, c);
+            cr[j] = cross3(sa - sb, sb - sc);
+        }
+        if (L == 1) { F.q[2 % FPL] = w.qk; F.md[2 % FPL] = w.mk; }     // face (1,2,3): kept by the last update, same operands
+        const bool ok = faces_from_cross_impl<L, MathFast, (L == 1 ? 2 : -1)>(cr, F);
+        if (!ok && live) { faces_from_cross_impl<L, MathCold, (L == 1 ? 2 : -1)>(cr, F); w.fl |= WF_COLD; }
     }
     const Vec3 M = simplex_mean(w.S);
 
@@ -557,9 +617,9 @@ GJK_HD int walk_round(const Lanes<L> &g, const HV &A, const HV &B, Walk &w)
         const Vec3 refc = pick4(w.S, f);                                    // simplex_(i,:), F:1240
         const double sc = dot3(q, refc - M);
         const double uc = dot3(refc, q);
-        const double dist = (sc < 0.0) ? -uc : uc;                          // (simplex_(i,:) - O) . nml(i,:)
+        const double dist = (sc < 0.0) ? negd(uc) : uc;                     // (simplex_(i,:) - O) . nml(i,:)
         all_pos = all_pos && (dist > 0.0);
-        if (fabs(uc) < 1.0e-8) {                                            // F:1248
+        if (live && fabs(uc) < 1.0e-8) {                                    // F:1248
             int a, b, c;
             face_rows(f, a, b, c);
             if (inside_pf3(pick4(w.S, a), pick4(w.S, b), pick4(w.S, c), O)) band_hit = true;
@@ -572,23 +632,59 @@ GJK_HD int walk_round(const Lanes<L> &g, const HV &A, const HV &B, Walk &w)
             uk = dot3(q, refp);
         }
         const bool flp = sk < 0.0;
-        const double wv = flp ? uk : -uk;                                   // DOT(-nml, simplex_(ref,:) - O)
+        const double wv = flp ? uk : negd(uk);                              // DOT(-nml, simplex_(ref,:) - O)
         if (j == 0 || wv > wbest) { wbest = wv; fbest = f; qbest = q; mbest = F.md[j]; flbest = flp; }   // MAXLOC: first maximum
     }
-    if (g.any(band_hit) || g.all(all_pos)) return first ? EXIT_INIT_CONTAIN : EXIT_LOOP_CONTAIN;   // F:164 / F:210
-    if (stall) return EXIT_LOOP_STALL;
-
-    // next iteration, F:186-194
-    if (w.iters + 1 > 50) { w.iters = 50; return EXIT_LOOP_CAP; }
-    ++w.iters;
     g.argmax_first(wbest, fbest);
     const int owner = fbest % L;
-    w.qk = v3(g.bcast(qbest.x, owner), g.bcast(qbest.y, owner), g.bcast(qbest.z, owner));
-    w.mk = g.bcast(mbest, owner);
-    const bool fl = g.bcast_i(flbest ? 1 : 0, owner) != 0;
-    w.k1 = k; w.D1 = dropped; w.k = fbest;
-    w.fl = (w.fl & (WF_COLD)) | (fl ? WF_FLIP : 0u) | (first ? 0u : WF_HAVE2);
-    return 0;
+    pk.k = fbest;
+    pk.qk = v3(g.bcast(qbest.x, owner), g.bcast(qbest.y, owner), g.bcast(qbest.z, owner));
+    pk.mk = g.bcast(mbest, owner);
+    pk.flip = g.bcast_i(flbest ? 1 : 0, owner) != 0;
+
+    int e = 0;
+    if (g.any(band_hit) || g.all(all_pos)) e = first ? EXIT_INIT_CONTAIN : EXIT_LOOP_CONTAIN;   // F:164 / F:210
+    else if (w.fl & WF_STALL) e = EXIT_LOOP_STALL;                          // F:219-234, decided when the simplex was updated
+    else if (w.iters + 1 > 50) { w.iters = 50; e = EXIT_LOOP_CAP; }         // F:186
+    else ++w.iters;
+    return e;
+}
+
+// second half: support along the chosen face's normal, new tetrahedron (in place), degenerate cases.
+template <int L, class HV>
+GJK_HD int walk_step(const Lanes<L> &g, const HV &A, const HV &B, Walk &w, const Pick &pk, bool live)
+{
+    const int k = pk.k;
+    const Vec3 sp = support(g, A, B, pk.flip ? neg(pk.qk) : pk.qk);         // F:1127
+    ++w.n_support;
+    const bool have2 = (w.fl & WF_HAVE2) != 0u;
+#if defined(GJK_SHADOW_HISTORY) && !defined(__CUDA_ARCH__)
+    shadow_history_check(w, k, sp, have2);
+#endif
+    const bool stall = live && stall_test(w.S[0], w.S[1], w.S[2], w.S[3], k, sp, w.D1, w.k1, have2);
+    w.D1 = sel(k == 0, w.S[1], sel(k == 1, w.S[2], sel(k == 2, w.S[3], w.S[0])));
+    w.k1 = k;
+    // F:1130-1150 in place: rows (a,b,c) of the kept face move up, the support point becomes row 4
+    w.S[0] = sel(k == 3, w.S[1], w.S[0]);
+    w.S[1] = sel(k == 0 || k == 3, w.S[2], w.S[1]);
+    w.S[2] = sel(k != 2, w.S[3], w.S[2]);
+    w.S[3] = sp;
+    w.qk = pk.qk; w.mk = pk.mk;
+    w.fl = (w.fl & (WF_COLD | WF_STOP)) | WF_HAVE2 | (stall ? WF_STALL : 0u);   // from now on simplex_last_2 exists
+    // degenerate cases against the kept face, F:199-206
+    int e = 0;
+    if (pk.mk < 1.0e-8) e = EXIT_LOOP_COLLINEAR;
+    else if (fabs(dot3(sp - w.S[0], pk.qk)) < 1.0e-8) e = EXIT_LOOP_COPLANAR;
+    return e;
+}
+
+template <int L, class HV>
+GJK_HD int walk_round(const Lanes<L> &g, const HV &A, const HV &B, Walk &w)
+{
+    Pick pk;
+    const int e = walk_test<L>(g, w, pk, true);
+    if (e) return e;
+    return walk_step<L>(g, A, B, w, pk, true);
 }
 
 // The whole GJKEPA flag path for one pair.  S: 4 rows, final simplex on return (row 3 zero on the

@@ -7,6 +7,7 @@
 // There is no CPU compute path: without a usable device every entry point fails.
 #include "../../include/gjkepa.h"
 #include "gjk_kernels.cuh"
+#include "gjk_two_stage.cuh"
 #include "epa_kernel.cuh"
 
 #include <cuda_runtime.h>
@@ -26,6 +27,9 @@ struct gjkepa_ctx {
     int lanes = 0;                 // 0 = automatic (tile kernel + 4-lane kernel for large hulls)
     int max_hull_hint = 0;         // caller's bound on vertices per hull (0 = unknown)
     int tile_ctas_per_sm = 2;      // persistent grid of the tile kernel
+    int walk_refill = 8;           // K1w re-packs a warp when this many lanes are idle
+    bool single_kernel = false;    // monolithic tile kernel instead of K1i + K1w
+    double *d_seed_f64 = nullptr; int32_t *d_seed_pair = nullptr; uint32_t *d_seed_fl = nullptr; int64_t *d_seed_off = nullptr; int64_t cap_seed = 0;
     int32_t *d_ovf = nullptr; int64_t cap_ovf = 0;
     int32_t *d_ovf2 = nullptr; int64_t cap_ovf2 = 0;
     // workspace (device)
@@ -113,6 +117,10 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_ovf) cudaFree(ctx->d_ovf);
     if (ctx->d_ovf2) cudaFree(ctx->d_ovf2);
+    if (ctx->d_seed_f64) cudaFree(ctx->d_seed_f64);
+    if (ctx->d_seed_pair) cudaFree(ctx->d_seed_pair);
+    if (ctx->d_seed_fl) cudaFree(ctx->d_seed_fl);
+    if (ctx->d_seed_off) cudaFree(ctx->d_seed_off);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -157,6 +165,18 @@ int gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n)
     if (!ctx || n < 0) return GJKEPA_ERR_ARG;
     ctx->max_hull_hint = n;
     return GJKEPA_OK;
+}
+
+int gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (key == GJKEPA_TUNE_WALK_REFILL) {
+        if (value < 1 || value > 32) return GJKEPA_ERR_ARG;
+        ctx->walk_refill = value;
+        return GJKEPA_OK;
+    }
+    if (key == GJKEPA_TUNE_SINGLE_KERNEL) { ctx->single_kernel = value != 0; return GJKEPA_OK; }
+    return GJKEPA_ERR_ARG;
 }
 
 int gjkepa_set_profiling(gjkepa_ctx *ctx, int32_t on)
@@ -262,7 +282,53 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     a.wl_simplex = want_list ? ctx->d_wl_simplex : nullptr;
     a.wl_count = ctx->d_counters;
     if (prof) CU(cudaEventRecord(ctx->ev[2], st));
-    if (use_tile) {
+    if (use_tile && !ctx->single_kernel) {
+        // K1i + K1w: one thread per pair, init in lockstep, walk with iteration compaction (gjk_two_stage.cuh)
+        const int cap_vertices = ctx->max_hull_hint > 0 ? (ctx->max_hull_hint < 16 ? ctx->max_hull_hint : 16) : 16;
+        gjk::TwoStageArgs ta;
+        ta.b = a;
+        ta.col_units = 2 * 3 * ((cap_vertices + 1) / 2);
+        ta.refill = ctx->walk_refill;
+        if (n_pairs > ctx->cap_seed) {
+            if (ctx->d_seed_f64) cudaFree(ctx->d_seed_f64);
+            if (ctx->d_seed_pair) cudaFree(ctx->d_seed_pair);
+            if (ctx->d_seed_fl) cudaFree(ctx->d_seed_fl);
+            if (ctx->d_seed_off) cudaFree(ctx->d_seed_off);
+            ctx->d_seed_f64 = nullptr; ctx->d_seed_pair = nullptr; ctx->d_seed_fl = nullptr; ctx->d_seed_off = nullptr; ctx->cap_seed = 0;
+            const int64_t ncap = ((n_pairs + n_pairs / 8 + 1024) + 31) & ~(int64_t)31;
+            cudaError_t e = cudaMalloc((void **)&ctx->d_seed_f64, (size_t)ncap * gjk::SEED_F64 * sizeof(double));
+            if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_pair, (size_t)ncap * sizeof(int32_t));
+            if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_fl, (size_t)ncap * sizeof(uint32_t));
+            if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_off, (size_t)ncap * 2 * sizeof(int64_t));
+            if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc seed queue", e);
+            ctx->cap_seed = ncap;
+        }
+        ta.q.f64 = ctx->d_seed_f64; ta.q.pair = ctx->d_seed_pair; ta.q.fln = ctx->d_seed_fl;
+        ta.q.oa = ctx->d_seed_off; ta.q.ob = ctx->d_seed_off + ctx->cap_seed;
+        ta.q.count = ctx->d_counters + 6; ta.q.head = ctx->d_counters + 7; ta.q.cap = ctx->cap_seed;
+        const size_t smem = (size_t)ta.col_units * gjk::T2_PITCH * (gjk::TILE / 32);
+        const int64_t n_ctas = (n_pairs + gjk::TILE - 1) / gjk::TILE;
+        int per_sm = 0;
+        if (fuse) {
+            CU(cudaFuncSetAttribute(gjk::gjk_init_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_kernel<true>, gjk::TILE, smem));
+            const int64_t res = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+            gjk::gjk_init_kernel<true><<<(unsigned)(n_ctas < res ? n_ctas : res), gjk::TILE, smem, st>>>(ta);
+        } else {
+            CU(cudaFuncSetAttribute(gjk::gjk_init_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_kernel<false>, gjk::TILE, smem));
+            const int64_t res = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+            gjk::gjk_init_kernel<false><<<(unsigned)(n_ctas < res ? n_ctas : res), gjk::TILE, smem, st>>>(ta);
+        }
+        ++ctx->launches;
+        CU(cudaFuncSetAttribute(gjk::gjk_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_walk_kernel, gjk::TILE, smem));
+        {
+            const int64_t res = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+            gjk::gjk_walk_kernel<<<(unsigned)(n_ctas < res ? n_ctas : res), gjk::TILE, smem, st>>>(ta);
+        }
+        ++ctx->launches;
+    } else if (use_tile) {
         // K1a: one thread per pair over shared-memory columns; pairs that do not fit overflow to K1b
         const int cap_vertices = ctx->max_hull_hint > 0 ? (ctx->max_hull_hint < 16 ? ctx->max_hull_hint : 16) : 16;
         a.col_doubles = 3 * 2 * cap_vertices;
@@ -284,6 +350,8 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
             gjk::gjk_tile_kernel<false><<<(unsigned)blocks, gjk::TILE, smem, st>>>(a);
         }
         ++ctx->launches;
+    }
+    if (use_tile) {
         // K1c: hulls too large for a column -> 4-lane sub-warps over TMA-staged slots; K1b: anything larger still
         const int hint = ctx->max_hull_hint;
         if (hint == 0 || hint > 16) {

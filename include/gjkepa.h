@@ -82,6 +82,12 @@ int  gjkepa_kernel_ms(gjkepa_ctx *ctx, double *ms /*[3]*/);
  * columns and lets the large-hull pass be skipped. */
 int  gjkepa_set_lanes(gjkepa_ctx *ctx, int32_t lanes);
 int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
+/* further knobs, by key.  WALK_REFILL: the walk kernel re-packs a warp with new pairs when this many of
+ * its 32 lanes are idle (1..32, default 8).  SINGLE_KERNEL: 1 = run the flag path as one kernel per tile
+ * (no iteration compaction; kept for A/B measurements), 0 = init kernel + compacting walk kernel (default). */
+#define GJKEPA_TUNE_WALK_REFILL    1
+#define GJKEPA_TUNE_SINGLE_KERNEL  2
+int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);
 
 /* ---- replaces CALL GJKEPA(...) (F:39-52): one pair, every scalar by reference, HOST arrays ----
  * Uses a process-wide default context on device 0 (created on first call). */

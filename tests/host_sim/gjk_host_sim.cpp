@@ -1,6 +1,7 @@
 // Host build of the product's GJK core (L = 1 lane instantiation of csrc/gjk_core.cuh) so that the
 // logic shared with the CUDA kernels can be compared against the oracle on a machine with no GPU.
 // Test-only: the shipped library never runs this path.
+#define GJK_SHADOW_HISTORY 1
 #include "../../collision_detect_gjk_epa_b200/csrc/gjk_core.cuh"
 #include <cstring>
 
@@ -39,5 +40,13 @@ extern "C" int hostsim_stall(const double *last1, const double *last2, int have2
     const int d1 = 6 - a1 - b1 - c1;
     int a, b, c; face_rows(k, a, b, c);
     Vec3 sp = v3(sp_[0], sp_[1], sp_[2]);
-    return stall_test(p[0], p[1], p[2], p[3], p[a], p[b], p[c], sp, l2[d1], k1, have2 != 0) ? 1 : 0;
+    (void)a; (void)b; (void)c;
+    return stall_test(p[0], p[1], p[2], p[3], k, sp, l2[d1], k1, have2 != 0) ? 1 : 0;
+}
+
+// walk iterations whose history bookkeeping was checked against explicit simplex_last_1/_2 arrays, and how
+// many disagreed (must be 0)
+extern "C" void hostsim_shadow_counts(long long *checks, long long *mismatch)
+{
+    *checks = gjk::g_shadow_checks; *mismatch = gjk::g_shadow_mismatch;
 }

@@ -12,11 +12,23 @@ DEPTH_RTOL = 1e-9
 NORMAL_TOL = 1e-9
 
 
-def check_against_oracle(orc, eng, b, mode, lanes=(0, 1, 2, 4), version=1, tol_ff=1.0):
+def configure(eng, variant):
+    """Kernel variants that must all give the same bits: 0 = automatic (init kernel + compacting walk kernel,
+    re-pack threshold 8), "r1"/"r32" = other re-pack thresholds, "mono" = one kernel per tile, 1/2/4 = sub-warp
+    kernels with that many lanes per pair."""
+    eng.set_tuning(eng.TUNE_SINGLE_KERNEL, 1 if variant == "mono" else 0)
+    eng.set_tuning(eng.TUNE_WALK_REFILL, int(variant[1:]) if isinstance(variant, str) and variant[0] == "r" else 8)
+    eng.set_lanes(variant if isinstance(variant, int) else 0)
+
+
+ALL_VARIANTS = (0, "r1", "r32", "mono", 1, 2, 4)
+
+
+def check_against_oracle(orc, eng, b, mode, lanes=ALL_VARIANTS, version=1, tol_ff=1.0):
     omode = {"gjk": orc.MODE_GJK, "epa": orc.MODE_EPA, "full": orc.MODE_FULL}[mode]
     ref = orc.batch(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=omode, version=version, tol_ff=tol_ff)
     for L in lanes:
-        eng.set_lanes(L)
+        configure(eng, L)
         got = eng.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=mode, version=version, tol_ff=tol_ff)
         assert np.array_equal(got["collision"], ref["collision"]), f"flags differ (lanes={L})"
         assert np.array_equal(got["status"] & 0xffff, ref["status"] & 0xffff), f"GJK exit path/iterations differ (lanes={L})"
@@ -101,7 +113,7 @@ def test_cfg4_mixed_sizes_and_deep_penetration(W, orc, engine):
 
 def test_cfg5_shared_hull_store(W, orc, engine):
     b = W.make_shared_store(50000, 200000, n_vert=16)
-    ref = check_against_oracle(orc, engine, b, "epa", lanes=(0, 4))
+    ref = check_against_oracle(orc, engine, b, "epa", lanes=(0, "r1", "mono", 4))
     assert 0.02 < ref["collision"].mean() < 0.98
 
 
@@ -121,8 +133,8 @@ def test_tolff_threshold_is_honoured(W, orc, engine):
 
 def test_golden_fixture(W, golden, engine):
     g = golden
-    for L in (0, 1, 2, 4):
-        engine.set_lanes(L)
+    for L in ALL_VARIANTS:
+        configure(engine, L)
         got = engine.batch_host(g["verts"], g["hull_off"], g["pair_a"], g["pair_b"], mode="epa")
         assert np.array_equal(got["collision"], g["collision"])
         assert np.array_equal(got["status"] & 0xff, g["exit_path"])
@@ -172,7 +184,7 @@ def test_full_size_properties_1m_pairs(W, orc, engine):
     determinism across runs and lane widths, zeroed outputs for misses, unit normals, and
     'translate p2 by (depth +- margin) * normal' separates / keeps the contact."""
     b = W.make_pairs("hull", 1_000_000, 0.85, n_vert=32)
-    engine.set_lanes(0)
+    configure(engine, 0)
     r4 = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="epa")
     engine.set_lanes(1)
     r1 = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="epa")
@@ -205,7 +217,7 @@ def test_max_hull_hint_and_overflow_to_subwarp_kernel(W, orc, engine):
     """lanes=0 (automatic): hulls up to 16 vertices run one thread per pair over shared-memory columns,
     larger ones overflow to the 4-lane kernel; a caller-supplied bound shrinks the columns.  Results
     must not depend on any of that."""
-    engine.set_lanes(0)
+    configure(engine, 0)
     b = W.make_mixed(40000, 0.4, seed=21, n_lo=4, n_hi=40)           # both paths in one batch
     ref = orc.batch(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=orc.MODE_EPA)
     for hint in (0, 40, 64):
@@ -221,3 +233,25 @@ def test_max_hull_hint_and_overflow_to_subwarp_kernel(W, orc, engine):
         assert np.array_equal(got["collision"], ref8["collision"])
         assert np.array_equal(got["status"] & 0xffff, ref8["status"] & 0xffff)
     engine.set_max_hull_vertices(0)
+
+
+def test_full_size_cfg2_kernel_variants_agree(W, orc, engine):
+    """BASELINE.json configs[1] at full size (1M box pairs, flags only): the compacting two-stage path, every
+    re-pack threshold, the single-kernel form and the 4-lane sub-warp kernel give identical flags and status
+    words; a bounded sample is checked against the oracle."""
+    b = W.make_pairs("box8", 1_000_000, 1.0)
+    engine.set_max_hull_vertices(8)
+    outs = {}
+    for v in (0, "r1", "r4", "r16", "r32", "mono", 4):
+        configure(engine, v)
+        outs[v] = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="gjk", want_contacts=True)
+    engine.set_max_hull_vertices(0)
+    configure(engine, 0)
+    for v, o in outs.items():
+        assert np.array_equal(o["collision"], outs[0]["collision"]), v
+        assert np.array_equal(o["status"], outs[0]["status"]), v
+        assert o["n_contacts"] == int(outs[0]["collision"].sum())
+    sel = np.random.default_rng(1).choice(b.n_pairs, 50000, replace=False).astype(np.int64)
+    ref = orc.batch(b.verts, b.hull_off, b.pair_a[sel], b.pair_b[sel], mode=orc.MODE_GJK)
+    assert np.array_equal(ref["collision"], outs[0]["collision"][sel])
+    assert np.array_equal(ref["status"] & 0xffff, outs[0]["status"][sel] & 0xffff)

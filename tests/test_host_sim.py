@@ -87,3 +87,14 @@ def test_stall_test_equals_the_reference_form(host_sim):
         assert bool(got) == want, (trial, k1, k, have2)
         n_true += want
     assert n_true > 200                                                  # the constructed cases do reach the exit
+
+
+def test_walk_history_bookkeeping_matches_explicit_arrays(W, host_sim):
+    """Every walk iteration of real workloads: simplex_last_2 rebuilt from (dropped vertex, kept face) equals the
+    explicitly kept array bit for bit, and the two-level stall test equals the reference's four-row form."""
+    for b in (W.make_pairs("box8", 50000, 1.0, seed=11), W.make_pairs("hull", 20000, 0.85, seed=12, n_vert=32),
+              W.make_mixed(10000, 0.25, seed=13), W.make_pairs("hull", 20000, 0.5, seed=14, n_vert=4)):
+        run_sim(host_sim, b)
+    checks, mism = C.c_longlong(0), C.c_longlong(0)
+    host_sim.hostsim_shadow_counts(C.byref(checks), C.byref(mism))
+    assert checks.value > 200000 and mism.value == 0

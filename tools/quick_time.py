@@ -22,6 +22,8 @@ def main():
     eng = Engine(0)
     eng.set_max_hull_vertices(int(np.diff(b.hull_off).max()))
     eng.set_profiling(True)
+    eng.set_tuning(eng.TUNE_SINGLE_KERNEL, int(os.environ.get('SINGLE', '0')))
+    eng.set_tuning(eng.TUNE_WALK_REFILL, int(os.environ.get('REFILL', '8')))
     chk = int(os.environ.get("CHECK", "20000"))
     ref = orc.batch(b.verts, b.hull_off, b.pair_a[:chk], b.pair_b[:chk], mode=orc.MODE_GJK) if chk else None
     for lanes in lanes_list:

@@ -206,13 +206,26 @@ struct HullViewStrided {
 // per-hull envelope sphere, F:1175-1182 (pair independent: computed once per hull by K0)
 struct Sphere { double cx, cy, cz, r; };
 
+// centroid = sums / REAL(n), F:1175.  For n a power of two the quotient is the product with 2^-k, bit for bit
+// (both are the correctly rounded value of the same real number), which spares three IEEE divisions per hull.
+GJK_HD void centroid_div(double sx, double sy, double sz, int n, Sphere &s)
+{
+    const double dn = (double)n;
+    if ((n & (n - 1)) == 0 && n > 0) {
+        const double inv = 1.0 / dn;                 // exact
+        s.cx = mul(sx, inv); s.cy = mul(sy, inv); s.cz = mul(sz, inv);
+    } else {
+        s.cx = sx / dn; s.cy = sy / dn; s.cz = sz / dn;
+    }
+}
+
 template <class HV>
 GJK_HD Sphere hull_sphere(const HV &h)
 {
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (int i = 0; i < h.n; ++i) { Vec3 v = h.get(i); sx = add(sx, v.x); sy = add(sy, v.y); sz = add(sz, v.z); }
-    double dn = (double)h.n;
-    Sphere s; s.cx = sx / dn; s.cy = sy / dn; s.cz = sz / dn;
+    Sphere s;
+    centroid_div(sx, sy, sz, h.n, s);
     // MAXVAL(NORM2(v_i - c)): a correctly rounded sqrt is monotone, so the maximum of the norms is the
     // sqrt of the maximum squared norm, bit for bit -- one sqrt per hull instead of n
     double r2 = -1.0;

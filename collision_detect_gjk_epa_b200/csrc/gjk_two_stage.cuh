@@ -72,10 +72,21 @@ __device__ __forceinline__ void scan_minmax(const HullViewT2 &hv, Vec3 d, int, i
     }
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+__device__ __forceinline__ void cp_async16_s(unsigned smem_addr, const void *gmem_src)
 {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8_s(unsigned smem_addr, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+}
+
+// pull the 128-byte lines of [ptr, ptr + bytes) towards L2 (no register result, never waited for)
+__device__ __forceinline__ void prefetch_l2_range(const void *ptr, int bytes)
+{
+    const char *p = reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)127);
+    const char *end = reinterpret_cast<const char *>(ptr) + bytes;
+    for (; p < end; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // Every `on` lane copies its own hull block into its own column, starting at `dst` (lanes run in lockstep,
@@ -85,37 +96,57 @@ __device__ __forceinline__ void stage_own_hull(char *dst, const double *src, int
     const unsigned FULL = 0xffffffffu;
     const bool lin = ((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);   // one linear 16-byte stream
     const int t_end = on ? 3 * h : 0;
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     if (__all_sync(FULL, lin || !on)) {
-        for (int t = 0; t < tmax; ++t)
-            if (t < t_end) cp_async16(dst + t * T2_PITCH, src + 2 * t);
+#pragma unroll 4
+        for (int t = 0; t < tmax; ++t, d += T2_PITCH, src += 2)
+            if (t < t_end) cp_async16_s(d, src);
     } else {
         const int odd = n & 1;
-        for (int t = 0; t < tmax; ++t) {
+        for (int t = 0; t < tmax; ++t, d += T2_PITCH) {
             if (t < t_end) {
                 const int ax = (t >= h) + (t >= 2 * h);
                 const int u = t - ax * h;
                 const int e0 = 2 * t - ax * odd;                    // = ax*n + 2u
                 const int e1 = (2 * u + 1 < n) ? e0 + 1 : e0;       // odd n: repeat the axis' last element
-                cp_async8(reinterpret_cast<double *>(dst + t * T2_PITCH), src + e0);
-                cp_async8(reinterpret_cast<double *>(dst + t * T2_PITCH) + 1, src + e1);
+                cp_async8_s(d, src + e0);
+                cp_async8_s(d + 8, src + e1);
             }
         }
     }
 }
 
-// envelope sphere F:1175-1182 from a T2 column (the padded repeats are skipped: the centroid sum is exact-order)
+// envelope sphere F:1175-1182 from a T2 column.  The centroid sum keeps the reference order (vertex by
+// vertex, padded repeats skipped); the radius is a maximum, for which the repeats are harmless.
 __device__ __forceinline__ Sphere hull_sphere_t2(const HullViewT2 &hv)
 {
     double sx = 0.0, sy = 0.0, sz = 0.0;
-    for (int i = 0; i < hv.n; ++i) { Vec3 v = hv.get(i); sx = add(sx, v.x); sy = add(sy, v.y); sz = add(sz, v.z); }
-    const double dn = (double)hv.n;
-    Sphere s; s.cx = sx / dn; s.cy = sy / dn; s.cz = sz / dn;
+    const int ay = hv.h * T2_PITCH, az = 2 * ay;
+    const char *p = hv.col;
+    for (int u = 0; u < (hv.n >> 1); ++u, p += T2_PITCH) {
+        const double2 X = *reinterpret_cast<const double2 *>(p);
+        const double2 Y = *reinterpret_cast<const double2 *>(p + ay);
+        const double2 Z = *reinterpret_cast<const double2 *>(p + az);
+        sx = add(add(sx, X.x), X.y); sy = add(add(sy, Y.x), Y.y); sz = add(add(sz, Z.x), Z.y);
+    }
+    if (hv.n & 1) {
+        sx = add(sx, *reinterpret_cast<const double *>(p)); sy = add(sy, *reinterpret_cast<const double *>(p + ay));
+        sz = add(sz, *reinterpret_cast<const double *>(p + az));
+    }
+    Sphere s;
+    centroid_div(sx, sy, sz, hv.n, s);
     double r2 = -1.0;
-    const Vec3 c = v3(s.cx, s.cy, s.cz);
-    for (int i = 0; i < hv.n; ++i) {
-        Vec3 dd = hv.get(i) - c;
-        double t = add(add(mul(dd.x, dd.x), mul(dd.y, dd.y)), mul(dd.z, dd.z));
-        if (t > r2) r2 = t;
+    p = hv.col;
+    for (int u = 0; u < hv.h; ++u, p += T2_PITCH) {
+        const double2 X = *reinterpret_cast<const double2 *>(p);
+        const double2 Y = *reinterpret_cast<const double2 *>(p + ay);
+        const double2 Z = *reinterpret_cast<const double2 *>(p + az);
+        const double dx0 = sub(X.x, s.cx), dy0 = sub(Y.x, s.cy), dz0 = sub(Z.x, s.cz);
+        const double dx1 = sub(X.y, s.cx), dy1 = sub(Y.y, s.cy), dz1 = sub(Z.y, s.cz);
+        const double t0 = add(add(mul(dx0, dx0), mul(dy0, dy0)), mul(dz0, dz0));
+        const double t1 = add(add(mul(dx1, dx1), mul(dy1, dy1)), mul(dz1, dz1));
+        if (t0 > r2) r2 = t0;
+        if (t1 > r2) r2 = t1;
     }
     s.r = (hv.n > 0) ? sqrt(r2) : -DBL_MAX;
     return s;
@@ -169,20 +200,32 @@ __device__ __forceinline__ void push_contacts(const BatchArgs &a, bool coll, int
 #define GJK_INIT_MIN_CTAS 4
 #endif
 #ifndef GJK_WALK_MIN_CTAS
-#define GJK_WALK_MIN_CTAS 4
+#define GJK_WALK_MIN_CTAS 3
 #endif
 
 // ------------------------------------------------------------------ K1i
-struct TileMeta { int ha, hb, nA, nB; long long oa, ob; bool valid; };
-__device__ __forceinline__ TileMeta load_tile_meta(const BatchArgs &a, int64_t tile, int64_t n_tiles, int lane)
+// Index chain of one tile, loaded in two steps so that neither waits inside the tile that issues it: the
+// pair's hull numbers two tiles ahead, the hull offsets (which need the numbers) one tile ahead.
+struct TileIds  { int ha, hb; bool valid; };
+struct TileMeta {                        // raw loads only: the vertex counts are formed when the tile is worked,
+    int ha, hb; long long oa, ea, ob, eb; bool valid;           // so nothing waits for these loads in the tile that issues them
+    __device__ __forceinline__ int nA() const { return (int)(ea - oa); }
+    __device__ __forceinline__ int nB() const { return (int)(eb - ob); }
+};
+__device__ __forceinline__ TileIds load_tile_ids(const BatchArgs &a, int64_t tile, int64_t n_tiles, int lane)
 {
-    TileMeta m; m.ha = m.hb = m.nA = m.nB = 0; m.oa = m.ob = 0; m.valid = false;
+    TileIds m; m.ha = m.hb = 0;
     const int64_t p = tile * 32 + lane;
-    if (tile < n_tiles && p < a.n_pairs) {
-        m.valid = true;
-        m.ha = __ldg(a.pair_a + p); m.hb = __ldg(a.pair_b + p);
-        m.oa = __ldg(a.hull_off + m.ha); m.nA = (int)(__ldg(a.hull_off + m.ha + 1) - m.oa);
-        m.ob = __ldg(a.hull_off + m.hb); m.nB = (int)(__ldg(a.hull_off + m.hb + 1) - m.ob);
+    m.valid = tile < n_tiles && p < a.n_pairs;
+    if (m.valid) { m.ha = __ldg(a.pair_a + p); m.hb = __ldg(a.pair_b + p); }
+    return m;
+}
+__device__ __forceinline__ TileMeta load_tile_meta(const BatchArgs &a, const TileIds &id)
+{
+    TileMeta m; m.ha = id.ha; m.hb = id.hb; m.oa = m.ea = m.ob = m.eb = 0; m.valid = id.valid;
+    if (id.valid) {
+        m.oa = __ldg(a.hull_off + id.ha); m.ea = __ldg(a.hull_off + id.ha + 1);
+        m.ob = __ldg(a.hull_off + id.hb); m.eb = __ldg(a.hull_off + id.hb + 1);
     }
     return m;
 }
@@ -201,16 +244,25 @@ gjk_init_kernel(TwoStageArgs ta)
     const int64_t n_warps = (int64_t)gridDim.x * (TILE / 32);
 
     int64_t tile = (int64_t)blockIdx.x * (TILE / 32) + warp;
-    TileMeta nx = load_tile_meta(a, tile, n_tiles, lane);
+    TileMeta cur = load_tile_meta(a, load_tile_ids(a, tile, n_tiles, lane));
+    TileMeta nx = load_tile_meta(a, load_tile_ids(a, tile + n_warps, n_tiles, lane));
+    TileIds nid = load_tile_ids(a, tile + 2 * n_warps, n_tiles, lane);
     for (; tile < n_tiles; tile += n_warps) {
-        const TileMeta m = nx;
+        const TileMeta m = cur;
         const int64_t p = tile * 32 + lane;
-        const int hA = (m.nA + 1) >> 1, hB = (m.nB + 1) >> 1;
+        const int nA = m.nA(), nB = m.nB();
+        const int hA = (nA + 1) >> 1, hB = (nB + 1) >> 1;
         const bool fits = m.valid && 3 * (hA + hB) <= ta.col_units;
         const int tmaxA = __reduce_max_sync(FULL, fits ? 3 * hA : 0), tmaxB = __reduce_max_sync(FULL, fits ? 3 * hB : 0);
-        stage_own_hull(col, a.verts + 3 * m.oa, m.nA, hA, fits, tmaxA);
-        stage_own_hull(col + 3 * hA * T2_PITCH, a.verts + 3 * m.ob, m.nB, hB, fits, tmaxB);
-        nx = load_tile_meta(a, tile + n_warps, n_tiles, lane);       // the next tile's index chain overlaps this tile's work
+        stage_own_hull(col, a.verts + 3 * m.oa, nA, hA, fits, tmaxA);
+        stage_own_hull(col + 3 * hA * T2_PITCH, a.verts + 3 * m.ob, nB, hB, fits, tmaxB);
+        if (nx.valid) {                                     // next tile: hull blocks on their way to L2 while this one is worked
+            prefetch_l2_range(a.verts + 3 * nx.oa, 24 * nx.nA());
+            prefetch_l2_range(a.verts + 3 * nx.ob, 24 * nx.nB());
+        }
+        cur = nx;
+        nx = load_tile_meta(a, nid);                        // the following tiles' index chain overlaps this tile's work
+        nid = load_tile_ids(a, tile + 3 * n_warps, n_tiles, lane);
         cp_async_wait_all();
         {   // hulls too large for a column: leave to the sub-warp kernels (one atomic per warp)
             const unsigned big = __ballot_sync(FULL, m.valid && !fits);
@@ -225,8 +277,8 @@ gjk_init_kernel(TwoStageArgs ta)
         int e = -1;                                         // -1: nothing to report for this lane
         if (fits) {
             HullViewT2 A, B;
-            A.col = col; A.n = m.nA; A.h = hA;
-            B.col = col + 3 * hA * T2_PITCH; B.n = m.nB; B.h = hB;
+            A.col = col; A.n = nA; A.h = hA;
+            B.col = col + 3 * hA * T2_PITCH; B.n = nB; B.h = hB;
             Sphere sa, sb;
             if (FUSE) { sa = hull_sphere_t2(A); sb = hull_sphere_t2(B); }
             else      { sa = a.sphere[m.ha];    sb = a.sphere[m.hb]; }
@@ -252,7 +304,7 @@ gjk_init_kernel(TwoStageArgs ta)
                 f[12 * cap] = w.qk.x; f[13 * cap] = w.qk.y; f[14 * cap] = w.qk.z;
                 f[15 * cap] = w.mk;
                 ta.q.pair[s] = (int32_t)p;
-                ta.q.fln[s] = ((w.fl & WF_COLD) ? SEED_COLD : 0u) | ((unsigned)m.nA << 4) | ((unsigned)m.nB << 18);
+                ta.q.fln[s] = ((w.fl & WF_COLD) ? SEED_COLD : 0u) | ((unsigned)nA << 4) | ((unsigned)nB << 18);
                 ta.q.oa[s] = m.oa; ta.q.ob[s] = m.ob;
             }
         }
@@ -276,44 +328,59 @@ gjk_walk_kernel(TwoStageArgs ta)
     HullViewT2 A, B;
     A.col = col; A.n = 0; A.h = 0; B = A;
     int64_t p = 0;
-    bool active = false, exhausted = false;
+    bool active = false;
     w.S[0] = w.S[1] = w.S[2] = w.S[3] = v3(0.0, 0.0, 0.0);
     w.qk = w.D1 = v3(0.0, 0.0, 0.0); w.mk = 0.0; w.k1 = 2; w.iters = 0; w.n_support = 0; w.fl = 0u;
-    // the warp draws seeds from the queue 32 at a time; lane i keeps the small fields of entry bbase + i
-    unsigned long long bbase = 0; int bcount = 0, bcur = 0;
-    int m_p = 0; unsigned m_fln = 0; long long m_oa = 0, m_ob = 0;
+    // The warp draws seeds from the queue 32 at a time; lane i keeps the small fields of entry base + i.  Two
+    // batches are held: `cur` is being handed out, `nxt` was fetched one batch earlier and its hull blocks and
+    // seed records have been prefetched to L2, so a re-pack waits for L2, not for HBM behind two index loads.
+    struct Batch { unsigned long long base; int n; int p; unsigned fln; long long oa, ob; };
+    auto fetch = [&](Batch &bt) {
+        if (lane == 0) bt.base = atomicAdd(ta.q.head, 32ull);
+        bt.base = __shfl_sync(FULL, bt.base, 0);
+        bt.n = bt.base < count ? (int)((count - bt.base) < 32ull ? (count - bt.base) : 32ull) : 0;
+        bt.p = 0; bt.fln = 0u; bt.oa = 0; bt.ob = 0;
+        if (lane < bt.n) {
+            bt.p = ta.q.pair[bt.base + lane]; bt.fln = ta.q.fln[bt.base + lane];
+            bt.oa = ta.q.oa[bt.base + lane];  bt.ob = ta.q.ob[bt.base + lane];
+        }
+    };
+    auto prefetch = [&](const Batch &bt) {
+        if (lane < bt.n) {
+            prefetch_l2_range(a.verts + 3 * bt.oa, 24 * (int)((bt.fln >> 4) & 0x3fffu));
+            prefetch_l2_range(a.verts + 3 * bt.ob, 24 * (int)(bt.fln >> 18));
+        }
+        if (bt.n > 0)                                               // seed records: 16 fields x 256 bytes, one line per lane
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ta.q.f64 + (size_t)(lane >> 1) * cap + bt.base + (lane & 1) * 16));
+    };
+    Batch cur, nxt;
+    fetch(cur); prefetch(cur);
+    fetch(nxt);
+    bool nxt_pf = false;
+    int bcur = 0;
 
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, !active);
         const int n_idle = __popc(idle);
-        if (n_idle >= ta.refill && !(exhausted && bcur >= bcount)) {
-            if (bcur >= bcount) {                                   // next batch of 32 seeds
-                if (lane == 0) bbase = atomicAdd(ta.q.head, 32ull);
-                bbase = __shfl_sync(FULL, bbase, 0);
-                exhausted = bbase + 32ull >= count;
-                bcount = bbase < count ? (int)((count - bbase) < 32ull ? (count - bbase) : 32ull) : 0;
-                bcur = 0;
-                if (lane < bcount) {
-                    m_p = ta.q.pair[bbase + lane]; m_fln = ta.q.fln[bbase + lane];
-                    m_oa = ta.q.oa[bbase + lane];  m_ob = ta.q.ob[bbase + lane];
-                }
-            }
-            const int avail = bcount - bcur;
+        if (n_idle >= ta.refill && (bcur < cur.n || nxt.n > 0)) {
+            if (!nxt_pf) { prefetch(nxt); nxt_pf = true; }
+            if (bcur >= cur.n) { cur = nxt; bcur = 0; fetch(nxt); nxt_pf = false; }
+            const int avail = cur.n - bcur;
             if (avail > 0) {
                 const int n_take = n_idle < avail ? n_idle : avail;
                 const int rank = __popc(idle & lt);
                 const bool take = !active && rank < n_take;
                 const int src = (bcur + rank) & 31;
-                const int sp_ = __shfl_sync(FULL, m_p, src);
-                const unsigned sfln = __shfl_sync(FULL, m_fln, src);
-                const long long soa = __shfl_sync(FULL, m_oa, src), sob = __shfl_sync(FULL, m_ob, src);
+                const int sp_ = __shfl_sync(FULL, cur.p, src);
+                const unsigned sfln = __shfl_sync(FULL, cur.fln, src);
+                const long long soa = __shfl_sync(FULL, cur.oa, src), sob = __shfl_sync(FULL, cur.ob, src);
                 const int nA = take ? (int)((sfln >> 4) & 0x3fffu) : 0, nB = take ? (int)(sfln >> 18) : 0;
                 const int hA = (nA + 1) >> 1, hB = (nB + 1) >> 1;
                 const int tmaxA = __reduce_max_sync(FULL, 3 * hA), tmaxB = __reduce_max_sync(FULL, 3 * hB);
                 stage_own_hull(col, a.verts + 3 * soa, nA, hA, take, tmaxA);
                 stage_own_hull(col + 3 * hA * T2_PITCH, a.verts + 3 * sob, nB, hB, take, tmaxB);
                 if (take) {
-                    const double *f = ta.q.f64 + (bbase + (unsigned long long)(bcur + rank));
+                    const double *f = ta.q.f64 + (cur.base + (unsigned long long)(bcur + rank));
 #pragma unroll
                     for (int r = 0; r < 4; ++r) w.S[r] = v3(f[(3 * r) * cap], f[(3 * r + 1) * cap], f[(3 * r + 2) * cap]);
                     w.qk = v3(f[12 * cap], f[13 * cap], f[14 * cap]);
@@ -330,7 +397,7 @@ gjk_walk_kernel(TwoStageArgs ta)
             }
         }
         if (!__any_sync(FULL, active)) {
-            if (exhausted && bcur >= bcount) break;
+            if (bcur >= cur.n && nxt.n == 0) break;
             continue;
         }
         // one round on every lane, finished or not: nothing is skipped, so no branch merges two walk states

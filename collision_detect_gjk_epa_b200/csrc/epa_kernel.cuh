@@ -53,6 +53,8 @@ struct EpaArgs {
     int32_t *ovf_items; unsigned long long *ovf_count;
     int32_t version; double tol_ff; bool full;
     int32_t *colli_type; double *nearest, *normal, *point, *depth; uint32_t *status;
+    double *result;                 // optional: normal xyz, depth (-1: no result) in the first 4 doubles of the entry's 12-double
+                                    // work-list slot (dead once the pair is retired); input of the contact kernel
 };
 
 template <int VC, int FC>
@@ -452,6 +454,10 @@ epa_kernel(EpaArgs a)
                 if (A.n <= FC && B.n <= FC) contact_epilogue(a, p, A, B, nrm, lane, st, P.nx, P.ny);     // planes are dead now
                 else st |= ST_HULL_FAIL;                                                            // hulls beyond the scratch: epilogue skipped
             }
+        }
+        if (lane == 0 && a.result) {
+            double *r = a.result + 12 * item;
+            r[0] = nrm.x; r[1] = nrm.y; r[2] = nrm.z; r[3] = ok ? depth : -1.0;
         }
         if (lane == 0 && a.status) a.status[p] |= st;
     }

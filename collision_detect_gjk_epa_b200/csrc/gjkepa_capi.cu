@@ -9,6 +9,8 @@
 #include "gjk_kernels.cuh"
 #include "gjk_two_stage.cuh"
 #include "epa_kernel.cuh"
+#include "epa_v3.cuh"
+#include "contact_kernel.cuh"
 
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -29,6 +31,7 @@ struct gjkepa_ctx {
     int tile_ctas_per_sm = 2;      // persistent grid of the tile kernel
     int walk_refill = 8;           // K1w re-packs a warp when this many lanes are idle
     bool single_kernel = false;    // monolithic tile kernel instead of K1i + K1w
+    bool epa_general = false;      // general EPA kernel only (no linked-mesh fast path)
     double *d_seed_f64 = nullptr; int32_t *d_seed_pair = nullptr; uint32_t *d_seed_fl = nullptr; int64_t *d_seed_off = nullptr; int64_t cap_seed = 0;
     int32_t *d_ovf = nullptr; int64_t cap_ovf = 0;
     int32_t *d_ovf2 = nullptr; int64_t cap_ovf2 = 0;
@@ -84,7 +87,7 @@ int gjkepa_create(gjkepa_ctx **out, int32_t device)
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_counters, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&ctx->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
@@ -176,6 +179,7 @@ int gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value)
         return GJKEPA_OK;
     }
     if (key == GJKEPA_TUNE_SINGLE_KERNEL) { ctx->single_kernel = value != 0; return GJKEPA_OK; }
+    if (key == GJKEPA_TUNE_EPA_GENERAL) { ctx->epa_general = value != 0; return GJKEPA_OK; }
     return GJKEPA_ERR_ARG;
 }
 
@@ -232,7 +236,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         if (point)      CU(cudaMemsetAsync(point, 0, (size_t)n_pairs * 3 * sizeof(double), st));
         if (depth)      CU(cudaMemsetAsync(depth, 0, (size_t)n_pairs * sizeof(double), st));
     }
-    CU(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
     if (n_pairs == 0) {
         if (n_contacts) CU(cudaMemsetAsync(n_contacts, 0, sizeof(int64_t), st));
         return GJKEPA_OK;
@@ -258,7 +262,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     }
     const bool use_tile = ctx->lanes == 0;
     if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf, ctx->cap_ovf, n_pairs); if (rc) return rc; }
-    if (use_tile) { rc = ensure(ctx, ctx->d_ovf2, ctx->cap_ovf2, n_pairs); if (rc) return rc; }
+    if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf2, ctx->cap_ovf2, n_pairs); if (rc) return rc; }
 
     ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = false;
     const bool prof = ctx->profiling;
@@ -410,11 +414,16 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         e.wl_count = ctx->d_counters; e.queue_head = ctx->d_counters + 1;
         e.version = version; e.tol_ff = tol_ff; e.full = (mode == GJKEPA_MODE_FULL);
         e.colli_type = colli_type; e.nearest = nearest; e.normal = normal; e.point = point;
-        e.depth = depth; e.status = status;
+        e.depth = depth; e.status = status; e.result = nullptr;
+        const bool k4 = !ctx->epa_general && mode == GJKEPA_MODE_FULL;     // contact epilogue as its own kernel
+        if (k4) { e.full = false; e.result = ctx->d_wl_simplex; }
         int nl = 0;
         if (prof) CU(cudaEventRecord(ctx->ev[4], st));
-        rc = epa::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_counters, &nl);
+        if (ctx->epa_general) rc = epa::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_counters, &nl);
+        else                  rc = epa3::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_ovf2, ctx->d_counters,
+                                                ctx->max_hull_hint > 0 && ctx->max_hull_hint <= 32, &nl);
         if (rc) return fail(ctx, GJKEPA_ERR_CUDA, "epa launch", (cudaError_t)rc);
+        if (k4) { contact::launch(e, ctx->sm_count, st); ++nl; }
         if (prof) { CU(cudaEventRecord(ctx->ev[5], st)); ctx->ev_valid[2] = true; }
         ctx->launches += nl;
         CU(cudaGetLastError());

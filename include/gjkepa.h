@@ -84,9 +84,12 @@ int  gjkepa_set_lanes(gjkepa_ctx *ctx, int32_t lanes);
 int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
 /* further knobs, by key.  WALK_REFILL: the walk kernel re-packs a warp with new pairs when this many of
  * its 32 lanes are idle (1..32, default 8).  SINGLE_KERNEL: 1 = run the flag path as one kernel per tile
- * (no iteration compaction; kept for A/B measurements), 0 = init kernel + compacting walk kernel (default). */
+ * (no iteration compaction; kept for A/B measurements), 0 = init kernel + compacting walk kernel (default).
+ * EPA_GENERAL: 1 = every colliding pair through the general EPA kernel (in-place face list), 0 = the linked-
+ * mesh kernels first, the general kernel for what they decline (default). */
 #define GJKEPA_TUNE_WALK_REFILL    1
 #define GJKEPA_TUNE_SINGLE_KERNEL  2
+#define GJKEPA_TUNE_EPA_GENERAL    3
 int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);
 
 /* ---- replaces CALL GJKEPA(...) (F:39-52): one pair, every scalar by reference, HOST arrays ----

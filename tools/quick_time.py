@@ -17,6 +17,7 @@ def main():
     elif wl == "hull16": b = W.make_pairs("hull", n, 0.85, n_vert=16)
     elif wl == "cfg5": b = W.make_shared_store(n // 10, n, n_vert=16)
     elif wl == "cfg4": b = W.make_mixed(n, 0.25)
+    elif wl == "cfg4deep": b = W.make_pairs("hull", n, 0.05, n_vert=64)
     dev = torch.device("cuda:0")
     t = [torch.from_numpy(x).to(dev) for x in (b.verts, b.hull_off, b.pair_a, b.pair_b)]
     eng = Engine(0)
@@ -24,6 +25,7 @@ def main():
     eng.set_profiling(True)
     eng.set_tuning(eng.TUNE_SINGLE_KERNEL, int(os.environ.get('SINGLE', '0')))
     eng.set_tuning(eng.TUNE_WALK_REFILL, int(os.environ.get('REFILL', '8')))
+    eng.set_tuning(eng.TUNE_EPA_GENERAL, int(os.environ.get('EPAGEN', '0')))
     chk = int(os.environ.get("CHECK", "20000"))
     ref = orc.batch(b.verts, b.hull_off, b.pair_a[:chk], b.pair_b[:chk], mode=orc.MODE_GJK) if chk else None
     for lanes in lanes_list:

@@ -247,6 +247,7 @@ GJK_HD bool sphere_hit(const Sphere &a, const Sphere &b)
 template <int L> struct Lanes;
 
 template <> struct Lanes<1> {
+    static constexpr int LANES = 1;
     int lane;
     unsigned mask;
     GJK_HD Lanes() : lane(0), mask(0u) {}
@@ -260,6 +261,7 @@ template <> struct Lanes<1> {
 
 #if defined(__CUDACC__)
 template <int L> struct Lanes {
+    static constexpr int LANES = L;
     int lane;            // lane within the group
     unsigned mask;       // warp mask of the group's lanes
     __device__ __forceinline__ Lanes()
@@ -294,6 +296,40 @@ template <int L> struct Lanes {
         }
     }
 };
+
+// The same interface for a warp whose 32/L groups execute the SAME instructions (each on its own pair, bodies
+// predicated): every collective takes the constant full mask, which spares the member-mask check nvcc wraps
+// around each shuffle / vote with a run-time mask, and must be reached by the whole warp.
+template <int L> struct LanesW {
+    static constexpr int LANES = L;
+    int lane, shift;
+    __device__ __forceinline__ LanesW() { const int wl = threadIdx.x & 31; lane = wl & (L - 1); shift = wl & ~(L - 1); }
+    __device__ __forceinline__ double bcast(double v, int src) const { return __shfl_sync(0xffffffffu, v, src, L); }
+    __device__ __forceinline__ int bcast_i(int v, int src) const { return __shfl_sync(0xffffffffu, v, src, L); }
+    __device__ __forceinline__ unsigned bits(bool p) const { return (__ballot_sync(0xffffffffu, p) >> shift) & ((1u << L) - 1u); }
+    __device__ __forceinline__ bool all(bool p) const { return bits(p) == ((1u << L) - 1u); }
+    __device__ __forceinline__ bool any(bool p) const { return bits(p) != 0u; }
+    __device__ __forceinline__ void argmax_first(double &v, int &i) const
+    {
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, v, o, L);
+            int oi = __shfl_xor_sync(0xffffffffu, i, o, L);
+            bool take = (ov > v) || (ov == v && oi < i);
+            v = take ? ov : v; i = take ? oi : i;
+        }
+    }
+    __device__ __forceinline__ void argmin_first(double &v, int &i) const
+    {
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, v, o, L);
+            int oi = __shfl_xor_sync(0xffffffffu, i, o, L);
+            bool take = (ov < v) || (ov == v && oi < i);
+            v = take ? ov : v; i = take ? oi : i;
+        }
+    }
+};
 #endif
 
 // Scans of one hull by lanes lane0, lane0+step, ...: first arg-max (and first arg-min) of d.v.  Views with
@@ -316,9 +352,10 @@ GJK_HD void scan_minmax(const HV &h, Vec3 d, int lane0, int step, double &hi, in
 }
 
 // support_mapping, F:1030-1062: p1(first argmax d.p1) - p2(first argmax (-d).p2)
-template <int L, class HV>
-GJK_HD Vec3 support(const Lanes<L> &g, const HV &A, const HV &B, Vec3 d)
+template <class G, class HV>
+GJK_HD Vec3 support(const G &g, const HV &A, const HV &B, Vec3 d)
 {
+    constexpr int L = G::LANES;
     double bA, bB; int iA, iB;
     scan_argmax(A, d, g.lane, L, bA, iA);
     scan_argmax(B, neg(d), g.lane, L, bB, iB);
@@ -329,9 +366,10 @@ GJK_HD Vec3 support(const Lanes<L> &g, const HV &A, const HV &B, Vec3 d)
 
 // supports along +d and -d from one pass (F:97 and F:103): dot(-d,v) == -dot(d,v) bit for bit, so
 // the first arg-max of dot(-d,.) is the first arg-min of dot(d,.).
-template <int L, class HV>
-GJK_HD void support_both(const Lanes<L> &g, const HV &A, const HV &B, Vec3 d, Vec3 &sp, Vec3 &sm)
+template <class G, class HV>
+GJK_HD void support_both(const G &g, const HV &A, const HV &B, Vec3 d, Vec3 &sp, Vec3 &sm)
 {
+    constexpr int L = G::LANES;
     double hiA, loA, hiB, loB; int ihA, ilA, ihB, ilB;
     scan_minmax(A, d, g.lane, L, hiA, ihA, loA, ilA);
     scan_minmax(B, d, g.lane, L, hiB, ihB, loB, ilB);
@@ -384,24 +422,6 @@ GJK_HD bool faces_from_cross_impl(const Vec3 *cr, Faces<L> &F)
         F.q[j] = (F.md[j] < 1.0e-12) ? v3(0.0, 0.0, 0.0) : q;       // UTZVEC, F:1349-1350
     }
     return ok;
-}
-
-// Unflipped unit normals of the four faces.  SKIP = 2 (L = 1 only): face (1,2,3) of the new simplex is
-// the face the walk just kept, whose cross product has the very same operands, so the caller has
-// already put its normal and norm in slot 2 and it is not recomputed.
-template <int L, int SKIP = -1>
-GJK_HD bool compute_faces(const Lanes<L> &g, const Vec3 *S, Faces<L> &F)
-{
-    Vec3 cr[Faces<L>::FPL];
-#pragma unroll
-    for (int j = 0; j < Faces<L>::FPL; ++j) if (j != SKIP) {
-        int f = g.lane + j * L, a, b, c;
-        face_rows(f, a, b, c);
-        Vec3 sa = pick4(S, a), sb = pick4(S, b), sc = pick4(S, c);
-        cr[j] = cross3(sa - sb, sb - sc);
-    }
-    if (!faces_from_cross_impl<L, MathFast, SKIP>(cr, F)) { faces_from_cross_impl<L, MathCold, SKIP>(cr, F); return true; }
-    return false;
 }
 
 GJK_HD Vec3 simplex_mean(const Vec3 *S)
@@ -531,8 +551,8 @@ inline void shadow_history_check(Walk &w, int k, Vec3 sp, bool have2)
 #endif
 
 // Initial tetrahedron.  Returns the exit path, or 0 with `w` ready for the first walk_round.
-template <int L, class HV>
-GJK_HD int gjk_init(const Lanes<L> &g, const HV &A, const HV &B, const Sphere &sa, const Sphere &sb, Walk &w)
+template <class G, class HV>
+GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, const Sphere &sb, Walk &w)
 {
     const Vec3 O = v3(0.0, 0.0, 0.0);
     w.S[0] = w.S[1] = w.S[2] = w.S[3] = O;
@@ -596,9 +616,10 @@ struct Pick { int k; Vec3 qk; double mk; bool flip; };
 
 // first half: face normals, containment, stall flag, iteration cap; chooses the next face.  Returns the exit
 // path or 0; the simplex is not modified.
-template <int L>
-GJK_HD int walk_test(const Lanes<L> &g, Walk &w, Pick &pk, bool live)
+template <class G>
+GJK_HD int walk_test(const G &g, Walk &w, Pick &pk, bool live)
 {
+    constexpr int L = G::LANES;
     constexpr int FPL = Faces<L>::FPL;
     const Vec3 O = v3(0.0, 0.0, 0.0);
     const bool first = (w.fl & WF_FIRST) != 0u;
@@ -655,8 +676,10 @@ GJK_HD int walk_test(const Lanes<L> &g, Walk &w, Pick &pk, bool live)
     pk.mk = g.bcast(mbest, owner);
     pk.flip = g.bcast_i(flbest ? 1 : 0, owner) != 0;
 
+    // both votes are taken unconditionally: with LanesW every lane of the warp must reach every collective
+    const bool on_band = g.any(band_hit), inside = g.all(all_pos);
     int e = 0;
-    if (g.any(band_hit) || g.all(all_pos)) e = first ? EXIT_INIT_CONTAIN : EXIT_LOOP_CONTAIN;   // F:164 / F:210
+    if (on_band || inside) e = first ? EXIT_INIT_CONTAIN : EXIT_LOOP_CONTAIN;                   // F:164 / F:210
     else if (w.fl & WF_STALL) e = EXIT_LOOP_STALL;                          // F:219-234, decided when the simplex was updated
     else if (w.iters + 1 > 50) { w.iters = 50; e = EXIT_LOOP_CAP; }         // F:186
     else ++w.iters;
@@ -664,8 +687,8 @@ GJK_HD int walk_test(const Lanes<L> &g, Walk &w, Pick &pk, bool live)
 }
 
 // second half: support along the chosen face's normal, new tetrahedron (in place), degenerate cases.
-template <int L, class HV>
-GJK_HD int walk_step(const Lanes<L> &g, const HV &A, const HV &B, Walk &w, const Pick &pk, bool live)
+template <class G, class HV>
+GJK_HD int walk_step(const G &g, const HV &A, const HV &B, Walk &w, const Pick &pk, bool live)
 {
     const int k = pk.k;
     const Vec3 sp = support(g, A, B, pk.flip ? neg(pk.qk) : pk.qk);         // F:1127
@@ -691,24 +714,24 @@ GJK_HD int walk_step(const Lanes<L> &g, const HV &A, const HV &B, Walk &w, const
     return e;
 }
 
-template <int L, class HV>
-GJK_HD int walk_round(const Lanes<L> &g, const HV &A, const HV &B, Walk &w)
+template <class G, class HV>
+GJK_HD int walk_round(const G &g, const HV &A, const HV &B, Walk &w)
 {
     Pick pk;
-    const int e = walk_test<L>(g, w, pk, true);
+    const int e = walk_test(g, w, pk, true);
     if (e) return e;
-    return walk_step<L>(g, A, B, w, pk, true);
+    return walk_step(g, A, B, w, pk, true);
 }
 
 // The whole GJKEPA flag path for one pair.  S: 4 rows, final simplex on return (row 3 zero on the
 // F:140 path, hazard H1).  All lanes of the group return the same values.
-template <int L, class HV>
-GJK_HD GjkOut gjk_pair(const Lanes<L> &g, const HV &A, const HV &B,
+template <class G, class HV>
+GJK_HD GjkOut gjk_pair(const G &g, const HV &A, const HV &B,
                        const Sphere &sa, const Sphere &sb, Vec3 *S)
 {
     Walk w;
-    int e = gjk_init<L>(g, A, B, sa, sb, w);
-    while (e == 0) e = walk_round<L>(g, A, B, w);
+    int e = gjk_init(g, A, B, sa, sb, w);
+    while (e == 0) e = walk_round(g, A, B, w);
     GjkOut o;
     o.exit_path = e; o.iters = w.iters; o.n_support = w.n_support;
     o.stop_flag = (w.fl & WF_STOP) != 0u; o.cold = (w.fl & WF_COLD) ? 1 : 0; o.band = 0;

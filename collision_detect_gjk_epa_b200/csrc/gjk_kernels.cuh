@@ -67,9 +67,10 @@ hull_prep_kernel(const double *__restrict__ verts, const int64_t *__restrict__ h
 
 // envelope sphere by a sub-warp: lane l sums axis l sequentially (the order matters), the radius is a
 // max over vertices (order-free)
-template <int L, class HV>
-__device__ __forceinline__ Sphere group_sphere(const Lanes<L> &g, const HV &h)
+template <class G, class HV>
+__device__ __forceinline__ Sphere group_sphere(const G &g, const HV &h)
 {
+    constexpr int L = G::LANES;
     double c[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
@@ -174,7 +175,7 @@ gjk_tile_kernel(BatchArgs a)
             if (FUSE) { sa = hull_sphere(A); sb = hull_sphere(B); }
             else      { sa = a.sphere[ha];   sb = a.sphere[hb]; }
             Vec3 S[4];
-            const GjkOut o = gjk_pair<1>(g, A, B, sa, sb, S);
+            const GjkOut o = gjk_pair(g, A, B, sa, sb, S);
             const bool coll = exit_is_collision(o.exit_path);
             if (a.collision) a.collision[p] = coll ? 1 : 0;
             if (a.status) a.status[p] = pack_status(o);
@@ -204,10 +205,10 @@ gjk_group_kernel(BatchArgs a)
         const HullView A = hull_view(a.verts, a.hull_off, ha);
         const HullView B = hull_view(a.verts, a.hull_off, hb);
         Sphere sa, sb;
-        if (FUSE) { sa = group_sphere<L>(g, A); sb = group_sphere<L>(g, B); }
+        if (FUSE) { sa = group_sphere(g, A); sb = group_sphere(g, B); }
         else      { sa = a.sphere[ha];          sb = a.sphere[hb]; }
         Vec3 S[4];
-        const GjkOut o = gjk_pair<L>(g, A, B, sa, sb, S);
+        const GjkOut o = gjk_pair(g, A, B, sa, sb, S);
         const bool coll = exit_is_collision(o.exit_path);
         if (g.lane == 0) {
             if (a.collision) a.collision[p] = coll ? 1 : 0;
@@ -326,10 +327,10 @@ gjk_group_staged_kernel(BatchArgs a, int slot_doubles)
             A.x = slot; A.y = slot + GA.n; A.z = slot + 2 * GA.n; A.n = GA.n;
             B.x = slot + 3 * GA.n; B.y = B.x + GB.n; B.z = B.y + GB.n; B.n = GB.n;
             Sphere sa, sb;
-            if (FUSE) { sa = group_sphere<L>(g, A); sb = group_sphere<L>(g, B); }
+            if (FUSE) { sa = group_sphere(g, A); sb = group_sphere(g, B); }
             else      { sa = a.sphere[ha];          sb = a.sphere[hb]; }
             Vec3 S[4];
-            const GjkOut o = gjk_pair<L>(g, A, B, sa, sb, S);
+            const GjkOut o = gjk_pair(g, A, B, sa, sb, S);
             const bool coll = exit_is_collision(o.exit_path);
             if (g.lane == 0) {
                 if (a.collision) a.collision[p] = coll ? 1 : 0;

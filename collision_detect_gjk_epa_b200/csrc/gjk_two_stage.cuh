@@ -282,7 +282,7 @@ gjk_init_kernel(TwoStageArgs ta)
             Sphere sa, sb;
             if (FUSE) { sa = hull_sphere_t2(A); sb = hull_sphere_t2(B); }
             else      { sa = a.sphere[m.ha];    sb = a.sphere[m.hb]; }
-            e = gjk_init<1>(g, A, B, sa, sb, w);
+            e = gjk_init(g, A, B, sa, sb, w);
             if (e > 0) {
                 if (a.collision) a.collision[p] = exit_is_collision(e) ? 1 : 0;
                 if (a.status) a.status[p] = pack_status_walk(e, w);
@@ -402,7 +402,7 @@ gjk_walk_kernel(TwoStageArgs ta)
         }
         // one round on every lane, finished or not: nothing is skipped, so no branch merges two walk states
         Pick pk;
-        const int e1 = walk_test<1>(g, w, pk, active);
+        const int e1 = walk_test(g, w, pk, active);
         const bool coll = active && e1 != 0 && exit_is_collision(e1);
         if (coll) {                                                 // park the tetrahedron in this lane's (now dead) column
             double2 *d = reinterpret_cast<double2 *>(col);
@@ -411,7 +411,7 @@ gjk_walk_kernel(TwoStageArgs ta)
             d[4 * 32] = make_double2(w.S[2].z, w.S[3].x); d[5 * 32] = make_double2(w.S[3].y, w.S[3].z);
         }
         const int iters_out = w.iters;
-        const int e2 = walk_step<1>(g, A, B, w, pk, active && e1 == 0);
+        const int e2 = walk_step(g, A, B, w, pk, active && e1 == 0);
         const int e = e1 ? e1 : e2;
         if (active && e) {
             if (a.collision) a.collision[p] = coll ? 1 : 0;

@@ -8,6 +8,7 @@
 #include "../../include/gjkepa.h"
 #include "gjk_kernels.cuh"
 #include "gjk_two_stage.cuh"
+#include "gjk_two_stage_group.cuh"
 #include "epa_kernel.cuh"
 #include "epa_v3.cuh"
 #include "contact_kernel.cuh"
@@ -15,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -58,6 +60,11 @@ int fail(gjkepa_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
     }
     return code;
 }
+
+// developer aid: GJKEPA_DEBUG_SYNC=1 in the environment synchronises after every kernel and names the one that failed
+static bool debug_sync_enabled() { static const bool on = [] { const char *e = getenv("GJKEPA_DEBUG_SYNC"); return e && e[0] == '1'; }(); return on; }
+#define DBG_SYNC(name) do { if (debug_sync_enabled()) { cudaError_t e_ = cudaStreamSynchronize(st); if (e_ == cudaSuccess) e_ = cudaGetLastError(); \
+    if (e_ != cudaSuccess) { fprintf(stderr, "gjkepa: kernel %s failed: %s\n", name, cudaGetErrorString(e_)); return fail(ctx, GJKEPA_ERR_CUDA, name, e_); } } } while (0)
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, GJKEPA_ERR_CUDA, #call, e_); } while (0)
 
@@ -329,7 +336,9 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_walk_kernel, gjk::TILE, smem));
         {
             const int64_t res = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+            DBG_SYNC("gjk_init_kernel");
             gjk::gjk_walk_kernel<<<(unsigned)(n_ctas < res ? n_ctas : res), gjk::TILE, smem, st>>>(ta);
+            DBG_SYNC("gjk_walk_kernel");
         }
         ++ctx->launches;
     } else if (use_tile) {
@@ -366,16 +375,41 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
             b.pair_list = ctx->d_ovf; b.pair_list_count = ctx->d_counters + 2;
             b.ovf_list = ctx->d_ovf2; b.ovf_count = ctx->d_counters + 5;
             int per_sm = 1;
-            if (fuse) {
-                CU(cudaFuncSetAttribute(gjk::gjk_group_staged_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_group_staged_kernel<4, true>, 128, smem_c));
-                gjk::gjk_group_staged_kernel<4, true><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(b, slot_doubles);
+            if (ctx->single_kernel) {
+                if (fuse) {
+                    CU(cudaFuncSetAttribute(gjk::gjk_group_staged_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_group_staged_kernel<4, true>, 128, smem_c));
+                    gjk::gjk_group_staged_kernel<4, true><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(b, slot_doubles);
+                } else {
+                    CU(cudaFuncSetAttribute(gjk::gjk_group_staged_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_group_staged_kernel<4, false>, 128, smem_c));
+                    gjk::gjk_group_staged_kernel<4, false><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(b, slot_doubles);
+                }
+                ++ctx->launches;
             } else {
-                CU(cudaFuncSetAttribute(gjk::gjk_group_staged_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_group_staged_kernel<4, false>, 128, smem_c));
-                gjk::gjk_group_staged_kernel<4, false><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(b, slot_doubles);
+                // K1ig + K1wg: init by free-running 4-lane groups, walk by 8 groups per warp in lockstep; the seed
+                // buffers of the thread-per-pair stage are free again by now (same stream), only the counters differ
+                gjk::TwoStageArgs tg;
+                tg.b = b; tg.col_units = 0; tg.refill = ctx->walk_refill;
+                tg.q.f64 = ctx->d_seed_f64; tg.q.pair = ctx->d_seed_pair; tg.q.fln = ctx->d_seed_fl;
+                tg.q.oa = ctx->d_seed_off; tg.q.ob = ctx->d_seed_off + ctx->cap_seed;
+                tg.q.count = ctx->d_counters + 10; tg.q.head = ctx->d_counters + 11; tg.q.cap = ctx->cap_seed;
+                if (fuse) {
+                    CU(cudaFuncSetAttribute(gjk::gjk_init_group_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_group_kernel<4, true>, 128, smem_c));
+                    gjk::gjk_init_group_kernel<4, true><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(tg, slot_doubles);
+                } else {
+                    CU(cudaFuncSetAttribute(gjk::gjk_init_group_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_group_kernel<4, false>, 128, smem_c));
+                    gjk::gjk_init_group_kernel<4, false><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(tg, slot_doubles);
+                }
+                DBG_SYNC("gjk_init_group_kernel");
+                CU(cudaFuncSetAttribute(gjk::gjk_walk_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_walk_group_kernel<4>, 128, smem_c));
+                gjk::gjk_walk_group_kernel<4><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(tg, slot_doubles);
+                DBG_SYNC("gjk_walk_group_kernel");
+                ctx->launches += 2;
             }
-            ++ctx->launches;
             if (hint == 0 || hint > 64) {
                 gjk::BatchArgs c = a;
                 c.pair_list = ctx->d_ovf2; c.pair_list_count = ctx->d_counters + 5;
@@ -423,7 +457,9 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         else                  rc = epa3::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_ovf2, ctx->d_counters,
                                                 ctx->max_hull_hint > 0 && ctx->max_hull_hint <= 32, &nl);
         if (rc) return fail(ctx, GJKEPA_ERR_CUDA, "epa launch", (cudaError_t)rc);
+        DBG_SYNC("epa kernels");
         if (k4) { contact::launch(e, ctx->sm_count, st); ++nl; }
+        DBG_SYNC("contact_kernel");
         if (prof) { CU(cudaEventRecord(ctx->ev[5], st)); ctx->ev_valid[2] = true; }
         ctx->launches += nl;
         CU(cudaGetLastError());

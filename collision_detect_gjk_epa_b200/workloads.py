@@ -167,6 +167,28 @@ def unit_cubes(offset=(0.5, 0.0, 0.0)) -> PairBatch:
     return PairBatch(verts, hull_off, np.array([0], np.int32), np.array([1], np.int32), name="cubes")
 
 
+def make_touching_mix(n_pairs: int, seed: int = 77, every: int = 5, n_vert: int = 20) -> PairBatch:
+    """Random hull(n_vert) pairs with, every `every`-th pair, two axis-aligned unit cubes carrying their 12
+    edge midpoints as extra vertices (20 vertices, same hull) that touch, nearly touch or overlap along x by
+    an exact amount.  These pairs reach the reference's 1e-8 bands (on-face containment F:1248, coplanar exits
+    F:157/F:203) inside warps whose other pairs do not -- the case a lockstep kernel must survive."""
+    assert n_vert == 20
+    b = make_pairs("hull", n_pairs, 0.85, seed=seed, n_vert=n_vert)
+    rng = np.random.default_rng(seed + 1)
+    c = np.array([[sx, sy, sz] for sz in (-1, 1) for sy in (-1, 1) for sx in (-1, 1)], float)
+    mids = np.array([(c[i] + c[j]) / 2 for i in range(8) for j in range(i + 1, 8) if np.sum(c[i] != c[j]) == 1])
+    cube = 0.5 * np.concatenate([c, mids])                     # (20,3)
+    gaps = np.array([1.0, 1.0 - 5e-9, 1.0 + 5e-9, 1.0 - 1e-6, 0.75, 1.0 + 1e-6, 0.5, 1.0, 0.999999995])
+    v = b.verts.reshape(-1, 3, n_vert)
+    for i in range(0, n_pairs, every):
+        shift = rng.integers(-2, 3, size=3).astype(float)       # exact small integers: the cubes stay axis-aligned
+        perm = rng.permutation(n_vert)
+        off = np.array([gaps[(i // every) % len(gaps)], 0.25 * ((i // every) % 3), 0.125 * ((i // every) % 2)])
+        v[2 * i] = (cube[perm] + shift).T
+        v[2 * i + 1] = (cube[rng.permutation(n_vert)] + shift + off).T
+    return PairBatch(v.reshape(-1), b.hull_off, b.pair_a, b.pair_b, name="touching_mix")
+
+
 CONFIGS = {
     # name: (factory, kwargs, mode)   -- BASELINE.json configs[1..4]
     "cfg2": (make_pairs, dict(kind="box8", sigma=1.0), "gjk"),

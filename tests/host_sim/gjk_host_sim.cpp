@@ -19,7 +19,7 @@ extern "C" void hostsim_gjk_batch(const double *verts, const int64_t *hull_off, 
         Sphere sa = hull_sphere(A), sb = hull_sphere(B);
         Lanes<1> g;
         Vec3 S[4];
-        GjkOut o = gjk_pair<1>(g, A, B, sa, sb, S);
+        GjkOut o = gjk_pair(g, A, B, sa, sb, S);
         collision[i] = exit_is_collision(o.exit_path) ? 1 : 0;
         status[i] = (uint32_t)o.exit_path | ((uint32_t)o.iters << 8) | (o.stop_flag ? (1u << 25) : 0u)
                   | (o.exit_path == EXIT_TRI_ORIGIN ? (1u << 28) : 0u);

@@ -257,3 +257,32 @@ def test_full_size_cfg2_kernel_variants_agree(W, orc, engine):
     ref = orc.batch(b.verts, b.hull_off, b.pair_a[sel], b.pair_b[sel], mode=orc.MODE_GJK)
     assert np.array_equal(ref["collision"], outs[0]["collision"][sel])
     assert np.array_equal(ref["status"] & 0xffff, outs[0]["status"][sel] & 0xffff)
+
+
+def test_touching_cubes_inside_lockstep_warps(W, orc, engine):
+    """Axis-aligned touching / nearly touching bodies (the reference's 1e-8 bands: on-face containment, coplanar
+    exits, origin-on-face EPA iterations) scattered among ordinary pairs, with 20-vertex hulls so that they run in
+    the kernels that keep several pairs per warp in lockstep.  Regression: a short-circuited vote once let the
+    groups of a warp take different numbers of collectives.  Flags, exit paths and depths must match the oracle
+    everywhere; normals are compared on the ordinary pairs only (for the planted cubes several faces tie exactly,
+    and at zero depth the sign follows the face winding -- DESIGN.md, known divergences)."""
+    b = W.make_touching_mix(40000)
+    ref = orc.batch(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=orc.MODE_EPA)
+    planted = np.zeros(b.n_pairs, bool); planted[::5] = True
+    assert len(set((ref["status"][planted] & 0xff).tolist())) >= 2 and ref["collision"][planted].min() == 0
+    for hint in (20, 0):
+        engine.set_max_hull_vertices(hint)
+        for v in (0, "r1", "r32", "mono", "gen", 4):
+            configure(engine, v)
+            got = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="epa")
+            assert np.array_equal(got["collision"], ref["collision"]), (hint, v)
+            assert np.array_equal(got["status"] & 0xffff, ref["status"] & 0xffff), (hint, v)
+            hit = (ref["collision"] > 0) & ((ref["status"] >> 24) == 0)
+            assert np.all((got["status"][hit] >> 24) == 0), (hint, v)
+            assert np.all(np.abs(got["depth"][hit] - ref["depth"][hit]) <= DEPTH_RTOL * np.maximum(ref["depth"][hit], 1.0)), (hint, v)
+            m = hit & ~planted
+            assert np.all(1.0 - np.sum(got["normal"][m] * ref["normal"][m], axis=1) <= NORMAL_TOL), (hint, v)
+            pn = got["normal"][hit & planted]
+            assert np.all(np.abs(np.linalg.norm(pn, axis=1) - 1.0) < 1e-12)
+    engine.set_max_hull_vertices(0)
+    configure(engine, 0)

@@ -63,7 +63,7 @@ def make_workload(name: str, n_pairs: int, seed: int):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
 
-    def __init__(self, index: int, period: float = 0.02):
+    def __init__(self, index: int, period: float = 0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -304,9 +304,9 @@ def main():
         "config": {"workload": desc, "pairs_per_gpu_per_step": n, "mode": mode, "sharding": f"pairs by index x{world}",
                    "l2": "inputs larger than L2 (hull store %.0f MB per GPU)" % (batch.verts.nbytes / 1e6),
                    "algorithmic_bytes_per_pair": bytes_per_pair,
-                   "colliding_fraction": hits_all / pairs_all, "lanes_per_pair": args.lanes or "auto (1 thread/pair over smem-staged hulls; 4-lane sub-warp for hulls > 16 vertices)"},
+                   "colliding_fraction": hits_all / pairs_all, "lanes_per_pair": args.lanes or "auto (hulls <= 16 vertices: 1 thread/pair, init kernel + compacting walk kernel; larger: 4 lanes/pair, 8 pairs per warp in lockstep)"},
         "contacts_per_s": hits_all * args.steps / (ms_total * 1e-3),
-        "roofline": {"bound": "hbm", "kernel": {"gjk": "gjk_kernel", "epa": "epa_kernel"}[dom],
+        "roofline": {"bound": "hbm", "kernel": {"gjk": "gjk stage (gjk_init_kernel + gjk_walk_kernel)", "epa": "epa stage (epa3_kernel + epa_kernel)"}[dom],
                      "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": (achieved / peak_gbs) if achieved else None, "peak_source": peak_src,
                      "traffic": (traffic or {}).get({"gjk": "gjk_kernel", "epa": "epa_kernel"}[dom]),

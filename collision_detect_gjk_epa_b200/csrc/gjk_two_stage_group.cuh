@@ -173,31 +173,21 @@ gjk_walk_group_kernel(TwoStageArgs ta, int slot_doubles)
             bt.oa = ta.q.oa[bt.base + lane];  bt.ob = ta.q.ob[bt.base + lane];
         }
     };
-    auto prefetch = [&](const Batch &bt) {
-#ifdef GJK_WALKG_NO_PREFETCH
-        return;
-#endif
-        if (lane < bt.n) {
-            prefetch_l2_range(a.verts + 3 * bt.oa, 24 * (int)((bt.fln >> 4) & 0x3fffu));
-            prefetch_l2_range(a.verts + 3 * bt.ob, 24 * (int)(bt.fln >> 18));
-        }
+    // L2 prefetch, a few pairs ahead only: with 1.5 KB per pair a whole batch per warp (x 2400 resident warps)
+    // outgrows L2 and the lines are gone again before they are used (ncu: DRAM reads 2x the hull bytes)
+    constexpr int AHEAD = 8;
+    auto prefetch_records = [&](const Batch &bt) {                // seed records: 16 fields x 256 bytes, one line per lane
         if (bt.n > 0)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ta.q.f64 + (size_t)(lane >> 1) * cap + bt.base + (lane & 1) * 16));
     };
-#ifdef GJK_DEBUG_BOUNDS
-    {   // whole-queue scan before anything is consumed
-        const long long nv_total = a.hull_off[a.n_hulls];
-        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (unsigned long long)gridDim.x * blockDim.x) {
-            const unsigned f_ = ta.q.fln[i]; const long long oa_ = ta.q.oa[i], ob_ = ta.q.ob[i]; const int p_ = ta.q.pair[i];
-            const int nA_ = (int)((f_ >> 4) & 0x3fffu), nB_ = (int)(f_ >> 18);
-            if (oa_ < 0 || ob_ < 0 || oa_ + nA_ > nv_total || ob_ + nB_ > nv_total || p_ < 0 || p_ >= a.n_pairs)
-                printf("SCAN bad seed %llu of %llu: p=%d fln=%08x oa=%lld ob=%lld S0x=%g mk=%g\n", i, count, p_, f_, oa_, ob_,
-                       ta.q.f64[i], ta.q.f64[15 * cap + i]);
+    auto prefetch_hulls = [&](const Batch &bt, int from) {         // the hull blocks of entries [from, from + AHEAD)
+        if (lane >= from && lane < from + AHEAD && lane < bt.n) {
+            prefetch_l2_range(a.verts + 3 * bt.oa, 24 * (int)((bt.fln >> 4) & 0x3fffu));
+            prefetch_l2_range(a.verts + 3 * bt.ob, 24 * (int)(bt.fln >> 18));
         }
-    }
-#endif
+    };
     Batch cur, nxt;
-    fetch(cur); prefetch(cur);
+    fetch(cur); prefetch_records(cur); prefetch_hulls(cur, 0);
     fetch(nxt);
     bool nxt_pf = false;
     int bcur = 0;
@@ -206,11 +196,13 @@ gjk_walk_group_kernel(TwoStageArgs ta, int slot_doubles)
         const unsigned idle = __ballot_sync(FULL, !active) & leaders;
         const int n_idle = __popc(idle);
         if (n_idle >= refill_groups && (bcur < cur.n || nxt.n > 0)) {
-            if (!nxt_pf) { prefetch(nxt); nxt_pf = true; }
+            if (!nxt_pf) { prefetch_records(nxt); nxt_pf = true; }
             if (bcur >= cur.n) { cur = nxt; bcur = 0; fetch(nxt); nxt_pf = false; }
             const int avail = cur.n - bcur;
             if (avail > 0) {
                 const int n_take = n_idle < avail ? n_idle : avail;
+                prefetch_hulls(cur, bcur + n_take);                 // what the next re-pack will take
+                if (bcur + n_take + AHEAD > 32) prefetch_hulls(nxt, bcur + n_take - 32);
                 const int rank = __popc(idle & before);
                 const bool take = !active && rank < n_take;
                 const int src = (bcur + rank) & 31;

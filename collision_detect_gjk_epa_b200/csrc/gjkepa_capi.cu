@@ -34,6 +34,7 @@ struct gjkepa_ctx {
     int walk_refill = 8;           // K1w re-packs a warp when this many lanes are idle
     bool single_kernel = false;    // monolithic tile kernel instead of K1i + K1w
     bool epa_general = false;      // general EPA kernel only (no linked-mesh fast path)
+    int tile_max_vertices = 16;    // largest hull the thread-per-pair kernels stage (larger ones: 4-lane kernels)
     double *d_seed_f64 = nullptr; int32_t *d_seed_pair = nullptr; uint32_t *d_seed_fl = nullptr; int64_t *d_seed_off = nullptr; int64_t cap_seed = 0;
     int32_t *d_ovf = nullptr; int64_t cap_ovf = 0;
     int32_t *d_ovf2 = nullptr; int64_t cap_ovf2 = 0;
@@ -187,6 +188,11 @@ int gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value)
     }
     if (key == GJKEPA_TUNE_SINGLE_KERNEL) { ctx->single_kernel = value != 0; return GJKEPA_OK; }
     if (key == GJKEPA_TUNE_EPA_GENERAL) { ctx->epa_general = value != 0; return GJKEPA_OK; }
+    if (key == GJKEPA_TUNE_TILE_MAX_VERTICES) {
+        if (value < 4 || value > 16) return GJKEPA_ERR_ARG;
+        ctx->tile_max_vertices = value;
+        return GJKEPA_OK;
+    }
     return GJKEPA_ERR_ARG;
 }
 
@@ -295,7 +301,8 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     if (prof) CU(cudaEventRecord(ctx->ev[2], st));
     if (use_tile && !ctx->single_kernel) {
         // K1i + K1w: one thread per pair, init in lockstep, walk with iteration compaction (gjk_two_stage.cuh)
-        const int cap_vertices = ctx->max_hull_hint > 0 ? (ctx->max_hull_hint < 16 ? ctx->max_hull_hint : 16) : 16;
+        const int tmax_v = ctx->tile_max_vertices;
+        const int cap_vertices = ctx->max_hull_hint > 0 ? (ctx->max_hull_hint < tmax_v ? ctx->max_hull_hint : tmax_v) : tmax_v;
         gjk::TwoStageArgs ta;
         ta.b = a;
         ta.col_units = 2 * 3 * ((cap_vertices + 1) / 2);
@@ -367,7 +374,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     if (use_tile) {
         // K1c: hulls too large for a column -> 4-lane sub-warps over TMA-staged slots; K1b: anything larger still
         const int hint = ctx->max_hull_hint;
-        if (hint == 0 || hint > 16) {
+        if (hint == 0 || hint > ctx->tile_max_vertices) {
             const int cap_v = (hint > 0 && hint < 64) ? hint : 64;
             const int slot_doubles = ((3 * 2 * cap_v + 15) / 16) * 16 + 4;
             const size_t smem_c = (size_t)slot_doubles * 8 /*pairs per warp*/ * 4 /*warps*/ * sizeof(double);

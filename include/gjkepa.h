@@ -90,6 +90,7 @@ int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
 #define GJKEPA_TUNE_WALK_REFILL    1
 #define GJKEPA_TUNE_SINGLE_KERNEL  2
 #define GJKEPA_TUNE_EPA_GENERAL    3
+#define GJKEPA_TUNE_TILE_MAX_VERTICES 4   /* 4..16 (default 16): largest hull run one thread per pair; larger ones get 4 lanes */
 int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);
 
 /* ---- replaces CALL GJKEPA(...) (F:39-52): one pair, every scalar by reference, HOST arrays ----

@@ -286,3 +286,23 @@ def test_touching_cubes_inside_lockstep_warps(W, orc, engine):
             assert np.all(np.abs(np.linalg.norm(pn, axis=1) - 1.0) < 1e-12)
     engine.set_max_hull_vertices(0)
     configure(engine, 0)
+
+
+def test_large_batch_equals_its_chunks(W, engine):
+    """cfg5-shaped batch well beyond the other tests (8M pairs over a shared store of 1M 16-vertex bodies): the
+    queues between the kernels, the work lists and every 32-bit index must hold up.  The whole batch and the same
+    pairs run as four chunks must give identical flags, status words, depths and normals; a second shape with
+    24-vertex hulls takes the 4-lane kernels."""
+    for n_vert, n_pairs in ((16, 8_000_000), (24, 3_000_000)):
+        b = W.make_shared_store(1_000_000, n_pairs, n_vert=n_vert, seed=31)
+        configure(engine, 0)
+        engine.set_max_hull_vertices(n_vert)
+        whole = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="epa", want_contacts=True)
+        assert whole["n_contacts"] == int(whole["collision"].sum()) and 0.05 < whole["collision"].mean() < 0.95
+        q = n_pairs // 4
+        for c in range(4):
+            sl = slice(c * q, (c + 1) * q)
+            part = engine.batch_host(b.verts, b.hull_off, b.pair_a[sl], b.pair_b[sl], mode="epa")
+            for k in ("collision", "status", "depth", "normal"):
+                assert np.array_equal(part[k], whole[k][sl]), (n_vert, c, k)
+    engine.set_max_hull_vertices(0)

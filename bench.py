@@ -160,10 +160,23 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line: dict):
+    """The one JSON line goes to the real stdout; everything else this process or its libraries print
+    (NCCL's version banner, warnings) was diverted to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # fd 1 -> stderr for libraries that print to stdout
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -344,7 +357,7 @@ def main():
         line["extra"] = {"workload": d3, "ms_per_step": ms3, "pairs_per_s": b3.n_pairs / ms3 * 1e3,
                          "contacts_per_s": h3 / ms3 * 1e3, "contacts": h3,
                          "algorithmic_gbs": b3.algorithmic_bytes_per_pair(33) * b3.n_pairs / (ms3 * 1e-3) / 1e9}
-    print(json.dumps(line), flush=True)
+    emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

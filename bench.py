@@ -357,6 +357,32 @@ def main():
         line["extra"] = {"workload": d3, "ms_per_step": ms3, "pairs_per_s": b3.n_pairs / ms3 * 1e3,
                          "contacts_per_s": h3 / ms3 * 1e3, "contacts": h3,
                          "algorithmic_gbs": b3.algorithmic_bytes_per_pair(33) * b3.n_pairs / (ms3 * 1e-3) / 1e9}
+    if not args.no_extra and args.workload == "cfg2" and world == 1:
+        # the same kind of step with the shapes resident on the device and only poses crossing PCIe
+        # (gjkepa_shapes_upload once, gjkepa_batch_posed_f64 per step): 2 bodies per pair, every body its own box
+        from collision_detect_gjk_epa_b200 import workloads as W
+        pb = W.make_posed(n_shapes=2 * args.pairs, n_bodies=2 * args.pairs, n_pairs=args.pairs, sigma=1.0, kind="box", seed=777)
+        eng.upload_shapes(pb.shape_verts, pb.shape_off)
+        hp = []
+        for x in (pb.body_shape, pb.pose, pb.pair_a, pb.pair_b):
+            tt, npv = pin(x); keep.append(tt); hp.append(npv)
+        tt = torch.empty((pb.n_pairs,), dtype=torch.uint8, pin_memory=True); keep.append(tt)
+        po = {"collision": tt.numpy()}
+        for _ in range(2):
+            eng.batch_posed(*hp, mode="gjk", out=po)
+        torch.cuda.synchronize()
+        kp = max(3, min(args.steps, 20))
+        t0 = time.perf_counter()
+        for _ in range(kp):
+            eng.batch_posed(*hp, mode="gjk", out=po)
+        torch.cuda.synchronize()
+        dtp = (time.perf_counter() - t0) / kp
+        line.setdefault("extra", {})["e2e_resident_shapes"] = {
+            "workload": "cfg2-shaped: 2M box bodies (shapes resident on the device), 1M body pairs, poses per step",
+            "value": pb.n_pairs / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3,
+            "h2d_bytes_per_step": int(sum(x.nbytes for x in hp)), "d2h_bytes_per_step": int(pb.n_pairs),
+            "colliding_fraction": float(po["collision"].mean()),
+            "api": "gjkepa_batch_posed_f64 (C ABI, pinned host buffers; pose applied on the device)"}
     emit(line)
     eng.close()
     if world > 1:

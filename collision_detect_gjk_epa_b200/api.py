@@ -135,6 +135,52 @@ class Engine:
             out["n_contacts"] = int(nc.value)
         return out
 
+    # ---- shapes resident on the device, poses per call (gjkepa_shapes_upload / gjkepa_batch_posed_f64) ----
+    def upload_shapes(self, shape_verts, shape_off):
+        """Body-space hull store (same layout as `verts`/`hull_off`), copied to the device once."""
+        shape_verts = np.ascontiguousarray(shape_verts, dtype=np.float64)
+        shape_off = np.ascontiguousarray(shape_off, dtype=np.int64)
+        self._check(self._L.gjkepa_shapes_upload(self._h, int(shape_off.shape[0] - 1), _np_ptr(shape_verts), _np_ptr(shape_off)),
+                    "gjkepa_shapes_upload")
+
+    def batch_posed(self, body_shape, pose, pair_a, pair_b, mode="full", version: int = 1, tol_ff: float = 1.0,
+                    out: Optional[dict] = None, want_status: bool = True, want_contacts: bool = False) -> dict:
+        """pose: (n_bodies, 12) = R row-major (9) + t (3); world vertex = ((r00*x + r01*y) + r02*z) + tx, applied on
+        the device.  pair_a / pair_b are body numbers.  HOST buffers in and out."""
+        mode = _MODES[mode]
+        body_shape = np.ascontiguousarray(body_shape, dtype=np.int32)
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        pair_a = np.ascontiguousarray(pair_a, dtype=np.int32)
+        pair_b = np.ascontiguousarray(pair_b, dtype=np.int32)
+        nb, n = int(body_shape.shape[0]), int(pair_a.shape[0])
+        assert pose.size == 12 * nb
+        if out is None:
+            out = {"collision": np.empty(n, np.uint8)}
+            if want_status:
+                out["status"] = np.empty(n, np.uint32)
+            if mode >= MODE_EPA:
+                out["depth"] = np.empty(n, np.float64)
+                out["normal"] = np.empty((n, 3), np.float64)
+            if mode >= MODE_FULL:
+                out["colli_type"] = np.empty(n, np.int32)
+                out["nearest"] = np.empty((n, 6), np.float64)
+                out["point"] = np.empty((n, 3), np.float64)
+            if want_contacts:
+                out["contact_index"] = np.empty(n, np.int32)
+        nc = C.c_int64(0)
+        rc = self._L.gjkepa_batch_posed_f64(
+            self._h, int(version), float(tol_ff), nb, _np_ptr(body_shape), _np_ptr(pose), n,
+            _np_ptr(pair_a), _np_ptr(pair_b), mode,
+            _np_ptr(out.get("collision")), _np_ptr(out.get("colli_type")), _np_ptr(out.get("nearest")),
+            _np_ptr(out.get("normal")), _np_ptr(out.get("point")), _np_ptr(out.get("depth")),
+            _np_ptr(out.get("status")),
+            C.cast(C.byref(nc), C.c_void_p) if want_contacts else C.c_void_p(0),
+            _np_ptr(out.get("contact_index")))
+        self._check(rc, "gjkepa_batch_posed_f64")
+        if want_contacts:
+            out["n_contacts"] = int(nc.value)
+        return out
+
     # ---- DEVICE buffers (torch CUDA tensors already resident in HBM), asynchronous ----
     def batch_device(self, verts, hull_off, pair_a, pair_b, mode="full", version: int = 1,
                      tol_ff: float = 1.0, out: Optional[dict] = None, want_status: bool = True,

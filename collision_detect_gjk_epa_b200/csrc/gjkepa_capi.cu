@@ -12,6 +12,9 @@
 #include "epa_kernel.cuh"
 #include "epa_v3.cuh"
 #include "contact_kernel.cuh"
+#include "pose_kernel.cuh"
+
+#include <cub/device/device_scan.cuh>
 
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -44,6 +47,12 @@ struct gjkepa_ctx {
     unsigned long long *d_counters = nullptr;      // [0] work-list length, [1] EPA queue head, [2] GJK overflow, [3] EPA pass-2 head, [4] EPA overflow
     // staging for the host-buffer entry (device)
     void *d_stage = nullptr; size_t cap_stage = 0;
+    // resident shapes (gjkepa_shapes_upload) and the world-space store rebuilt from poses per call
+    double *d_shape_verts = nullptr; int64_t *d_shape_off = nullptr; int64_t n_shapes = 0, max_shape_verts = 0;
+    double *d_world = nullptr; int64_t cap_world = 0;            // doubles
+    int64_t *d_world_off = nullptr; int64_t cap_world_off = 0;   // sizes, then offsets (n_bodies + 1 each)
+    void *d_scan_tmp = nullptr; size_t cap_scan_tmp = 0;
+    void *d_stage2 = nullptr; size_t cap_stage2 = 0;
     unsigned long long *h_counters = nullptr;      // pinned
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;
@@ -133,6 +142,12 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
     if (ctx->d_seed_fl) cudaFree(ctx->d_seed_fl);
     if (ctx->d_seed_off) cudaFree(ctx->d_seed_off);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->d_shape_verts) cudaFree(ctx->d_shape_verts);
+    if (ctx->d_shape_off) cudaFree(ctx->d_shape_off);
+    if (ctx->d_world) cudaFree(ctx->d_world);
+    if (ctx->d_world_off) cudaFree(ctx->d_world_off);
+    if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
+    if (ctx->d_stage2) cudaFree(ctx->d_stage2);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -548,6 +563,144 @@ int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         for (int64_t i = 0; i < n_pairs; ++i)
             if (h_flags[i]) { if (contact_index) contact_index[c] = (int32_t)i; ++c; }
         if (n_contacts) *n_contacts = c;
+    }
+    return GJKEPA_OK;
+}
+
+// ---- shapes resident on the device, poses per call ----
+int gjkepa_shapes_upload(gjkepa_ctx *ctx, int64_t n_shapes, const double *shape_verts, const int64_t *shape_off)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (n_shapes <= 0 || !shape_verts || !shape_off || shape_off[0] != 0) return fail(ctx, GJKEPA_ERR_ARG, "bad shape store");
+    int64_t mx = 0;
+    for (int64_t i = 0; i < n_shapes; ++i) {
+        const int64_t n = shape_off[i + 1] - shape_off[i];
+        if (n <= 0) return fail(ctx, GJKEPA_ERR_ARG, "empty shape");
+        if (n > mx) mx = n;
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_shape_verts) { cudaFree(ctx->d_shape_verts); ctx->d_shape_verts = nullptr; }
+    if (ctx->d_shape_off) { cudaFree(ctx->d_shape_off); ctx->d_shape_off = nullptr; }
+    ctx->n_shapes = 0;
+    const int64_t nv = shape_off[n_shapes];
+    cudaError_t e = cudaMalloc((void **)&ctx->d_shape_verts, (size_t)nv * 3 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_shape_off, (size_t)(n_shapes + 1) * sizeof(int64_t));
+    if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc shape store", e);
+    CU(cudaMemcpy(ctx->d_shape_verts, shape_verts, (size_t)nv * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->d_shape_off, shape_off, (size_t)(n_shapes + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    ctx->n_shapes = n_shapes; ctx->max_shape_verts = mx;
+    return GJKEPA_OK;
+}
+
+int gjkepa_batch_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                           int64_t n_bodies, const int32_t *body_shape, const double *pose,
+                           int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
+                           uint8_t *collision, int32_t *colli_type, double *nearest,
+                           double *normal, double *point, double *depth,
+                           uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (ctx->n_shapes <= 0) return fail(ctx, GJKEPA_ERR_ARG, "no shapes uploaded (gjkepa_shapes_upload)");
+    if (n_pairs < 0 || n_bodies <= 0 || !body_shape || !pose) return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or null input");
+    if (n_pairs > 0 && (!pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (n_pairs == 0) { if (n_contacts) *n_contacts = 0; return GJKEPA_OK; }
+
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const bool need_flags = collision || contact_index || n_contacts;
+    size_t o_shape = 0;
+    size_t o_pose  = o_shape + al((size_t)n_bodies * sizeof(int32_t));
+    size_t o_pa    = o_pose + al((size_t)n_bodies * 12 * sizeof(double));
+    size_t o_pb    = o_pa + al((size_t)n_pairs * sizeof(int32_t));
+    size_t o_col   = o_pb + al((size_t)n_pairs * sizeof(int32_t));
+    size_t o_type  = o_col + al(need_flags ? (size_t)n_pairs : 0);
+    size_t o_near  = o_type + al(colli_type ? (size_t)n_pairs * sizeof(int32_t) : 0);
+    size_t o_nrm   = o_near + al(nearest ? (size_t)n_pairs * 6 * sizeof(double) : 0);
+    size_t o_pt    = o_nrm + al(normal ? (size_t)n_pairs * 3 * sizeof(double) : 0);
+    size_t o_dep   = o_pt + al(point ? (size_t)n_pairs * 3 * sizeof(double) : 0);
+    size_t o_st    = o_dep + al(depth ? (size_t)n_pairs * sizeof(double) : 0);
+    size_t total   = o_st + al(status ? (size_t)n_pairs * sizeof(uint32_t) : 0);
+    if (total > ctx->cap_stage2) {
+        if (ctx->d_stage2) { cudaFree(ctx->d_stage2); ctx->d_stage2 = nullptr; ctx->cap_stage2 = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_stage2, total + total / 8);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
+        ctx->cap_stage2 = total + total / 8;
+    }
+    // world store sized by the largest shape (no device->host round trip for the exact total)
+    const int64_t need_world = n_bodies * ctx->max_shape_verts * 3;
+    if (need_world > ctx->cap_world) {
+        if (ctx->d_world) { cudaFree(ctx->d_world); ctx->d_world = nullptr; ctx->cap_world = 0; }
+        cudaError_t e = cudaMalloc((void **)&ctx->d_world, (size_t)need_world * sizeof(double));
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc world store", e);
+        ctx->cap_world = need_world;
+    }
+    if (2 * (n_bodies + 1) > ctx->cap_world_off) {
+        if (ctx->d_world_off) { cudaFree(ctx->d_world_off); ctx->d_world_off = nullptr; ctx->cap_world_off = 0; }
+        cudaError_t e = cudaMalloc((void **)&ctx->d_world_off, (size_t)2 * (n_bodies + 1) * sizeof(int64_t));
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc world offsets", e);
+        ctx->cap_world_off = 2 * (n_bodies + 1);
+    }
+    int64_t *d_sizes = ctx->d_world_off, *d_off = ctx->d_world_off + (n_bodies + 1);
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_sizes, d_off, (int)(n_bodies + 1), st));
+    if (tmp_bytes > ctx->cap_scan_tmp) {
+        if (ctx->d_scan_tmp) { cudaFree(ctx->d_scan_tmp); ctx->d_scan_tmp = nullptr; ctx->cap_scan_tmp = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_scan_tmp, tmp_bytes + 256);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc scan scratch", e);
+        ctx->cap_scan_tmp = tmp_bytes + 256;
+    }
+
+    char *base = (char *)ctx->d_stage2;
+    CU(cudaMemcpyAsync(base + o_shape, body_shape, (size_t)n_bodies * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_pose, pose, (size_t)n_bodies * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_pa, pair_a, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_pb, pair_b, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    {   // Kp: sizes -> offsets -> world-space hull blocks
+        const int threads = 256;
+        pose::body_sizes_kernel<<<(unsigned)((n_bodies + 1 + threads - 1) / threads), threads, 0, st>>>(
+            (const int32_t *)(base + o_shape), ctx->d_shape_off, n_bodies, ctx->n_shapes, d_sizes);
+        size_t tb = ctx->cap_scan_tmp;
+        CU(cub::DeviceScan::ExclusiveSum(ctx->d_scan_tmp, tb, d_sizes, d_off, (int)(n_bodies + 1), st));
+        int64_t blocks = (n_bodies * 8 + threads - 1) / threads;
+        const int64_t max_blocks = (int64_t)ctx->sm_count * 32;
+        if (blocks > max_blocks) blocks = max_blocks;
+        pose::apply_pose_kernel<<<(unsigned)blocks, threads, 0, st>>>(ctx->d_shape_verts, ctx->d_shape_off,
+            (const int32_t *)(base + o_shape), (const double *)(base + o_pose), d_off, n_bodies, ctx->n_shapes, ctx->d_world);
+        ctx->launches += 2;
+        CU(cudaGetLastError());
+    }
+    const int save_hint = ctx->max_hull_hint;
+    if (save_hint == 0) ctx->max_hull_hint = (int)ctx->max_shape_verts;      // the shape store bounds the hull sizes
+    int rc = gjkepa_batch_device_f64(ctx, version, tol_ff, n_bodies, ctx->d_world, d_off, n_pairs,
+        (const int32_t *)(base + o_pa), (const int32_t *)(base + o_pb), mode,
+        need_flags ? (uint8_t *)(base + o_col) : nullptr,
+        colli_type ? (int32_t *)(base + o_type) : nullptr,
+        nearest ? (double *)(base + o_near) : nullptr,
+        normal ? (double *)(base + o_nrm) : nullptr,
+        point ? (double *)(base + o_pt) : nullptr,
+        depth ? (double *)(base + o_dep) : nullptr,
+        status ? (uint32_t *)(base + o_st) : nullptr, nullptr, nullptr);
+    ctx->max_hull_hint = save_hint;
+    if (rc) return rc;
+
+    std::vector<uint8_t> tmp_flags;
+    uint8_t *h_flags = collision;
+    if (need_flags && !h_flags) { tmp_flags.resize((size_t)n_pairs); h_flags = tmp_flags.data(); }
+    if (need_flags) CU(cudaMemcpyAsync(h_flags, base + o_col, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    if (colli_type) CU(cudaMemcpyAsync(colli_type, base + o_type, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (nearest)    CU(cudaMemcpyAsync(nearest, base + o_near, (size_t)n_pairs * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (normal)     CU(cudaMemcpyAsync(normal, base + o_nrm, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (point)      CU(cudaMemcpyAsync(point, base + o_pt, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (depth)      CU(cudaMemcpyAsync(depth, base + o_dep, (size_t)n_pairs * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (status)     CU(cudaMemcpyAsync(status, base + o_st, (size_t)n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_contacts || contact_index) {
+        int64_t cnt = 0;
+        for (int64_t i = 0; i < n_pairs; ++i)
+            if (h_flags[i]) { if (contact_index) contact_index[cnt] = (int32_t)i; ++cnt; }
+        if (n_contacts) *n_contacts = cnt;
     }
     return GJKEPA_OK;
 }

@@ -167,6 +167,44 @@ def unit_cubes(offset=(0.5, 0.0, 0.0)) -> PairBatch:
     return PairBatch(verts, hull_off, np.array([0], np.int32), np.array([1], np.int32), name="cubes")
 
 
+@dataclass
+class PosedBatch:
+    """Body-space shapes + per-body poses + body pairs (input of gjkepa_batch_posed_f64)."""
+    shape_verts: np.ndarray    # float64, packed shape blocks [x(n) | y(n) | z(n)]
+    shape_off: np.ndarray      # int64, n_shapes+1
+    body_shape: np.ndarray     # int32, n_bodies
+    pose: np.ndarray           # float64 (n_bodies, 12): R row-major, t
+    pair_a: np.ndarray         # int32 body numbers
+    pair_b: np.ndarray
+
+    @property
+    def n_pairs(self) -> int:
+        return int(self.pair_a.shape[0])
+
+
+def make_posed(n_shapes: int, n_bodies: int, n_pairs: int, sigma: float = 0.85, seed: int = 4242,
+               n_lo: int = 8, n_hi: int = 8, kind: str = "box") -> PosedBatch:
+    """Bodies instance a library of shapes (boxes, or hull(n) with n ~ U{n_lo..n_hi}) under random rigid poses;
+    pairs join bodies whose centres are N(0, sigma^2) apart (body b+1 is placed relative to body b for b even)."""
+    rng = np.random.default_rng(seed)
+    sizes = np.full(n_shapes, 8) if kind == "box" else rng.integers(n_lo, n_hi + 1, size=n_shapes)
+    shape_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    shape_verts = np.empty(3 * int(shape_off[-1]))
+    for n in np.unique(sizes):
+        idx = np.nonzero(sizes == n)[0]
+        loc = _box8_local(rng, len(idx)) if kind == "box" else _hull_local(rng, len(idx), int(n))
+        blk = np.ascontiguousarray(loc.transpose(0, 2, 1)).reshape(len(idx), 3 * n)
+        shape_verts[(3 * shape_off[idx][:, None] + np.arange(3 * n)[None, :])] = blk
+    body_shape = rng.integers(0, n_shapes, size=n_bodies).astype(np.int32)
+    rot = _quat_rot(rng, n_bodies).reshape(n_bodies, 9)
+    t = rng.uniform(-50.0, 50.0, size=(n_bodies, 3))
+    t[1::2] = t[0::2][: len(t[1::2])] + rng.standard_normal((len(t[1::2]), 3)) * sigma
+    pose = np.concatenate([rot, t], axis=1)
+    pa = (2 * rng.integers(0, n_bodies // 2, size=n_pairs)).astype(np.int32)
+    pb = pa + 1
+    return PosedBatch(shape_verts, shape_off, body_shape, pose, pa, pb.astype(np.int32))
+
+
 def make_touching_mix(n_pairs: int, seed: int = 77, every: int = 5, n_vert: int = 20) -> PairBatch:
     """Random hull(n_vert) pairs with, every `every`-th pair, two axis-aligned unit cubes carrying their 12
     edge midpoints as extra vertices (20 vertices, same hull) that touch, nearly touch or overlap along x by

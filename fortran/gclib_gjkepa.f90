@@ -15,7 +15,7 @@ MODULE GCLIB_GJKEPA
     USE, INTRINSIC :: ISO_C_BINDING
     IMPLICIT NONE
     PRIVATE
-    PUBLIC :: GJKEPA, GJKEPA_BATCH, GJKEPA_CTX_CREATE, GJKEPA_CTX_DESTROY
+    PUBLIC :: GJKEPA, GJKEPA_BATCH, GJKEPA_CTX_CREATE, GJKEPA_CTX_DESTROY, GJKEPA_SHAPES_UPLOAD, GJKEPA_BATCH_POSED
 
     INTEGER(C_INT32_T), PARAMETER, PUBLIC :: GJKEPA_MODE_GJK = 0, GJKEPA_MODE_EPA = 1, GJKEPA_MODE_FULL = 2
 
@@ -56,6 +56,23 @@ MODULE GCLIB_GJKEPA
             TYPE(C_PTR), VALUE :: verts, hull_off, pair_a, pair_b
             TYPE(C_PTR), VALUE :: collision, colli_type, nearest, normal, point, depth, status
             TYPE(C_PTR), VALUE :: n_contacts, contact_index
+            INTEGER(C_INT) :: rc
+        END FUNCTION
+        FUNCTION gjkepa_shapes_upload(ctx, n_shapes, shape_verts, shape_off) BIND(C, NAME="gjkepa_shapes_upload") RESULT(rc)
+            IMPORT :: C_PTR, C_INT, C_INT64_T
+            TYPE(C_PTR), VALUE :: ctx, shape_verts, shape_off
+            INTEGER(C_INT64_T), VALUE :: n_shapes
+            INTEGER(C_INT) :: rc
+        END FUNCTION
+        FUNCTION gjkepa_batch_posed_f64(ctx, version, tol_ff, n_bodies, body_shape, pose, n_pairs, pair_a, pair_b, mode, &
+                                        collision, colli_type, nearest, normal, point, depth, status, &
+                                        n_contacts, contact_index) BIND(C, NAME="gjkepa_batch_posed_f64") RESULT(rc)
+            IMPORT :: C_PTR, C_INT, C_INT32_T, C_INT64_T, C_DOUBLE
+            TYPE(C_PTR), VALUE :: ctx, body_shape, pose, pair_a, pair_b
+            TYPE(C_PTR), VALUE :: collision, colli_type, nearest, normal, point, depth, status, n_contacts, contact_index
+            INTEGER(C_INT32_T), VALUE :: version, mode
+            REAL(C_DOUBLE), VALUE :: tol_ff
+            INTEGER(C_INT64_T), VALUE :: n_bodies, n_pairs
             INTEGER(C_INT) :: rc
         END FUNCTION gjkepa_batch_f64
     END INTERFACE
@@ -122,5 +139,39 @@ CONTAINS
                               C_LOC(status_), C_NULL_PTR, C_NULL_PTR)
         IF (rc /= 0) ERROR STOP "GJKEPA_BATCH: the CUDA narrow phase failed"
     END SUBROUTINE GJKEPA_BATCH
+
+    ! Shapes stay on the GPU, only poses cross PCIe per call.  shape_verts/shape_off: a hull store of BODY-space
+    ! shapes (layout as verts/hull_off above), copied to the device once.
+    SUBROUTINE GJKEPA_SHAPES_UPLOAD(ctx, shape_verts, shape_off)
+        TYPE(C_PTR), INTENT(IN) :: ctx
+        REAL(C_DOUBLE),     INTENT(IN), TARGET, CONTIGUOUS :: shape_verts(:)
+        INTEGER(C_INT64_T), INTENT(IN), TARGET, CONTIGUOUS :: shape_off(:)
+        INTEGER(C_INT) :: rc
+        rc = gjkepa_shapes_upload(ctx, INT(SIZE(shape_off) - 1, C_INT64_T), C_LOC(shape_verts), C_LOC(shape_off))
+        IF (rc /= 0) ERROR STOP "GJKEPA_SHAPES_UPLOAD failed"
+    END SUBROUTINE GJKEPA_SHAPES_UPLOAD
+
+    ! body_shape(b): 0-based shape number of body b; pose(:,b) = r00 r01 r02 r10 r11 r12 r20 r21 r22 tx ty tz
+    ! (R row-major; world = ((r00*x + r01*y) + r02*z) + tx, applied on the device); pair_a/pair_b: 0-based BODY numbers.
+    SUBROUTINE GJKEPA_BATCH_POSED(ctx, version_, TOL_FF_, body_shape, pose, pair_a, pair_b, mode, &
+                                  collision_, colliType_, nearest_points_, collision_normal_, &
+                                  collision_point_, penetration_depth_, status_)
+        TYPE(C_PTR), INTENT(IN) :: ctx
+        INTEGER*4, INTENT(IN) :: version_, mode
+        REAL*8,    INTENT(IN) :: TOL_FF_
+        INTEGER(C_INT32_T), INTENT(IN), TARGET, CONTIGUOUS :: body_shape(:), pair_a(:), pair_b(:)
+        REAL(C_DOUBLE),     INTENT(IN), TARGET, CONTIGUOUS :: pose(:,:)                  ! (12,n_bodies)
+        INTEGER(C_INT8_T),  INTENT(OUT), TARGET, CONTIGUOUS :: collision_(:)
+        INTEGER(C_INT32_T), INTENT(OUT), TARGET, CONTIGUOUS :: colliType_(:), status_(:)
+        REAL(C_DOUBLE),     INTENT(OUT), TARGET, CONTIGUOUS :: nearest_points_(:,:,:), collision_normal_(:,:)
+        REAL(C_DOUBLE),     INTENT(OUT), TARGET, CONTIGUOUS :: collision_point_(:,:), penetration_depth_(:)
+        INTEGER(C_INT) :: rc
+        rc = gjkepa_batch_posed_f64(ctx, version_, TOL_FF_, INT(SIZE(body_shape), C_INT64_T), C_LOC(body_shape), &
+                                    C_LOC(pose), INT(SIZE(pair_a), C_INT64_T), C_LOC(pair_a), C_LOC(pair_b), mode, &
+                                    C_LOC(collision_), C_LOC(colliType_), C_LOC(nearest_points_), &
+                                    C_LOC(collision_normal_), C_LOC(collision_point_), C_LOC(penetration_depth_), &
+                                    C_LOC(status_), C_NULL_PTR, C_NULL_PTR)
+        IF (rc /= 0) ERROR STOP "GJKEPA_BATCH_POSED: the CUDA narrow phase failed"
+    END SUBROUTINE GJKEPA_BATCH_POSED
 
 END MODULE GCLIB_GJKEPA

@@ -123,6 +123,23 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                             double *normal_dev, double *point_dev, double *depth_dev,
                             uint32_t *status_dev, int64_t *n_contacts_dev, int32_t *contact_index_dev);
 
+/* ---- shapes resident on the device, poses per call (upstream of the reference path) ----
+ * A caller of GJKEPA passes world-space vertices, i.e. it applies each body's pose on the host first.  With the
+ * body-space shapes uploaded once, only poses cross PCIe per call (96 B per body instead of 24 B per vertex) and
+ * the pose is applied on the device with this arithmetic (IEEE, every operation rounded, no FMA), R row-major:
+ *     x' = ((r00*x + r01*y) + r02*z) + tx     (likewise y', z')
+ * so a host that transforms the same way and calls gjkepa_batch_f64 gets bit-identical results.
+ * shape_verts/shape_off: a hull store as above (HOST buffers, copied; replaces any earlier upload).
+ * body_shape[b]: shape number of body b; pose: 12 doubles per body (r00 r01 r02 r10 .. r22 tx ty tz);
+ * pair_a/pair_b: BODY numbers.  Outputs as gjkepa_batch_f64. */
+int gjkepa_shapes_upload(gjkepa_ctx *ctx, int64_t n_shapes, const double *shape_verts, const int64_t *shape_off);
+int gjkepa_batch_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                           int64_t n_bodies, const int32_t *body_shape, const double *pose /*12*n_bodies*/,
+                           int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
+                           uint8_t *collision, int32_t *colli_type, double *nearest /*6*np*/,
+                           double *normal /*3*np*/, double *point /*3*np*/, double *depth,
+                           uint32_t *status, int64_t *n_contacts, int32_t *contact_index);
+
 /* self-test hook (host buffers, n elements each): the library's straight-line IEEE sqrt / division
  * sequences next to the compiler's operators; in_range bit 0 = division fast path valid, bit 1 = sqrt */
 int gjkepa_debug_fp64(gjkepa_ctx *ctx, int64_t n, const double *a, const double *b, double *q_fast,

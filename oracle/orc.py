@@ -148,3 +148,28 @@ def ground_truth(p1, p2):
     d = np.sort(-off)
     second = float(d[np.argmax(d > d[0] + 1e-9)]) if np.any(d > d[0] + 1e-9) else float("inf")
     return inside, float(-off[k]), nrm.copy(), second
+
+
+def apply_pose(shape_verts, shape_off, body_shape, pose):
+    """World-space hull store from body-space shapes and poses, with the arithmetic the product's pose kernel is
+    specified to use (include/gjkepa.h): x' = ((r00*x + r01*y) + r02*z) + tx, every operation rounded (numpy
+    evaluates element-wise products and sums separately: no FMA).  Returns (verts, hull_off).  Test
+    infrastructure, like everything under oracle/."""
+    shape_off = np.asarray(shape_off, np.int64); body_shape = np.asarray(body_shape, np.int64)
+    pose = np.asarray(pose, np.float64).reshape(-1, 12)
+    n = (shape_off[1:] - shape_off[:-1])[body_shape]
+    hull_off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    verts = np.empty(3 * int(hull_off[-1]))
+    for size in np.unique(n):                                   # vectorised per shape size
+        idx = np.nonzero(n == size)[0]
+        so = shape_off[body_shape[idx]]
+        g = (3 * so[:, None] + np.arange(3 * size)[None, :])
+        blk = np.asarray(shape_verts)[g].reshape(len(idx), 3, size)
+        x, y, z = blk[:, 0], blk[:, 1], blk[:, 2]
+        p = pose[idx]
+        wx = ((p[:, 0, None] * x + p[:, 1, None] * y) + p[:, 2, None] * z) + p[:, 9, None]
+        wy = ((p[:, 3, None] * x + p[:, 4, None] * y) + p[:, 5, None] * z) + p[:, 10, None]
+        wz = ((p[:, 6, None] * x + p[:, 7, None] * y) + p[:, 8, None] * z) + p[:, 11, None]
+        w = np.stack([wx, wy, wz], axis=1).reshape(len(idx), 3 * size)
+        verts[(3 * hull_off[idx][:, None] + np.arange(3 * size)[None, :])] = w
+    return verts, hull_off

@@ -306,3 +306,29 @@ def test_large_batch_equals_its_chunks(W, engine):
             for k in ("collision", "status", "depth", "normal"):
                 assert np.array_equal(part[k], whole[k][sl]), (n_vert, c, k)
     engine.set_max_hull_vertices(0)
+
+
+def test_resident_shapes_and_poses(W, orc, engine):
+    """gjkepa_shapes_upload + gjkepa_batch_posed_f64: the pose is applied on the device with the arithmetic stated in
+    include/gjkepa.h.  The result must be BIT-IDENTICAL to transforming on the host the same way (oracle/orc.py
+    apply_pose) and calling the world-space entry, and must match the oracle on those world-space hulls."""
+    configure(engine, 0)
+    for kw, mode in ((dict(n_shapes=500, n_bodies=60000, n_pairs=80000, kind="box"), "full"),
+                     (dict(n_shapes=300, n_bodies=40000, n_pairs=50000, kind="hull", n_lo=4, n_hi=40), "epa")):
+        pb = W.make_posed(**kw)
+        engine.upload_shapes(pb.shape_verts, pb.shape_off)
+        got = engine.batch_posed(pb.body_shape, pb.pose, pb.pair_a, pb.pair_b, mode=mode, want_contacts=True)
+        verts, hull_off = orc.apply_pose(pb.shape_verts, pb.shape_off, pb.body_shape, pb.pose)
+        engine.set_max_hull_vertices(int(np.diff(pb.shape_off).max()))   # the posed entry derives this bound from the shapes
+        same = engine.batch_host(verts, hull_off, pb.pair_a, pb.pair_b, mode=mode, want_contacts=True)
+        engine.set_max_hull_vertices(0)
+        nc = same["n_contacts"]
+        assert got["n_contacts"] == nc and np.array_equal(got["contact_index"][:nc], same["contact_index"][:nc])
+        for k in same:
+            if k not in ("n_contacts", "contact_index"):
+                assert np.array_equal(got[k], same[k]), k
+        assert 0.1 < got["collision"].mean() < 0.9
+        b = W.PairBatch(verts, hull_off, pb.pair_a, pb.pair_b)
+        check_against_oracle(orc, engine, b, mode, lanes=(0,))
+    with pytest.raises(Exception):
+        engine.batch_posed(pb.body_shape, pb.pose[:-1], pb.pair_a, pb.pair_b)

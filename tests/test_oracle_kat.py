@@ -151,3 +151,23 @@ def test_quickhull_standin_properties(orc):
     cube = np.array([[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)], float)
     grid = np.array([[x, y, z] for x in (0, .5, 1) for y in (0, .5, 1) for z in (0, .5, 1)], float)
     assert len(orc.quickhull(cube)) == 12 and len(orc.quickhull(grid)) == 12   # coplanar points swallowed
+
+
+def test_apply_pose_is_the_stated_arithmetic(orc, W):
+    """oracle/orc.py apply_pose (what a host would do before CALL GJKEPA, and what the pose kernel is specified to
+    do): x' = ((r00*x + r01*y) + r02*z) + tx, operation by operation, against a scalar evaluation; layout kept."""
+    pb = W.make_posed(40, 300, 10, kind="hull", n_lo=4, n_hi=12, seed=3)
+    verts, hull_off = orc.apply_pose(pb.shape_verts, pb.shape_off, pb.body_shape, pb.pose)
+    assert hull_off[0] == 0 and hull_off[-1] * 3 == verts.shape[0]
+    for b in (0, 7, 123, 299):
+        s = pb.body_shape[b]
+        n = int(pb.shape_off[s + 1] - pb.shape_off[s])
+        assert hull_off[b + 1] - hull_off[b] == n
+        blk = pb.shape_verts[3 * pb.shape_off[s]:3 * pb.shape_off[s + 1]].reshape(3, n)
+        w = verts[3 * hull_off[b]:3 * hull_off[b + 1]].reshape(3, n)
+        p = pb.pose[b]
+        for i in range(n):
+            x, y, z = (float(v) for v in blk[:, i])
+            for ax in range(3):
+                want = ((float(p[3 * ax]) * x + float(p[3 * ax + 1]) * y) + float(p[3 * ax + 2]) * z) + float(p[9 + ax])
+                assert w[ax, i] == want

@@ -420,7 +420,10 @@ inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32
         a.item_list = nullptr; a.item_count = nullptr;
         a.queue_head = counters + 1;
         a.ovf_items = ovf1; a.ovf_count = counters + 4;
-        rc = launch_one<16, 36, 68, 64>(a, sm_count, st);
+#ifndef EPA3_LP
+#define EPA3_LP 16
+#endif
+        rc = launch_one<EPA3_LP, 36, 68, 64>(a, sm_count, st);
         if (rc) return rc;
         ++nl;
         b.item_list = ovf1; b.item_count = counters + 4;

@@ -199,6 +199,10 @@ __device__ __forceinline__ void push_contacts(const BatchArgs &a, bool coll, int
 #ifndef GJK_INIT_MIN_CTAS
 #define GJK_INIT_MIN_CTAS 4
 #endif
+#ifndef GJK_INIT_THREADS
+#define GJK_INIT_THREADS 128
+#endif
+constexpr int INIT_THREADS = GJK_INIT_THREADS;
 #ifndef GJK_WALK_MIN_CTAS
 #define GJK_WALK_MIN_CTAS 3
 #endif
@@ -231,7 +235,7 @@ __device__ __forceinline__ TileMeta load_tile_meta(const BatchArgs &a, const Til
 }
 
 template <bool FUSE>
-__global__ void __launch_bounds__(TILE, GJK_INIT_MIN_CTAS)
+__global__ void __launch_bounds__(INIT_THREADS, GJK_INIT_MIN_CTAS)
 gjk_init_kernel(TwoStageArgs ta)
 {
     extern __shared__ __align__(16) char sm2[];
@@ -241,9 +245,9 @@ gjk_init_kernel(TwoStageArgs ta)
     char *col = sm2 + (size_t)warp * ta.col_units * T2_PITCH + lane * 16;
     const Lanes<1> g;
     const int64_t n_tiles = (a.n_pairs + 31) / 32;
-    const int64_t n_warps = (int64_t)gridDim.x * (TILE / 32);
+    const int64_t n_warps = (int64_t)gridDim.x * (INIT_THREADS / 32);
 
-    int64_t tile = (int64_t)blockIdx.x * (TILE / 32) + warp;
+    int64_t tile = (int64_t)blockIdx.x * (INIT_THREADS / 32) + warp;
     TileMeta cur = load_tile_meta(a, load_tile_ids(a, tile, n_tiles, lane));
     TileMeta nx = load_tile_meta(a, load_tile_ids(a, tile + n_warps, n_tiles, lane));
     TileIds nid = load_tile_ids(a, tile + 2 * n_warps, n_tiles, lane);

@@ -340,18 +340,20 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         ta.q.oa = ctx->d_seed_off; ta.q.ob = ctx->d_seed_off + ctx->cap_seed;
         ta.q.count = ctx->d_counters + 6; ta.q.head = ctx->d_counters + 7; ta.q.cap = ctx->cap_seed;
         const size_t smem = (size_t)ta.col_units * gjk::T2_PITCH * (gjk::TILE / 32);
+        const size_t smem_i = (size_t)ta.col_units * gjk::T2_PITCH * (gjk::INIT_THREADS / 32);
         const int64_t n_ctas = (n_pairs + gjk::TILE - 1) / gjk::TILE;
+        const int64_t n_ctas_i = (n_pairs + gjk::INIT_THREADS - 1) / gjk::INIT_THREADS;
         int per_sm = 0;
         if (fuse) {
-            CU(cudaFuncSetAttribute(gjk::gjk_init_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_kernel<true>, gjk::TILE, smem));
+            CU(cudaFuncSetAttribute(gjk::gjk_init_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_kernel<true>, gjk::INIT_THREADS, smem_i));
             const int64_t res = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
-            gjk::gjk_init_kernel<true><<<(unsigned)(n_ctas < res ? n_ctas : res), gjk::TILE, smem, st>>>(ta);
+            gjk::gjk_init_kernel<true><<<(unsigned)(n_ctas_i < res ? n_ctas_i : res), gjk::INIT_THREADS, smem_i, st>>>(ta);
         } else {
-            CU(cudaFuncSetAttribute(gjk::gjk_init_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_kernel<false>, gjk::TILE, smem));
+            CU(cudaFuncSetAttribute(gjk::gjk_init_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_kernel<false>, gjk::INIT_THREADS, smem_i));
             const int64_t res = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
-            gjk::gjk_init_kernel<false><<<(unsigned)(n_ctas < res ? n_ctas : res), gjk::TILE, smem, st>>>(ta);
+            gjk::gjk_init_kernel<false><<<(unsigned)(n_ctas_i < res ? n_ctas_i : res), gjk::INIT_THREADS, smem_i, st>>>(ta);
         }
         ++ctx->launches;
         CU(cudaFuncSetAttribute(gjk::gjk_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -471,7 +473,8 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         e.version = version; e.tol_ff = tol_ff; e.full = (mode == GJKEPA_MODE_FULL);
         e.colli_type = colli_type; e.nearest = nearest; e.normal = normal; e.point = point;
         e.depth = depth; e.status = status; e.result = nullptr;
-        const bool k4 = !ctx->epa_general && mode == GJKEPA_MODE_FULL;     // contact epilogue as its own kernel
+        // contact epilogue as its own kernel (always for version 2, which the in-kernel epilogue does not have)
+        const bool k4 = mode == GJKEPA_MODE_FULL && (!ctx->epa_general || version == 2);
         if (k4) { e.full = false; e.result = ctx->d_wl_simplex; }
         int nl = 0;
         if (prof) CU(cudaEventRecord(ctx->ev[4], st));

@@ -54,7 +54,7 @@ typedef struct gjkepa_ctx gjkepa_ctx;
 #define GJKEPA_ST_EPA_CAP      (1u << 24)  /* F:299 */
 #define GJKEPA_ST_STOP         (1u << 25)
 #define GJKEPA_ST_HULL_FAIL    (1u << 26)  /* EPA polytope degenerate or over capacity */
-#define GJKEPA_ST_BAD_VERSION  (1u << 27)  /* version_ not 1 or 3 (F:329-340) */
+#define GJKEPA_ST_BAD_VERSION  (1u << 27)  /* version_ not 1, 2 or 3 (F:329-340: the reference PAUSEs and STOPs) */
 #define GJKEPA_ST_H1           (1u << 28)  /* F:140 path (simplex row 4 defined as zero) */
 #define GJKEPA_ST_TOPO_WARN    (1u << 29)  /* diagnostic: an EPA visible region was not a disk */
 #define GJKEPA_ST_COLD_MATH    (1u << 30)  /* diagnostic: an operand left the straight-line sqrt/div range and

@@ -567,6 +567,116 @@ static void collision_point_01(const hull_t *a, const hull_t *b, const double nr
     }
 }
 
+/* ---- get_collisionPoint_02, F:457-696.  The reference keeps the support vertices in GCLIB_List's List_Array3d
+ * (un-vendored; used only as an append-only array: reset / append / getSize / atIndex, F:466-468, F:526, F:540),
+ * restated here as plain arrays in append order. ---- */
+#define CP2_MAX 256
+
+/* AddAllSupports, F:510-530: every vertex within tol of the strict maximum along nml, in index order */
+static int all_supports(const hull_t *h, const double nml[3], double tol, double (*out)[3])
+{
+    double mx = -DBL_MAX, v[3]; int i, n = 0;
+    for (i = 0; i < h->n; ++i) { hull_pt(h, i, v); double t = dot3(nml, v); if (t > mx) mx = t; }
+    for (i = 0; i < h->n; ++i) {
+        hull_pt(h, i, v);
+        double t = dot3(nml, v);
+        if (t > mx - tol && n < CP2_MAX) { memcpy(out[n], v, 3 * sizeof(double)); ++n; }
+    }
+    return n;
+}
+
+/* FOOT_PL, F:1496-1510: foot of P on the line through V1, V2 */
+static void foot_pl(const double p[3], const double v1[3], const double v2[3], double r[3])
+{
+    double d[3], u[3], pv[3];
+    sub3(v2, v1, d); utzvec(d, u); sub3(p, v1, pv);
+    double t = dot3(pv, u);
+    r[0] = v1[0] + t * u[0]; r[1] = v1[1] + t * u[1]; r[2] = v1[2] + t * u[2];
+}
+
+/* FOOT_LL, F:1445-1491: feet of the common perpendicular of two lines (parallel: midpoint of the first) */
+static void foot_ll(const double p1[3], const double q1[3], const double p2[3], const double q2[3], double f1[3], double f2[3])
+{
+    double d1[3], d2[3], r[3];
+    sub3(q1, p1, d1); sub3(q2, p2, d2); sub3(p1, p2, r);
+    double a = dot3(d1, d1), b = dot3(d1, d2), c = dot3(d1, r), e = dot3(d2, d2), f = dot3(d2, r);
+    double d = a * e - b * b;
+    int i;
+    if (fabs(d) < 1.0e-12) {
+        for (i = 0; i < 3; ++i) f1[i] = (p1[i] + q1[i]) / 2.0;
+        foot_pl(f1, p2, q2, f2);
+    } else {
+        double s = (b * f - c * e) / d, t = (a * f - b * c) / d;
+        for (i = 0; i < 3; ++i) { f1[i] = p1[i] + s * (q1[i] - p1[i]); f2[i] = p2[i] + t * (q2[i] - p2[i]); }
+    }
+}
+
+/* SORT_CLOCK, F:1517-1575: polygon vertices in counter-clockwise order around their centroid, starting from
+ * the first.  Quirks kept: the angle is reduced with a SINGLE-precision 2*pi (F:1547); OVERLAP (all points within
+ * 1e-12, F:1399-1418) returns before anything is written -- the result is then undefined in the reference, here
+ * the input order.  IS_POINT_IN_ORDERED_POINTS compares against ALL rows of the result, written or not (F:1560-
+ * 1571, uninitialised memory in the reference); only the rows already written are compared here. */
+static void sort_clock(double (*pts)[3], int n, double (*out)[3])
+{
+    int i, j, k, overlap = 1;
+    for (i = 0; i < n - 1 && overlap; ++i)
+        for (j = i + 1; j < n && overlap; ++j)
+            for (k = 0; k < 3; ++k) if (fabs(pts[i][k] - pts[j][k]) > 1.0e-12) { overlap = 0; break; }
+    memcpy(out, pts, (size_t)n * 3 * sizeof(double));
+    if (overlap) return;
+    double cen[3] = {0.0, 0.0, 0.0}, v1[3], v2[3], nrm[3], cr[3];
+    for (k = 0; k < 3; ++k) { double sum = 0.0; for (i = 0; i < n; ++i) sum = sum + pts[i][k]; cen[k] = sum / (double)n; }
+    sub3(pts[1], pts[0], v1); sub3(pts[2], pts[0], v2); cross3(v1, v2, nrm);
+    const double two_pi = (double)(2.0f * acosf(-1.0f));
+    for (i = 1; i < n; ++i) {
+        double min_angle = DBL_MAX; int index = -1;
+        for (j = 0; j < n; ++j) {
+            int used = 0, m;
+            for (m = 0; m < i; ++m) if (pts[j][0] == out[m][0] && pts[j][1] == out[m][1] && pts[j][2] == out[m][2]) { used = 1; break; }
+            if (used) continue;
+            sub3(pts[j], cen, v1); sub3(out[i - 1], cen, v2);
+            cross3(v2, v1, cr);
+            double ang = atan2(dot3(nrm, cr), dot3(v1, v2));
+            ang = fmod(ang + two_pi, two_pi);
+            if (ang < 0.0) ang += two_pi;                            /* MODULO takes the sign of its second argument */
+            if (ang < min_angle) { min_angle = ang; index = j; }
+        }
+        if (index < 0) index = 0;                                     /* duplicates exhausted the candidates: reference reads row -1 */
+        memcpy(out[i], pts[index], 3 * sizeof(double));
+    }
+}
+
+static void collision_point_02(const hull_t *a, const hull_t *b, const double nrm[3], double res[3])
+{
+    static _Thread_local double s1[CP2_MAX][3], s2[CP2_MAX][3], sorted[CP2_MAX][3];
+    double nd[3];
+    int i, k;
+    res[0] = res[1] = res[2] = 0.0;
+    neg3(nrm, nd);
+    const int n1 = all_supports(a, nrm, 1.0e-1, s1), n2 = all_supports(b, nd, 1.0e-1, s2);
+    if (n1 == 1 && n2 == 1) { for (i = 0; i < 3; ++i) res[i] = (s1[0][i] + s2[0][i]) / 2.0; }          /* case_01 */
+    else if (n1 == 1 && n2 >= 2) memcpy(res, s1[0], 3 * sizeof(double));                                 /* case_02 */
+    else if (n1 >= 2 && n2 == 1) memcpy(res, s2[0], 3 * sizeof(double));
+    else if (n1 == 2 && n2 == 2) {                                                                        /* case_03 */
+        double f1[3], f2[3];
+        foot_ll(s1[0], s1[1], s2[0], s2[1], f1, f2);
+        for (i = 0; i < 3; ++i) res[i] = (f1[i] + f2[i]) / 2.0;
+    } else if ((n1 == 2 && n2 >= 3) || (n1 >= 3 && n2 == 2)) {                                            /* case_04 */
+        double (*poly)[3] = (n1 >= 3) ? s1 : s2; const int np = (n1 >= 3) ? n1 : n2;
+        double (*seg)[3] = (n1 >= 3) ? s2 : s1;
+        sort_clock(poly, np, sorted);
+        int c = 0;
+        for (i = 0; i < 2; ++i) if (orc_is_inside_pf(&sorted[0][0], np, seg[i])) ++c;
+        if (c == 0) {                                                                                     /* case_04_1 */
+            double cen[3];
+            for (k = 0; k < 3; ++k) { double sum = 0.0; for (i = 0; i < np; ++i) sum = sum + poly[i][k]; cen[k] = sum / (double)np; }
+            foot_pl(cen, seg[0], seg[1], res);
+        } else for (i = 0; i < 3; ++i) res[i] = (seg[0][i] + seg[1][i]) * 0.5;                            /* case_04_2 / _3 */
+    } else if (n1 >= 3 && n2 >= 3) {                                                                      /* case_05 */
+        for (k = 0; k < 3; ++k) { double sum = 0.0; for (i = 0; i < n1; ++i) sum = sum + s1[i][k]; res[k] = sum / (double)n1; }
+    }
+}
+
 /* get_collisionPoint_03, F:426-452 */
 static void collision_point_03(const hull_t *a, const hull_t *b, const double nrm[3], double res[3], double nnew[3])
 {
@@ -620,11 +730,12 @@ static void epa_solve(int version, double tol_ff, const hull_t *a, const hull_t 
 
     nearest_points(a, b, out->normal, out->nearest);                              /* F:326 */
     if (version == 1) collision_point_01(a, b, out->normal, out->point);
+    else if (version == 2) collision_point_02(a, b, out->normal, out->point);
     else if (version == 3) {
         double nnew[3];
         collision_point_03(a, b, out->normal, out->point, nnew);
         memcpy(out->normal, nnew, sizeof nnew);
-    } else { out->status |= ORC_ST_BAD_VERSION; }                                  /* version 2 needs GCLIB_List; else STOP */
+    } else { out->status |= ORC_ST_BAD_VERSION; }                                  /* the reference PAUSEs and STOPs, F:336-339 */
     out->colli_type = collision_type(a, b, out->normal, tol_ff);                  /* F:343 */
 }
 

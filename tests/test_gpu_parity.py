@@ -129,6 +129,15 @@ def test_version3_turntable_contact_point(W, orc, engine):
     check_against_oracle(orc, engine, W.make_pairs("hull", 20000, 0.5, seed=8, n_vert=12), "full", version=3)
 
 
+def test_version2_general_contact_point(W, orc, engine):
+    """version_ = 2 (get_collisionPoint_02, F:457-696): vertex/vertex, vertex/face, edge/edge (FOOT_LL), edge/face
+    (SORT_CLOCK + IS_INSIDE_PF + FOOT_PL) and face/face branches, on boxes (faces and edges in contact), small hulls
+    and the planted axis-aligned cubes."""
+    check_against_oracle(orc, engine, W.make_pairs("box8", 40000, 0.8, seed=17), "full", version=2, lanes=(0, "gen", 4))
+    check_against_oracle(orc, engine, W.make_pairs("hull", 30000, 0.4, seed=18, n_vert=10), "full", version=2, lanes=(0, "gen"))
+    check_against_oracle(orc, engine, W.make_pairs("hull", 10000, 0.7, seed=19, n_vert=40), "full", version=2, lanes=(0,))
+
+
 def test_tolff_threshold_is_honoured(W, orc, engine):
     check_against_oracle(orc, engine, W.make_pairs("box8", 20000, 0.8, seed=9), "full", tol_ff=0.05)
 

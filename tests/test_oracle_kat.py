@@ -134,7 +134,9 @@ def test_version3_and_bad_version(orc, W):
     r3 = orc.pair(a, b, version=3)
     assert np.allclose(r3["normal"], [1, 0, 0]) and abs(r3["point"][2] - a[:, 2].mean()) < 1e-15
     r2 = orc.pair(a, b, version=2)
-    assert r2["status"] & orc.ST_BAD_VERSION
+    assert not (r2["status"] & orc.ST_BAD_VERSION) and np.allclose(r2["point"], [0.5, 0, 0], atol=1e-12)
+    r7 = orc.pair(a, b, version=7)                                    # the reference PAUSEs and STOPs (F:336-339)
+    assert r7["status"] & orc.ST_BAD_VERSION and r7["collision"] and abs(r7["depth"] - 0.5) < 1e-12
 
 
 def test_quickhull_standin_properties(orc):

@@ -54,6 +54,7 @@ struct gjkepa_ctx {
     void *d_scan_tmp = nullptr; size_t cap_scan_tmp = 0;
     void *d_stage2 = nullptr; size_t cap_stage2 = 0;
     unsigned long long *h_counters = nullptr;      // pinned
+    char *h_small = nullptr, *d_small = nullptr;   // packed staging for tiny batches (pinned host mirror + device block)
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -61,6 +62,8 @@ struct gjkepa_ctx {
 };
 
 namespace {
+
+constexpr int32_t GJKEPA_MODE_NO_CLEAR_ = 1 << 8;      // internal: the output block was cleared by the caller
 
 int fail(gjkepa_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
 {
@@ -149,6 +152,8 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
     if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
     if (ctx->d_stage2) cudaFree(ctx->d_stage2);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
+    if (ctx->d_small) cudaFree(ctx->d_small);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
@@ -250,6 +255,8 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                             uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
+    const bool no_clear = (mode & GJKEPA_MODE_NO_CLEAR_) != 0;
+    mode &= ~GJKEPA_MODE_NO_CLEAR_;
     if (n_pairs < 0 || n_hulls < 0 || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL)
         return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or mode");
     if (n_pairs > 0 && (!verts || !hull_off || !pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
@@ -257,7 +264,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     cudaStream_t st = ctx->stream;
 
     // outputs of non-colliding pairs are zero (F:65-71)
-    if (n_pairs > 0) {
+    if (n_pairs > 0 && !no_clear) {
         if (colli_type) CU(cudaMemsetAsync(colli_type, 0, (size_t)n_pairs * sizeof(int32_t), st));
         if (nearest)    CU(cudaMemsetAsync(nearest, 0, (size_t)n_pairs * 6 * sizeof(double), st));
         if (normal)     CU(cudaMemsetAsync(normal, 0, (size_t)n_pairs * 3 * sizeof(double), st));
@@ -288,7 +295,10 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
             ctx->cap_wl = ncap;
         }
     }
-    const bool use_tile = ctx->lanes == 0;
+    // tiny batches (the drop-in single-pair call above all) are launch-latency bound: one free-running 4-lane GJK
+    // kernel and the general EPA kernel instead of the staged pipelines (4 launches instead of 9)
+    const bool tiny = ctx->lanes == 0 && n_pairs <= 256;
+    const bool use_tile = ctx->lanes == 0 && !tiny;
     if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf, ctx->cap_ovf, n_pairs); if (rc) return rc; }
     if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf2, ctx->cap_ovf2, n_pairs); if (rc) return rc; }
 
@@ -444,7 +454,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
             }
         }
     } else {
-        const int L = ctx->lanes;
+        const int L = tiny ? 4 : ctx->lanes;
         const int threads = 128;
         const int64_t groups_per_block = threads / L;
         int64_t blocks = (n_pairs + groups_per_block - 1) / groups_per_block;
@@ -478,7 +488,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         if (k4) { e.full = false; e.result = ctx->d_wl_simplex; }
         int nl = 0;
         if (prof) CU(cudaEventRecord(ctx->ev[4], st));
-        if (ctx->epa_general) rc = epa::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_counters, &nl);
+        if (ctx->epa_general || tiny) rc = epa::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_counters, &nl);
         else                  rc = epa3::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_ovf2, ctx->d_counters,
                                                 ctx->max_hull_hint > 0 && ctx->max_hull_hint <= 32, &nl);
         if (rc) return fail(ctx, GJKEPA_ERR_CUDA, "epa launch", (cudaError_t)rc);
@@ -513,6 +523,53 @@ int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     const int64_t n_vert = hull_off[n_hulls];
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const bool need_flags = collision || contact_index || n_contacts;
+    {   // Tiny batches (the drop-in single-pair call): every copy or memset is ~10 us of driver time, so inputs travel
+        // as ONE block from a pinned mirror, all outputs come back as ONE block, one memset clears them.
+        constexpr size_t SMALL = 96 * 1024;
+        auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+        const size_t i_verts = 0, i_off = a16((size_t)n_vert * 24), i_pa = i_off + a16((size_t)(n_hulls + 1) * 8),
+                     i_pb = i_pa + a16((size_t)n_pairs * 4), in_bytes = i_pb + a16((size_t)n_pairs * 4);
+        const size_t q_col = in_bytes, q_type = q_col + a16((size_t)n_pairs), q_near = q_type + a16((size_t)n_pairs * 4),
+                     q_nrm = q_near + a16((size_t)n_pairs * 48), q_pt = q_nrm + a16((size_t)n_pairs * 24),
+                     q_dep = q_pt + a16((size_t)n_pairs * 24), q_st = q_dep + a16((size_t)n_pairs * 8),
+                     all_bytes = q_st + a16((size_t)n_pairs * 4);
+        if (n_pairs <= 256 && all_bytes <= SMALL) {
+            if (!ctx->h_small) {
+                cudaError_t e = cudaHostAlloc((void **)&ctx->h_small, SMALL, cudaHostAllocDefault);
+                if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_small, SMALL);
+                if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "small staging", e);
+            }
+            char *h = ctx->h_small, *d = ctx->d_small;
+            std::memcpy(h + i_verts, verts, (size_t)n_vert * 24);
+            std::memcpy(h + i_off, hull_off, (size_t)(n_hulls + 1) * 8);
+            std::memcpy(h + i_pa, pair_a, (size_t)n_pairs * 4);
+            std::memcpy(h + i_pb, pair_b, (size_t)n_pairs * 4);
+            CU(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
+            CU(cudaMemsetAsync(d + q_col, 0, all_bytes - q_col, st));           // F:65-71 for every output at once
+            int rc = gjkepa_batch_device_f64(ctx, version, tol_ff, n_hulls, (const double *)(d + i_verts), (const int64_t *)(d + i_off),
+                n_pairs, (const int32_t *)(d + i_pa), (const int32_t *)(d + i_pb), mode | GJKEPA_MODE_NO_CLEAR_,
+                (uint8_t *)(d + q_col), colli_type ? (int32_t *)(d + q_type) : nullptr, nearest ? (double *)(d + q_near) : nullptr,
+                normal ? (double *)(d + q_nrm) : nullptr, point ? (double *)(d + q_pt) : nullptr, depth ? (double *)(d + q_dep) : nullptr,
+                status ? (uint32_t *)(d + q_st) : nullptr, nullptr, nullptr);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(h + q_col, d + q_col, all_bytes - q_col, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            const uint8_t *hf = (const uint8_t *)(h + q_col);
+            if (collision) std::memcpy(collision, hf, (size_t)n_pairs);
+            if (colli_type) std::memcpy(colli_type, h + q_type, (size_t)n_pairs * 4);
+            if (nearest) std::memcpy(nearest, h + q_near, (size_t)n_pairs * 48);
+            if (normal) std::memcpy(normal, h + q_nrm, (size_t)n_pairs * 24);
+            if (point) std::memcpy(point, h + q_pt, (size_t)n_pairs * 24);
+            if (depth) std::memcpy(depth, h + q_dep, (size_t)n_pairs * 8);
+            if (status) std::memcpy(status, h + q_st, (size_t)n_pairs * 4);
+            if (n_contacts || contact_index) {
+                int64_t cnt = 0;
+                for (int64_t i = 0; i < n_pairs; ++i) if (hf[i]) { if (contact_index) contact_index[cnt] = (int32_t)i; ++cnt; }
+                if (n_contacts) *n_contacts = cnt;
+            }
+            return GJKEPA_OK;
+        }
+    }
     size_t o_verts = 0;
     size_t o_off   = o_verts + al((size_t)n_vert * 3 * sizeof(double));
     size_t o_pa    = o_off + al((size_t)(n_hulls + 1) * sizeof(int64_t));

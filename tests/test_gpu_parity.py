@@ -341,3 +341,15 @@ def test_resident_shapes_and_poses(W, orc, engine):
         check_against_oracle(orc, engine, b, mode, lanes=(0,))
     with pytest.raises(Exception):
         engine.batch_posed(pb.body_shape, pb.pose[:-1], pb.pair_a, pb.pair_b)
+
+
+def test_large_hulls_take_the_general_kernels(W, orc, engine):
+    """Hulls beyond every staging buffer (100 and 200 vertices; 65 + 64 straddles the 128-vertex EPA buffer): the
+    4-lane kernel reading global memory, the general EPA kernel with unstaged hulls and the contact kernel's scans."""
+    for n_vert, n_pairs, sigma in ((100, 6000, 0.8), (200, 2500, 0.9), (65, 6000, 0.8)):
+        b = W.make_pairs("hull", n_pairs, sigma, seed=50 + n_vert, n_vert=n_vert)
+        for version in (1, 2):
+            ref = check_against_oracle(orc, engine, b, "full", lanes=(0, "gen"), version=version)
+        assert 0.2 < ref["collision"].mean() < 0.98
+    b = W.make_mixed(8000, 0.4, seed=61, n_lo=50, n_hi=150)
+    check_against_oracle(orc, engine, b, "full", lanes=(0, 4))

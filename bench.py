@@ -383,6 +383,46 @@ def main():
             "h2d_bytes_per_step": int(sum(x.nbytes for x in hp)), "d2h_bytes_per_step": int(pb.n_pairs),
             "colliding_fraction": float(po["collision"].mean()),
             "api": "gjkepa_batch_posed_f64 (C ABI, pinned host buffers; pose applied on the device)"}
+    if not args.no_extra and args.workload == "cfg2" and world == 1:
+        # upstream of the path: candidate pairs built on the device (gjkepa_broadphase_posed_f64) for 1M posed bodies
+        # instancing 1000 resident hull(16) shapes on a jittered lattice -- the cfg5 kind of scene
+        rng = np.random.default_rng(99)
+        nb = args.pairs
+        ps = W.make_posed(n_shapes=1000, n_bodies=2, n_pairs=1, kind="hull", n_lo=16, n_hi=16, seed=5)
+        eng.upload_shapes(ps.shape_verts, ps.shape_off)
+        g = int(np.ceil(nb ** (1.0 / 3.0)))
+        idx = np.arange(nb)
+        site = np.stack([idx % g, (idx // g) % g, idx // (g * g)], axis=1).astype(np.float64)
+        t = (site + rng.uniform(-0.3, 0.3, size=(nb, 3))) * 1.6
+        pose = np.concatenate([W._quat_rot(rng, nb).reshape(nb, 9), t], axis=1)
+        shp = rng.integers(0, 1000, size=nb).astype(np.int32)
+        hb = []
+        for x in (shp, pose):
+            tt, npv = pin(x); keep.append(tt); hb.append(npv)
+        cap = 24 * nb
+        ta = torch.empty((cap,), dtype=torch.int32, pin_memory=True); tb_ = torch.empty((cap,), dtype=torch.int32, pin_memory=True)
+        keep += [ta, tb_]
+        import ctypes as C
+        tot = C.c_int64(0)
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+
+        def bp_call():
+            rc = eng._L.gjkepa_broadphase_posed_f64(eng._h, nb, vp(hb[0]), vp(hb[1]), cap, C.c_void_p(ta.data_ptr()),
+                                                    C.c_void_p(tb_.data_ptr()), C.cast(C.byref(tot), C.c_void_p))
+            eng._check(rc, "gjkepa_broadphase_posed_f64")
+        for _ in range(2):
+            bp_call()
+        kb = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(kb):
+            bp_call()
+        dtb = (time.perf_counter() - t0) / kb
+        line.setdefault("extra", {})["e2e_broadphase"] = {
+            "workload": f"{nb} posed hull(16) bodies (1000 resident shapes) on a jittered lattice, pitch 1.6",
+            "bodies_per_s": nb / dtb, "candidate_pairs": int(tot.value), "candidate_pairs_per_s": tot.value / dtb,
+            "ms_per_step": dtb * 1e3, "h2d_bytes_per_step": int(sum(x.nbytes for x in hb)),
+            "d2h_bytes_per_step": int(8 * min(tot.value, cap)),
+            "api": "gjkepa_broadphase_posed_f64 (C ABI, pinned host buffers; pairs passing the reference's sphere test F:1185)"}
     emit(line)
     eng.close()
     if world > 1:

@@ -181,6 +181,39 @@ class Engine:
             out["n_contacts"] = int(nc.value)
         return out
 
+    # ---- candidate pairs on the device (gjkepa_broadphase_f64 / gjkepa_broadphase_posed_f64) ----
+    def _broadphase(self, call, what: str, cap: int):
+        """Runs `call(cap, pair_a, pair_b, n_pairs)`; grows the buffers once when the first guess was too small."""
+        cap = max(int(cap), 0)
+        while True:
+            pa, pb = np.empty(cap, np.int32), np.empty(cap, np.int32)
+            total = C.c_int64(0)
+            self._check(call(cap, _np_ptr(pa) if cap else C.c_void_p(0), _np_ptr(pb) if cap else C.c_void_p(0),
+                             C.cast(C.byref(total), C.c_void_p)), what)
+            if total.value <= cap:
+                return pa[:total.value], pb[:total.value]
+            cap = int(total.value)
+
+    def broadphase(self, verts, hull_off, cap: int = 0):
+        """All pairs of hulls (a < b) that pass the reference's spherical-envelope test (F:1165-1188), found through
+        a uniform grid on the device; returns (pair_a, pair_b), int32, in a deterministic order.  HOST buffers."""
+        verts = np.ascontiguousarray(verts, dtype=np.float64)
+        hull_off = np.ascontiguousarray(hull_off, dtype=np.int64)
+        nh = int(hull_off.shape[0] - 1)
+        return self._broadphase(
+            lambda c, pa, pb, tot: self._L.gjkepa_broadphase_f64(self._h, nh, _np_ptr(verts), _np_ptr(hull_off), c, pa, pb, tot),
+            "gjkepa_broadphase_f64", cap or 8 * nh)
+
+    def broadphase_posed(self, body_shape, pose, cap: int = 0):
+        """Same over posed bodies of the resident shape store (upload_shapes); pose as in batch_posed."""
+        body_shape = np.ascontiguousarray(body_shape, dtype=np.int32)
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        nb = int(body_shape.shape[0])
+        assert pose.size == 12 * nb
+        return self._broadphase(
+            lambda c, pa, pb, tot: self._L.gjkepa_broadphase_posed_f64(self._h, nb, _np_ptr(body_shape), _np_ptr(pose), c, pa, pb, tot),
+            "gjkepa_broadphase_posed_f64", cap or 8 * nb)
+
     # ---- DEVICE buffers (torch CUDA tensors already resident in HBM), asynchronous ----
     def batch_device(self, verts, hull_off, pair_a, pair_b, mode="full", version: int = 1,
                      tol_ff: float = 1.0, out: Optional[dict] = None, want_status: bool = True,

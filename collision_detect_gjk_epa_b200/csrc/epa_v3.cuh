@@ -229,8 +229,11 @@ __device__ __forceinline__ int mesh_insert(const Grp<LP> &g, Mesh<VC, FC, HC> &P
 
 constexpr int WARPS = 4;
 
+#ifndef EPA3_MIN_CTAS
+#define EPA3_MIN_CTAS 5
+#endif
 template <int LP, int VC, int FC, int HC>
-__global__ void __launch_bounds__(WARPS * 32, 5)
+__global__ void __launch_bounds__(WARPS * 32, EPA3_MIN_CTAS)
 epa3_kernel(EpaArgs a)
 {
     static_assert(FC <= 255 && VC <= 255, "ids are bytes");

@@ -13,8 +13,10 @@
 #include "epa_v3.cuh"
 #include "contact_kernel.cuh"
 #include "pose_kernel.cuh"
+#include "broadphase.cuh"
 
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -53,6 +55,7 @@ struct gjkepa_ctx {
     int64_t *d_world_off = nullptr; int64_t cap_world_off = 0;   // sizes, then offsets (n_bodies + 1 each)
     void *d_scan_tmp = nullptr; size_t cap_scan_tmp = 0;
     void *d_stage2 = nullptr; size_t cap_stage2 = 0;
+    void *d_bp = nullptr; size_t cap_bp = 0;                     // broad-phase workspace
     unsigned long long *h_counters = nullptr;      // pinned
     char *h_small = nullptr, *d_small = nullptr;   // packed staging for tiny batches (pinned host mirror + device block)
     // optional per-kernel timing (CUDA events on the launching stream)
@@ -151,6 +154,7 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
     if (ctx->d_world_off) cudaFree(ctx->d_world_off);
     if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
     if (ctx->d_stage2) cudaFree(ctx->d_stage2);
+    if (ctx->d_bp) cudaFree(ctx->d_bp);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->d_small) cudaFree(ctx->d_small);
@@ -627,6 +631,96 @@ int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     return GJKEPA_OK;
 }
 
+// Kp: world-space hull store of n_bodies posed shapes (device inputs), left in ctx->d_world; *d_off_out = its offsets
+static int posed_world(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t *d_body_shape, const double *d_pose, int64_t **d_off_out)
+{
+    cudaStream_t st = ctx->stream;
+    // world store sized by the largest shape (no device->host round trip for the exact total)
+    const int64_t need_world = n_bodies * ctx->max_shape_verts * 3;
+    if (need_world > ctx->cap_world) {
+        if (ctx->d_world) { cudaFree(ctx->d_world); ctx->d_world = nullptr; ctx->cap_world = 0; }
+        cudaError_t e = cudaMalloc((void **)&ctx->d_world, (size_t)need_world * sizeof(double));
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc world store", e);
+        ctx->cap_world = need_world;
+    }
+    if (2 * (n_bodies + 1) > ctx->cap_world_off) {
+        if (ctx->d_world_off) { cudaFree(ctx->d_world_off); ctx->d_world_off = nullptr; ctx->cap_world_off = 0; }
+        cudaError_t e = cudaMalloc((void **)&ctx->d_world_off, (size_t)2 * (n_bodies + 1) * sizeof(int64_t));
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc world offsets", e);
+        ctx->cap_world_off = 2 * (n_bodies + 1);
+    }
+    int64_t *d_sizes = ctx->d_world_off, *d_off = ctx->d_world_off + (n_bodies + 1);
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_sizes, d_off, (int)(n_bodies + 1), st));
+    if (tmp_bytes > ctx->cap_scan_tmp) {
+        if (ctx->d_scan_tmp) { cudaFree(ctx->d_scan_tmp); ctx->d_scan_tmp = nullptr; ctx->cap_scan_tmp = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_scan_tmp, tmp_bytes + 256);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc scan scratch", e);
+        ctx->cap_scan_tmp = tmp_bytes + 256;
+    }
+    const int threads = 256;
+    pose::body_sizes_kernel<<<(unsigned)((n_bodies + 1 + threads - 1) / threads), threads, 0, st>>>(
+        d_body_shape, ctx->d_shape_off, n_bodies, ctx->n_shapes, d_sizes);
+    size_t tb = ctx->cap_scan_tmp;
+    CU(cub::DeviceScan::ExclusiveSum(ctx->d_scan_tmp, tb, d_sizes, d_off, (int)(n_bodies + 1), st));
+    int64_t blocks = (n_bodies * 8 + threads - 1) / threads;
+    const int64_t max_blocks = (int64_t)ctx->sm_count * 32;
+    if (blocks > max_blocks) blocks = max_blocks;
+    pose::apply_pose_kernel<<<(unsigned)blocks, threads, 0, st>>>(ctx->d_shape_verts, ctx->d_shape_off,
+        d_body_shape, d_pose, d_off, n_bodies, ctx->n_shapes, ctx->d_world);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    *d_off_out = d_off;
+    return GJKEPA_OK;
+}
+
+// Kb: candidate pairs of a device-resident hull store into device buffers; *h_total = number of passing pairs (synchronises)
+static int broadphase_device(gjkepa_ctx *ctx, int64_t n, const double *d_verts, const int64_t *d_hull_off,
+                             int64_t cap, int32_t *d_pa, int32_t *d_pb, int64_t *h_total)
+{
+    cudaStream_t st = ctx->stream;
+    int rc = ensure(ctx, ctx->d_sphere, ctx->cap_sphere, n);
+    if (rc) return rc;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t sort_tmp = 0, scan_tmp = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                       (const int32_t *)nullptr, (int32_t *)nullptr, (int)n, 0, 63, st));
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const int64_t *)nullptr, (int64_t *)nullptr, (int)(n + 1), st));
+    const size_t o_bounds = 0, o_k0 = al(sizeof(bp::Bounds)), o_k1 = o_k0 + al((size_t)n * 8), o_i0 = o_k1 + al((size_t)n * 8),
+                 o_i1 = o_i0 + al((size_t)n * 4), o_cnt = o_i1 + al((size_t)n * 4), o_off = o_cnt + al((size_t)(n + 1) * 8),
+                 o_tmp = o_off + al((size_t)(n + 1) * 8), total = o_tmp + al(sort_tmp > scan_tmp ? sort_tmp : scan_tmp);
+    if (total > ctx->cap_bp) {
+        if (ctx->d_bp) { cudaFree(ctx->d_bp); ctx->d_bp = nullptr; ctx->cap_bp = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_bp, total + total / 8);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc broad-phase workspace", e);
+        ctx->cap_bp = total + total / 8;
+    }
+    char *w = (char *)ctx->d_bp;
+    bp::Bounds *d_b = (bp::Bounds *)(w + o_bounds);
+    unsigned long long *k0 = (unsigned long long *)(w + o_k0), *k1 = (unsigned long long *)(w + o_k1);
+    int32_t *i0 = (int32_t *)(w + o_i0), *i1 = (int32_t *)(w + o_i1);
+    int64_t *d_cnt = (int64_t *)(w + o_cnt), *d_offs = (int64_t *)(w + o_off);
+    const int threads = 256;
+    const unsigned blocks = (unsigned)(((n + threads - 1) / threads) < (int64_t)ctx->sm_count * 16 ? ((n + threads - 1) / threads) : (int64_t)ctx->sm_count * 16);
+    gjk::hull_prep_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(d_verts, d_hull_off, n, ctx->d_sphere);
+    bp::bounds_init_kernel<<<1, 1, 0, st>>>(d_b);
+    bp::bounds_kernel<<<blocks, threads, 0, st>>>(ctx->d_sphere, n, d_b);
+    bp::keys_kernel<<<blocks, threads, 0, st>>>(ctx->d_sphere, n, d_b, k0, i0);
+    size_t tb = sort_tmp;
+    CU(cub::DeviceRadixSort::SortPairs(w + o_tmp, tb, k0, k1, i0, i1, (int)n, 0, 63, st));
+    const unsigned pblocks = (unsigned)(((n + 127) / 128) < (int64_t)ctx->sm_count * 32 ? ((n + 127) / 128) : (int64_t)ctx->sm_count * 32);
+    CU(cudaMemsetAsync(d_cnt + n, 0, sizeof(int64_t), st));
+    bp::pairs_kernel<false><<<pblocks, 128, 0, st>>>(ctx->d_sphere, n, d_b, k1, i1, d_cnt, nullptr, 0, nullptr, nullptr);
+    tb = scan_tmp;
+    CU(cub::DeviceScan::ExclusiveSum(w + o_tmp, tb, d_cnt, d_offs, (int)(n + 1), st));
+    bp::pairs_kernel<true><<<pblocks, 128, 0, st>>>(ctx->d_sphere, n, d_b, k1, i1, d_cnt, d_offs, cap, d_pa, d_pb);
+    ctx->launches += 6;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_total, d_offs + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GJKEPA_OK;
+}
+
 // ---- shapes resident on the device, poses per call ----
 int gjkepa_shapes_upload(gjkepa_ctx *ctx, int64_t n_shapes, const double *shape_verts, const int64_t *shape_off)
 {
@@ -688,48 +782,15 @@ int gjkepa_batch_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
         ctx->cap_stage2 = total + total / 8;
     }
-    // world store sized by the largest shape (no device->host round trip for the exact total)
-    const int64_t need_world = n_bodies * ctx->max_shape_verts * 3;
-    if (need_world > ctx->cap_world) {
-        if (ctx->d_world) { cudaFree(ctx->d_world); ctx->d_world = nullptr; ctx->cap_world = 0; }
-        cudaError_t e = cudaMalloc((void **)&ctx->d_world, (size_t)need_world * sizeof(double));
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc world store", e);
-        ctx->cap_world = need_world;
-    }
-    if (2 * (n_bodies + 1) > ctx->cap_world_off) {
-        if (ctx->d_world_off) { cudaFree(ctx->d_world_off); ctx->d_world_off = nullptr; ctx->cap_world_off = 0; }
-        cudaError_t e = cudaMalloc((void **)&ctx->d_world_off, (size_t)2 * (n_bodies + 1) * sizeof(int64_t));
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc world offsets", e);
-        ctx->cap_world_off = 2 * (n_bodies + 1);
-    }
-    int64_t *d_sizes = ctx->d_world_off, *d_off = ctx->d_world_off + (n_bodies + 1);
-    size_t tmp_bytes = 0;
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_sizes, d_off, (int)(n_bodies + 1), st));
-    if (tmp_bytes > ctx->cap_scan_tmp) {
-        if (ctx->d_scan_tmp) { cudaFree(ctx->d_scan_tmp); ctx->d_scan_tmp = nullptr; ctx->cap_scan_tmp = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_scan_tmp, tmp_bytes + 256);
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc scan scratch", e);
-        ctx->cap_scan_tmp = tmp_bytes + 256;
-    }
-
     char *base = (char *)ctx->d_stage2;
     CU(cudaMemcpyAsync(base + o_shape, body_shape, (size_t)n_bodies * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_pose, pose, (size_t)n_bodies * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_pa, pair_a, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_pb, pair_b, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    {   // Kp: sizes -> offsets -> world-space hull blocks
-        const int threads = 256;
-        pose::body_sizes_kernel<<<(unsigned)((n_bodies + 1 + threads - 1) / threads), threads, 0, st>>>(
-            (const int32_t *)(base + o_shape), ctx->d_shape_off, n_bodies, ctx->n_shapes, d_sizes);
-        size_t tb = ctx->cap_scan_tmp;
-        CU(cub::DeviceScan::ExclusiveSum(ctx->d_scan_tmp, tb, d_sizes, d_off, (int)(n_bodies + 1), st));
-        int64_t blocks = (n_bodies * 8 + threads - 1) / threads;
-        const int64_t max_blocks = (int64_t)ctx->sm_count * 32;
-        if (blocks > max_blocks) blocks = max_blocks;
-        pose::apply_pose_kernel<<<(unsigned)blocks, threads, 0, st>>>(ctx->d_shape_verts, ctx->d_shape_off,
-            (const int32_t *)(base + o_shape), (const double *)(base + o_pose), d_off, n_bodies, ctx->n_shapes, ctx->d_world);
-        ctx->launches += 2;
-        CU(cudaGetLastError());
+    int64_t *d_off = nullptr;
+    {
+        int rcw = posed_world(ctx, n_bodies, (const int32_t *)(base + o_shape), (const double *)(base + o_pose), &d_off);
+        if (rcw) return rcw;
     }
     const int save_hint = ctx->max_hull_hint;
     if (save_hint == 0) ctx->max_hull_hint = (int)ctx->max_shape_verts;      // the shape store bounds the hull sizes
@@ -763,6 +824,79 @@ int gjkepa_batch_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         if (n_contacts) *n_contacts = cnt;
     }
     return GJKEPA_OK;
+}
+
+// ---- candidate pairs on the device ----
+static int broadphase_out(gjkepa_ctx *ctx, int64_t n, const double *d_verts, const int64_t *d_off,
+                          int64_t cap, int32_t *pair_a, int32_t *pair_b, int64_t *n_pairs)
+{
+    cudaStream_t st = ctx->stream;
+    int32_t *d_pa = nullptr, *d_pb = nullptr;
+    if (cap > 0) {
+        int rc = ensure(ctx, ctx->d_ovf, ctx->cap_ovf, cap); if (rc) return rc;       // borrowed: free between batches
+        rc = ensure(ctx, ctx->d_ovf2, ctx->cap_ovf2, cap); if (rc) return rc;
+        d_pa = ctx->d_ovf; d_pb = ctx->d_ovf2;
+    }
+    int64_t total = 0;
+    int rc = broadphase_device(ctx, n, d_verts, d_off, cap, d_pa, d_pb, &total);
+    if (rc) return rc;
+    const int64_t m = total < cap ? total : cap;
+    if (m > 0) {
+        CU(cudaMemcpyAsync(pair_a, d_pa, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(pair_b, d_pb, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    *n_pairs = total;
+    return GJKEPA_OK;
+}
+
+int gjkepa_broadphase_f64(gjkepa_ctx *ctx, int64_t n_hulls, const double *verts, const int64_t *hull_off,
+                          int64_t cap, int32_t *pair_a, int32_t *pair_b, int64_t *n_pairs)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (n_hulls <= 0 || !verts || !hull_off || cap < 0 || !n_pairs || (cap > 0 && (!pair_a || !pair_b)) || n_hulls > 0x7fffffff)
+        return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or null input");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const int64_t n_vert = hull_off[n_hulls];
+    const size_t o_off = al((size_t)n_vert * 24), total = o_off + al((size_t)(n_hulls + 1) * 8);
+    if (total > ctx->cap_stage) {
+        if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->cap_stage = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_stage, total + total / 8);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
+        ctx->cap_stage = total + total / 8;
+    }
+    char *base = (char *)ctx->d_stage;
+    CU(cudaMemcpyAsync(base, verts, (size_t)n_vert * 24, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_off, hull_off, (size_t)(n_hulls + 1) * 8, cudaMemcpyHostToDevice, st));
+    return broadphase_out(ctx, n_hulls, (const double *)base, (const int64_t *)(base + o_off), cap, pair_a, pair_b, n_pairs);
+}
+
+int gjkepa_broadphase_posed_f64(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t *body_shape, const double *pose,
+                                int64_t cap, int32_t *pair_a, int32_t *pair_b, int64_t *n_pairs)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (ctx->n_shapes <= 0) return fail(ctx, GJKEPA_ERR_ARG, "no shapes uploaded (gjkepa_shapes_upload)");
+    if (n_bodies <= 0 || !body_shape || !pose || cap < 0 || !n_pairs || (cap > 0 && (!pair_a || !pair_b)) || n_bodies > 0x7fffffff)
+        return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or null input");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_pose = al((size_t)n_bodies * sizeof(int32_t)), total = o_pose + al((size_t)n_bodies * 12 * sizeof(double));
+    if (total > ctx->cap_stage2) {
+        if (ctx->d_stage2) { cudaFree(ctx->d_stage2); ctx->d_stage2 = nullptr; ctx->cap_stage2 = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_stage2, total + total / 8);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
+        ctx->cap_stage2 = total + total / 8;
+    }
+    char *base = (char *)ctx->d_stage2;
+    CU(cudaMemcpyAsync(base, body_shape, (size_t)n_bodies * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_pose, pose, (size_t)n_bodies * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    int64_t *d_off = nullptr;
+    int rc = posed_world(ctx, n_bodies, (const int32_t *)base, (const double *)(base + o_pose), &d_off);
+    if (rc) return rc;
+    return broadphase_out(ctx, n_bodies, ctx->d_world, d_off, cap, pair_a, pair_b, n_pairs);
 }
 
 // ---- self-test hook: the straight-line sqrt / division sequences of fp64_exact.cuh against the

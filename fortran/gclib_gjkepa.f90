@@ -15,7 +15,8 @@ MODULE GCLIB_GJKEPA
     USE, INTRINSIC :: ISO_C_BINDING
     IMPLICIT NONE
     PRIVATE
-    PUBLIC :: GJKEPA, GJKEPA_BATCH, GJKEPA_CTX_CREATE, GJKEPA_CTX_DESTROY, GJKEPA_SHAPES_UPLOAD, GJKEPA_BATCH_POSED
+    PUBLIC :: GJKEPA, GJKEPA_BATCH, GJKEPA_CTX_CREATE, GJKEPA_CTX_DESTROY, GJKEPA_SHAPES_UPLOAD, GJKEPA_BATCH_POSED, &
+              GJKEPA_BROADPHASE, GJKEPA_BROADPHASE_POSED
 
     INTEGER(C_INT32_T), PARAMETER, PUBLIC :: GJKEPA_MODE_GJK = 0, GJKEPA_MODE_EPA = 1, GJKEPA_MODE_FULL = 2
 
@@ -74,7 +75,23 @@ MODULE GCLIB_GJKEPA
             REAL(C_DOUBLE), VALUE :: tol_ff
             INTEGER(C_INT64_T), VALUE :: n_bodies, n_pairs
             INTEGER(C_INT) :: rc
-        END FUNCTION gjkepa_batch_f64
+        END FUNCTION
+        FUNCTION gjkepa_broadphase_f64(ctx, n_hulls, verts, hull_off, cap, pair_a, pair_b, n_pairs) &
+                                       BIND(C, NAME="gjkepa_broadphase_f64") RESULT(rc)
+            IMPORT :: C_PTR, C_INT, C_INT64_T
+            TYPE(C_PTR), VALUE :: ctx, verts, hull_off, pair_a, pair_b
+            INTEGER(C_INT64_T), VALUE :: n_hulls, cap
+            INTEGER(C_INT64_T) :: n_pairs
+            INTEGER(C_INT) :: rc
+        END FUNCTION
+        FUNCTION gjkepa_broadphase_posed_f64(ctx, n_bodies, body_shape, pose, cap, pair_a, pair_b, n_pairs) &
+                                             BIND(C, NAME="gjkepa_broadphase_posed_f64") RESULT(rc)
+            IMPORT :: C_PTR, C_INT, C_INT64_T
+            TYPE(C_PTR), VALUE :: ctx, body_shape, pose, pair_a, pair_b
+            INTEGER(C_INT64_T), VALUE :: n_bodies, cap
+            INTEGER(C_INT64_T) :: n_pairs
+            INTEGER(C_INT) :: rc
+        END FUNCTION
     END INTERFACE
 
 CONTAINS
@@ -173,5 +190,33 @@ CONTAINS
                                     C_LOC(status_), C_NULL_PTR, C_NULL_PTR)
         IF (rc /= 0) ERROR STOP "GJKEPA_BATCH_POSED: the CUDA narrow phase failed"
     END SUBROUTINE GJKEPA_BATCH_POSED
+
+    ! Candidate pairs on the device: every pair of bodies (a < b, 0-based) that passes the reference's own rough test
+    ! (RoughCollisionDetection_SphericalEnvelope: NORM2(mp1 - mp2) <= r1 + r2 + 1.0), found through a uniform grid
+    ! instead of the host's loop over all pairs.  n_pairs may exceed SIZE(pair_a): then only the first SIZE(pair_a)
+    ! were written and the call is repeated with larger arrays.
+    SUBROUTINE GJKEPA_BROADPHASE(ctx, verts, hull_off, pair_a, pair_b, n_pairs)
+        TYPE(C_PTR), INTENT(IN) :: ctx
+        REAL(C_DOUBLE),     INTENT(IN), TARGET, CONTIGUOUS :: verts(:)
+        INTEGER(C_INT64_T), INTENT(IN), TARGET, CONTIGUOUS :: hull_off(:)
+        INTEGER(C_INT32_T), INTENT(OUT), TARGET, CONTIGUOUS :: pair_a(:), pair_b(:)
+        INTEGER(C_INT64_T), INTENT(OUT) :: n_pairs
+        INTEGER(C_INT) :: rc
+        rc = gjkepa_broadphase_f64(ctx, INT(SIZE(hull_off) - 1, C_INT64_T), C_LOC(verts), C_LOC(hull_off), &
+                                   INT(MIN(SIZE(pair_a), SIZE(pair_b)), C_INT64_T), C_LOC(pair_a), C_LOC(pair_b), n_pairs)
+        IF (rc /= 0) ERROR STOP "GJKEPA_BROADPHASE failed"
+    END SUBROUTINE GJKEPA_BROADPHASE
+
+    SUBROUTINE GJKEPA_BROADPHASE_POSED(ctx, body_shape, pose, pair_a, pair_b, n_pairs)
+        TYPE(C_PTR), INTENT(IN) :: ctx
+        INTEGER(C_INT32_T), INTENT(IN), TARGET, CONTIGUOUS :: body_shape(:)
+        REAL(C_DOUBLE),     INTENT(IN), TARGET, CONTIGUOUS :: pose(:,:)                  ! (12,n_bodies)
+        INTEGER(C_INT32_T), INTENT(OUT), TARGET, CONTIGUOUS :: pair_a(:), pair_b(:)
+        INTEGER(C_INT64_T), INTENT(OUT) :: n_pairs
+        INTEGER(C_INT) :: rc
+        rc = gjkepa_broadphase_posed_f64(ctx, INT(SIZE(body_shape), C_INT64_T), C_LOC(body_shape), C_LOC(pose), &
+                                         INT(MIN(SIZE(pair_a), SIZE(pair_b)), C_INT64_T), C_LOC(pair_a), C_LOC(pair_b), n_pairs)
+        IF (rc /= 0) ERROR STOP "GJKEPA_BROADPHASE_POSED failed"
+    END SUBROUTINE GJKEPA_BROADPHASE_POSED
 
 END MODULE GCLIB_GJKEPA

@@ -140,6 +140,17 @@ int gjkepa_batch_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                            double *normal /*3*np*/, double *point /*3*np*/, double *depth,
                            uint32_t *status, int64_t *n_contacts, int32_t *contact_index);
 
+/* ---- candidate pairs on the device (upstream of the reference path) ----
+ * Emits every pair of bodies (a < b) that passes the reference's own rough test, RoughCollisionDetection_
+ * SphericalEnvelope (F:1165-1188: NORM2(mp1 - mp2) <= r1 + r2 + 1.0, same arithmetic, so the SET is bit-exact with a host
+ * that tests all pairs), found through a uniform grid.  pair_a/pair_b: HOST buffers of `cap` entries; *n_pairs
+ * receives the number of passing pairs, which may exceed cap (then only the first cap were written: call again
+ * with larger buffers).  The order is deterministic.  The _posed form takes bodies as gjkepa_batch_posed_f64 does. */
+int gjkepa_broadphase_f64(gjkepa_ctx *ctx, int64_t n_hulls, const double *verts, const int64_t *hull_off,
+                          int64_t cap, int32_t *pair_a, int32_t *pair_b, int64_t *n_pairs);
+int gjkepa_broadphase_posed_f64(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t *body_shape, const double *pose,
+                                int64_t cap, int32_t *pair_a, int32_t *pair_b, int64_t *n_pairs);
+
 /* self-test hook (host buffers, n elements each): the library's straight-line IEEE sqrt / division
  * sequences next to the compiler's operators; in_range bit 0 = division fast path valid, bit 1 = sqrt */
 int gjkepa_debug_fp64(gjkepa_ctx *ctx, int64_t n, const double *a, const double *b, double *q_fast,

@@ -14,6 +14,7 @@
 #include <math.h>
 #include <float.h>
 #include <string.h>
+#include <stdlib.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -841,6 +842,41 @@ void orc_gjkepa_pair(int32_t version, double tol_ff,
 #undef FINISH
 done:
     return;
+}
+
+/* Every pair (a < b) of a hull store that passes F:1185, by testing ALL pairs (the checker for the product's
+ * grid broad phase).  Spheres per hull first (F:1175-1182), then the F:1185 comparison per pair; pairs come out in
+ * lexicographic order.  Returns the number of passing pairs; writes at most cap of them. */
+int64_t orc_sphere_pairs(const double *verts, const int64_t *hull_off, int64_t n_hulls,
+                         int64_t cap, int32_t *pair_a, int32_t *pair_b)
+{
+    double *sp = (double *)malloc((size_t)n_hulls * 4 * sizeof(double));
+    int64_t *row = (int64_t *)calloc((size_t)n_hulls + 1, sizeof(int64_t));
+    int64_t a, total = 0;
+    if (!sp || !row) { free(sp); free(row); return -1; }
+#pragma omp parallel for schedule(static)
+    for (a = 0; a < n_hulls; ++a) {
+        hull_t h = mk_hull(verts + 3 * hull_off[a], (int32_t)(hull_off[a + 1] - hull_off[a]));
+        hull_sphere(&h, sp + 4 * a, sp + 4 * a + 3);
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma omp parallel for schedule(dynamic, 64)
+        for (a = 0; a < n_hulls; ++a) {
+            int64_t b, k = 0;
+            for (b = a + 1; b < n_hulls; ++b) {
+                double d[3];
+                sub3(sp + 4 * a, sp + 4 * b, d);
+                if (norm2_3(d) <= sp[4 * a + 3] + sp[4 * b + 3] + 1.0) {
+                    if (pass == 1 && row[a] + k < cap) { pair_a[row[a] + k] = (int32_t)a; pair_b[row[a] + k] = (int32_t)b; }
+                    ++k;
+                }
+            }
+            if (pass == 0) row[a + 1] = k;
+        }
+        if (pass == 0) { for (a = 0; a < n_hulls; ++a) row[a + 1] += row[a]; total = row[n_hulls]; }
+    }
+    free(sp); free(row);
+    return total;
 }
 
 int orc_max_threads(void)

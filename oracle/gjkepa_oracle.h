@@ -86,6 +86,9 @@ int  orc_sphere_test(const double *p1, int32_t n1, const double *p2, int32_t n2)
 /* hull stand-in: pts (npts,3) row-major -> tris (ntri,9) row-major; returns 0 on success */
 int  orc_quickhull(const double *pts, int32_t npts, double *tris, int32_t *ntri, int32_t cap);
 void orc_dir_table(int32_t row1based, double d[3]);
+/* all pairs (a < b) passing the F:1185 sphere test, brute force, lexicographic; returns the count */
+int64_t orc_sphere_pairs(const double *verts, const int64_t *hull_off, int64_t n_hulls,
+                         int64_t cap, int32_t *pair_a, int32_t *pair_b);
 int  orc_max_threads(void);
 
 #ifdef __cplusplus

@@ -69,6 +69,8 @@ def lib():
         L.orc_dir_table.argtypes = [C.c_int32, dp]
         L.orc_dir_table.restype = None
         L.orc_max_threads.restype = C.c_int
+        L.orc_sphere_pairs.argtypes = [dp, C.POINTER(C.c_int64), C.c_int64, C.c_int64, ip, ip]
+        L.orc_sphere_pairs.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -173,3 +175,17 @@ def apply_pose(shape_verts, shape_off, body_shape, pose):
         w = np.stack([wx, wy, wz], axis=1).reshape(len(idx), 3 * size)
         verts[(3 * hull_off[idx][:, None] + np.arange(3 * size)[None, :])] = w
     return verts, hull_off
+
+
+def sphere_pairs(verts, hull_off):
+    """All pairs (a < b) passing the reference's envelope-sphere test (F:1185), by brute force over all pairs, in
+    lexicographic order: the checker for the product's grid broad phase."""
+    verts = np.ascontiguousarray(verts, dtype=np.float64)
+    hull_off = np.ascontiguousarray(hull_off, dtype=np.int64)
+    nh = hull_off.shape[0] - 1
+    ip32, ip64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    z = np.empty(1, np.int32)
+    total = lib().orc_sphere_pairs(_dp(verts), hull_off.ctypes.data_as(ip64), nh, 0, z.ctypes.data_as(ip32), z.ctypes.data_as(ip32))
+    pa, pb = np.empty(max(total, 1), np.int32), np.empty(max(total, 1), np.int32)
+    lib().orc_sphere_pairs(_dp(verts), hull_off.ctypes.data_as(ip64), nh, total, pa.ctypes.data_as(ip32), pb.ctypes.data_as(ip32))
+    return pa[:total], pb[:total]

@@ -1,0 +1,98 @@
+"""Candidate pairs on the device: gjkepa_broadphase_f64 / gjkepa_broadphase_posed_f64 must emit
+exactly the pairs (a < b) that pass the reference's own rough test, RoughCollisionDetection_SphericalEnvelope
+(reference src/GCLIB_GJKEPA.f90:1165-1188) -- the SET is bit-exact against the oracle's all-pairs scan
+(oracle.orc.sphere_pairs), so a pair the grid leaves out is one GJKEPA would have returned FALSE for at F:77."""
+import numpy as np
+import pytest
+
+
+def _scene(W, n_bodies, n_vert, spacing, seed):
+    b = W.make_shared_store(n_bodies, 1, n_vert=n_vert, seed=seed, spacing=spacing)
+    return b.verts, b.hull_off
+
+
+def _as_set(pa, pb):
+    return set(zip(pa.tolist(), pb.tolist()))
+
+
+def test_oracle_all_pairs_scan_is_the_sphere_test(W, orc):
+    """The checker itself: orc.sphere_pairs == orc_sphere_test (F:1185) applied to every pair, lexicographic."""
+    verts, off = _scene(W, 400, 12, 2.5, 3)
+    pa, pb = orc.sphere_pairs(verts, off)
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    want = []
+    for a in range(400):
+        for b in range(a + 1, 400):
+            va, vb = verts[3 * off[a]:3 * off[a + 1]], verts[3 * off[b]:3 * off[b + 1]]
+            if orc.lib().orc_sphere_test(va.ctypes.data_as(dp), 12, vb.ctypes.data_as(dp), 12):
+                want.append((a, b))
+    assert list(zip(pa.tolist(), pb.tolist())) == want
+    assert 0 < len(want) < 400 * 399 // 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_bodies,n_vert,spacing", [(5000, 16, 2.5), (20000, 8, 4.0), (3000, 32, 1.0), (64, 4, 100.0)])
+def test_grid_broadphase_equals_all_pairs_scan(W, orc, engine, n_bodies, n_vert, spacing):
+    verts, off = _scene(W, n_bodies, n_vert, spacing, seed=n_bodies)
+    ra, rb = orc.sphere_pairs(verts, off)
+    ga, gb = engine.broadphase(verts, off)
+    assert np.all(ga < gb)
+    assert len(ga) == len(ra) and _as_set(ga, gb) == _as_set(ra, rb)
+    ga2, gb2 = engine.broadphase(verts, off, cap=max(len(ra) // 3, 1))     # too small a first guess: grows, same list
+    assert np.array_equal(ga, ga2) and np.array_equal(gb, gb2)              # and the order is deterministic
+
+
+@pytest.mark.gpu
+def test_broadphase_scene_extremes(W, orc, engine):
+    """Everything in one cell; two far-apart clusters (cell numbers in the hundreds of thousands); bodies of very
+    different sizes (one large radius sets the cell size); negative coordinates."""
+    rng = np.random.default_rng(5)
+    verts, off = _scene(W, 600, 8, 0.05, 9)                                 # one clump: ~all pairs pass
+    ra, rb = orc.sphere_pairs(verts, off)
+    ga, gb = engine.broadphase(verts, off)
+    assert len(ra) > 0.9 * 600 * 599 / 2 and _as_set(ga, gb) == _as_set(ra, rb)
+    v = verts.reshape(600, 3, 8).copy()
+    v[300:] += np.array([4.0e6, -3.0e6, 2.5e6])[None, :, None]             # second cluster far away
+    v[::7] *= rng.uniform(2.0, 6.0, size=(len(v[::7]), 1, 1))              # some much larger bodies
+    v -= 1.0e3
+    verts2 = v.reshape(-1)
+    ra, rb = orc.sphere_pairs(verts2, off)
+    ga, gb = engine.broadphase(verts2, off)
+    assert len(ra) > 0 and _as_set(ga, gb) == _as_set(ra, rb)
+
+
+@pytest.mark.gpu
+def test_broadphase_feeds_the_narrow_phase(W, orc, engine):
+    """Candidate list -> gjkepa_batch_f64 gives the oracle's flags on those pairs; every pair the grid left out is
+    a sphere reject in the oracle (exit path 1, FALSE)."""
+    n = 4000
+    verts, off = _scene(W, n, 16, 1.6, 21)
+    ga, gb = engine.broadphase(verts, off)
+    got = engine.batch_host(verts, off, ga, gb, mode="epa")
+    ref = orc.batch(verts, off, ga, gb, mode=orc.MODE_EPA)
+    assert np.array_equal(got["collision"], ref["collision"]) and np.all((ref["status"] & 0xff) != 1)
+    assert 0.02 < got["collision"].mean() < 0.98
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, n, 20000).astype(np.int32); b = rng.integers(0, n, 20000).astype(np.int32)
+    keep = a < b
+    a, b = a[keep], b[keep]
+    cand = _as_set(ga, gb)
+    out = np.array([(x, y) not in cand for x, y in zip(a.tolist(), b.tolist())])
+    miss = orc.batch(verts, off, a[out], b[out], mode=orc.MODE_GJK)
+    assert out.sum() > 1000 and np.all((miss["status"] & 0xff) == 1) and not miss["collision"].any()
+
+
+@pytest.mark.gpu
+def test_broadphase_over_posed_bodies(W, orc, engine):
+    pb = W.make_posed(n_shapes=200, n_bodies=6000, n_pairs=10, kind="hull", n_lo=4, n_hi=24)
+    pb.pose[:, 9:] *= 0.12                                                   # denser scene
+    engine.upload_shapes(pb.shape_verts, pb.shape_off)
+    ga, gb = engine.broadphase_posed(pb.body_shape, pb.pose)
+    verts, off = orc.apply_pose(pb.shape_verts, pb.shape_off, pb.body_shape, pb.pose)
+    ra, rb = orc.sphere_pairs(verts, off)
+    assert len(ra) > 1000 and _as_set(ga, gb) == _as_set(ra, rb)
+    ha, hb = engine.broadphase(verts, off)                                   # same list as the world-space entry
+    assert np.array_equal(ga, ha) and np.array_equal(gb, hb)
+    with pytest.raises(Exception):
+        engine.broadphase_posed(pb.body_shape, pb.pose[:-1])

@@ -384,6 +384,27 @@ def main():
             "colliding_fraction": float(po["collision"].mean()),
             "api": "gjkepa_batch_posed_f64 (C ABI, pinned host buffers; pose applied on the device)"}
     if not args.no_extra and args.workload == "cfg2" and world == 1:
+        # fp32 mode: the same cfg2 step through gjkepa_batch_f32 (float hull store over PCIe, binary64 kernels on the device)
+        t32, v32 = pin(batch.verts.astype(np.float32)); keep.append(t32)
+        f_in = [v32, h_in[1], h_in[2], h_in[3]]
+        f_out = {"collision": h_out["collision"]}
+        eng.set_max_hull_vertices(int(np.diff(batch.hull_off).max()))
+        for _ in range(2):
+            eng.batch_host_f32(*f_in, mode="gjk", out=f_out)
+        torch.cuda.synchronize()
+        kf = max(3, min(args.steps, 20))
+        t0 = time.perf_counter()
+        for _ in range(kf):
+            eng.batch_host_f32(*f_in, mode="gjk", out=f_out)
+        torch.cuda.synchronize()
+        dtf = (time.perf_counter() - t0) / kf
+        line.setdefault("extra", {})["e2e_f32_mode"] = {
+            "workload": "cfg2 with the hull store as float32 at the boundary",
+            "value": batch.n_pairs / dtf, "unit": UNIT, "ms_per_step": dtf * 1e3,
+            "h2d_bytes_per_step": int(sum(x.nbytes for x in f_in)), "d2h_bytes_per_step": int(batch.n_pairs),
+            "colliding_fraction": float(f_out["collision"].mean()),
+            "api": "gjkepa_batch_f32 (C ABI, pinned host buffers; device widens to binary64, same kernels)"}
+    if not args.no_extra and args.workload == "cfg2" and world == 1:
         # upstream of the path: candidate pairs built on the device (gjkepa_broadphase_posed_f64) for 1M posed bodies
         # instancing 1000 resident hull(16) shapes on a jittered lattice -- the cfg5 kind of scene
         rng = np.random.default_rng(99)

@@ -135,6 +135,48 @@ class Engine:
             out["n_contacts"] = int(nc.value)
         return out
 
+    # ---- fp32 mode: binary32 at the boundary (gjkepa_batch_f32) ----
+    def batch_host_f32(self, verts, hull_off, pair_a, pair_b, mode="full", version: int = 1, tol_ff: float = 1.0,
+                       out: Optional[dict] = None, want_status: bool = True, want_contacts: bool = False) -> dict:
+        """Same call as batch_host with a float32 hull store and float32 real-valued results (half the PCIe bytes).
+        The device widens the store and runs the binary64 kernels: flags/status are those of batch_host on the
+        float-rounded vertices, the reals are its doubles rounded once (include/gjkepa.h)."""
+        mode = _MODES[mode]
+        verts = np.ascontiguousarray(verts, dtype=np.float32)
+        hull_off = np.ascontiguousarray(hull_off, dtype=np.int64)
+        pair_a = np.ascontiguousarray(pair_a, dtype=np.int32)
+        pair_b = np.ascontiguousarray(pair_b, dtype=np.int32)
+        n = int(pair_a.shape[0])
+        nh = int(hull_off.shape[0] - 1)
+        if out is None:
+            out = {"collision": np.empty(n, np.uint8)}
+            if want_status:
+                out["status"] = np.empty(n, np.uint32)
+            if mode >= MODE_EPA:
+                out["depth"] = np.empty(n, np.float32)
+                out["normal"] = np.empty((n, 3), np.float32)
+            if mode >= MODE_FULL:
+                out["colli_type"] = np.empty(n, np.int32)
+                out["nearest"] = np.empty((n, 6), np.float32)
+                out["point"] = np.empty((n, 3), np.float32)
+            if want_contacts:
+                out["contact_index"] = np.empty(n, np.int32)
+        for k in ("depth", "normal", "nearest", "point"):
+            assert k not in out or out[k].dtype == np.float32, f"{k} must be float32"
+        nc = C.c_int64(0)
+        rc = self._L.gjkepa_batch_f32(
+            self._h, int(version), float(tol_ff), nh, _np_ptr(verts), _np_ptr(hull_off), n,
+            _np_ptr(pair_a), _np_ptr(pair_b), mode,
+            _np_ptr(out.get("collision")), _np_ptr(out.get("colli_type")), _np_ptr(out.get("nearest")),
+            _np_ptr(out.get("normal")), _np_ptr(out.get("point")), _np_ptr(out.get("depth")),
+            _np_ptr(out.get("status")),
+            C.cast(C.byref(nc), C.c_void_p) if want_contacts else C.c_void_p(0),
+            _np_ptr(out.get("contact_index")))
+        self._check(rc, "gjkepa_batch_f32")
+        if want_contacts:
+            out["n_contacts"] = int(nc.value)
+        return out
+
     # ---- shapes resident on the device, poses per call (gjkepa_shapes_upload / gjkepa_batch_posed_f64) ----
     def upload_shapes(self, shape_verts, shape_off):
         """Body-space hull store (same layout as `verts`/`hull_off`), copied to the device once."""

@@ -14,6 +14,7 @@
 #include "contact_kernel.cuh"
 #include "pose_kernel.cuh"
 #include "broadphase.cuh"
+#include "f32_io.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -622,6 +623,90 @@ int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     if (status)     CU(cudaMemcpyAsync(status, base + o_st, (size_t)n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
 
+    if (n_contacts || contact_index) {
+        int64_t c = 0;
+        for (int64_t i = 0; i < n_pairs; ++i)
+            if (h_flags[i]) { if (contact_index) contact_index[c] = (int32_t)i; ++c; }
+        if (n_contacts) *n_contacts = c;
+    }
+    return GJKEPA_OK;
+}
+
+// ---- binary32 at the boundary: float hull store in, float results out; the device widens and runs the binary64 kernels ----
+int gjkepa_batch_f32(gjkepa_ctx *ctx, int32_t version, float tol_ff,
+                     int64_t n_hulls, const float *verts, const int64_t *hull_off,
+                     int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
+                     uint8_t *collision, int32_t *colli_type, float *nearest,
+                     float *normal, float *point, float *depth,
+                     uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (n_pairs < 0 || n_hulls < 0) return fail(ctx, GJKEPA_ERR_ARG, "bad sizes");
+    if (n_pairs > 0 && (!verts || !hull_off || !pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (n_pairs == 0) { if (n_contacts) *n_contacts = 0; return GJKEPA_OK; }
+
+    const int64_t n_vert = hull_off[n_hulls];
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const bool need_flags = collision || contact_index || n_contacts;
+    // double results, back to back so ONE narrowing launch covers them: nearest | normal | point | depth
+    const size_t r_near = 0, r_nrm = r_near + (nearest ? (size_t)n_pairs * 6 : 0), r_pt = r_nrm + (normal ? (size_t)n_pairs * 3 : 0),
+                 r_dep = r_pt + (point ? (size_t)n_pairs * 3 : 0), r_all = r_dep + (depth ? (size_t)n_pairs : 0);     // elements
+    size_t o_v32   = 0;
+    size_t o_verts = o_v32 + al((size_t)n_vert * 3 * sizeof(float));
+    size_t o_off   = o_verts + al((size_t)n_vert * 3 * sizeof(double));
+    size_t o_pa    = o_off + al((size_t)(n_hulls + 1) * sizeof(int64_t));
+    size_t o_pb    = o_pa + al((size_t)n_pairs * sizeof(int32_t));
+    size_t o_col   = o_pb + al((size_t)n_pairs * sizeof(int32_t));
+    size_t o_type  = o_col + al(need_flags ? (size_t)n_pairs : 0);
+    size_t o_st    = o_type + al(colli_type ? (size_t)n_pairs * sizeof(int32_t) : 0);
+    size_t o_r64   = o_st + al(status ? (size_t)n_pairs * sizeof(uint32_t) : 0);
+    size_t o_r32   = o_r64 + al(r_all * sizeof(double));
+    size_t total   = o_r32 + al(r_all * sizeof(float));
+    if (total > ctx->cap_stage) {
+        if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->cap_stage = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_stage, total + total / 8);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
+        ctx->cap_stage = total + total / 8;
+    }
+    char *base = (char *)ctx->d_stage;
+    CU(cudaMemcpyAsync(base + o_v32, verts, (size_t)n_vert * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_off, hull_off, (size_t)(n_hulls + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_pa, pair_a, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + o_pb, pair_b, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    const int threads = 256;
+    auto grid = [&](int64_t work) { int64_t b = (work + threads - 1) / threads; const int64_t m = (int64_t)ctx->sm_count * 16;
+                                    return (unsigned)(b < 1 ? 1 : (b > m ? m : b)); };
+    f32io::widen_kernel<<<grid(n_vert * 3 / 4 + 1), threads, 0, st>>>((const float *)(base + o_v32), (double *)(base + o_verts), n_vert * 3);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    double *r64 = (double *)(base + o_r64);
+    int rc = gjkepa_batch_device_f64(ctx, version, (double)tol_ff, n_hulls,
+        (const double *)(base + o_verts), (const int64_t *)(base + o_off), n_pairs,
+        (const int32_t *)(base + o_pa), (const int32_t *)(base + o_pb), mode,
+        need_flags ? (uint8_t *)(base + o_col) : nullptr,
+        colli_type ? (int32_t *)(base + o_type) : nullptr,
+        nearest ? r64 + r_near : nullptr, normal ? r64 + r_nrm : nullptr, point ? r64 + r_pt : nullptr, depth ? r64 + r_dep : nullptr,
+        status ? (uint32_t *)(base + o_st) : nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    float *r32 = (float *)(base + o_r32);
+    if (r_all > 0) {
+        f32io::narrow_kernel<<<grid((int64_t)r_all / 2 + 1), threads, 0, st>>>(r64, r32, (int64_t)r_all);
+        ++ctx->launches;
+        CU(cudaGetLastError());
+    }
+    std::vector<uint8_t> tmp_flags;
+    uint8_t *h_flags = collision;
+    if (need_flags && !h_flags) { tmp_flags.resize((size_t)n_pairs); h_flags = tmp_flags.data(); }
+    if (need_flags) CU(cudaMemcpyAsync(h_flags, base + o_col, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
+    if (colli_type) CU(cudaMemcpyAsync(colli_type, base + o_type, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (nearest)    CU(cudaMemcpyAsync(nearest, r32 + r_near, (size_t)n_pairs * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (normal)     CU(cudaMemcpyAsync(normal, r32 + r_nrm, (size_t)n_pairs * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (point)      CU(cudaMemcpyAsync(point, r32 + r_pt, (size_t)n_pairs * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (depth)      CU(cudaMemcpyAsync(depth, r32 + r_dep, (size_t)n_pairs * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (status)     CU(cudaMemcpyAsync(status, base + o_st, (size_t)n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     if (n_contacts || contact_index) {
         int64_t c = 0;
         for (int64_t i = 0; i < n_pairs; ++i)

@@ -113,6 +113,21 @@ int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                      double *normal /*3*np*/, double *point /*3*np*/, double *depth,
                      uint32_t *status, int64_t *n_contacts, int32_t *contact_index);
 
+/* ---- fp32 mode: binary32 at the boundary (north_star: "1e-5 if an fp32 mode is offered") ----
+ * Same call with the hull store, the tolerance and the real-valued results as float: half the bytes over PCIe, which
+ * bounds the host-buffer step.  The device widens the store once (exact) and runs the SAME binary64 kernels, because
+ * the reference's decision thresholds (1e-8 bands F:157,203,1248; 1e-12 degeneracy tests F:1349,1388) lie below
+ * binary32's epsilon and a binary32 walk could not evaluate them.  Hence: flags, colli_type and status are exactly
+ * what gjkepa_batch_f64 returns for the float-rounded vertices; depth / normal / nearest / point are that call's
+ * doubles rounded once to float.  Against the unrounded binary64 hulls: depth and normal within 1e-5 (relative to
+ * the hull scale), flags equal except for pairs whose gap or overlap is below the rounding of the vertices. */
+int gjkepa_batch_f32(gjkepa_ctx *ctx, int32_t version, float tol_ff,
+                     int64_t n_hulls, const float *verts, const int64_t *hull_off,
+                     int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
+                     uint8_t *collision, int32_t *colli_type, float *nearest /*6*np*/,
+                     float *normal /*3*np*/, float *point /*3*np*/, float *depth,
+                     uint32_t *status, int64_t *n_contacts, int32_t *contact_index);
+
 /* ---- same, DEVICE buffers already resident in HBM (no copies; asynchronous on the stream) ----
  * n_contacts_dev: device int64 (optional).  contact_index_dev: optional, UNORDERED on this path. */
 int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,

@@ -16,7 +16,7 @@ MODULE GCLIB_GJKEPA
     IMPLICIT NONE
     PRIVATE
     PUBLIC :: GJKEPA, GJKEPA_BATCH, GJKEPA_CTX_CREATE, GJKEPA_CTX_DESTROY, GJKEPA_SHAPES_UPLOAD, GJKEPA_BATCH_POSED, &
-              GJKEPA_BROADPHASE, GJKEPA_BROADPHASE_POSED
+              GJKEPA_BROADPHASE, GJKEPA_BROADPHASE_POSED, GJKEPA_BATCH_R4
 
     INTEGER(C_INT32_T), PARAMETER, PUBLIC :: GJKEPA_MODE_GJK = 0, GJKEPA_MODE_EPA = 1, GJKEPA_MODE_FULL = 2
 
@@ -74,6 +74,17 @@ MODULE GCLIB_GJKEPA
             INTEGER(C_INT32_T), VALUE :: version, mode
             REAL(C_DOUBLE), VALUE :: tol_ff
             INTEGER(C_INT64_T), VALUE :: n_bodies, n_pairs
+            INTEGER(C_INT) :: rc
+        END FUNCTION
+        FUNCTION gjkepa_batch_f32(ctx, version, tol_ff, n_hulls, verts, hull_off, n_pairs, pair_a, pair_b, mode, &
+                                  collision, colli_type, nearest, normal, point, depth, status, &
+                                  n_contacts, contact_index) BIND(C, NAME="gjkepa_batch_f32") RESULT(rc)
+            IMPORT :: C_PTR, C_INT, C_INT32_T, C_INT64_T, C_FLOAT
+            TYPE(C_PTR), VALUE :: ctx, verts, hull_off, pair_a, pair_b
+            TYPE(C_PTR), VALUE :: collision, colli_type, nearest, normal, point, depth, status, n_contacts, contact_index
+            INTEGER(C_INT32_T), VALUE :: version, mode
+            REAL(C_FLOAT), VALUE :: tol_ff
+            INTEGER(C_INT64_T), VALUE :: n_hulls, n_pairs
             INTEGER(C_INT) :: rc
         END FUNCTION
         FUNCTION gjkepa_broadphase_f64(ctx, n_hulls, verts, hull_off, cap, pair_a, pair_b, n_pairs) &
@@ -218,5 +229,29 @@ CONTAINS
                                          INT(MIN(SIZE(pair_a), SIZE(pair_b)), C_INT64_T), C_LOC(pair_a), C_LOC(pair_b), n_pairs)
         IF (rc /= 0) ERROR STOP "GJKEPA_BROADPHASE_POSED failed"
     END SUBROUTINE GJKEPA_BROADPHASE_POSED
+
+    ! fp32 mode for hosts that keep REAL*4 geometry: float hull store and float results cross PCIe, the device widens
+    ! the store and runs the same REAL*8 kernels (flags = GJKEPA's on the float-rounded vertices; reals within 1e-5).
+    SUBROUTINE GJKEPA_BATCH_R4(ctx, version_, TOL_FF_, verts, hull_off, pair_a, pair_b, mode, &
+                               collision_, colliType_, nearest_points_, collision_normal_, &
+                               collision_point_, penetration_depth_, status_)
+        TYPE(C_PTR), INTENT(IN) :: ctx
+        INTEGER*4, INTENT(IN) :: version_, mode
+        REAL*4,    INTENT(IN) :: TOL_FF_
+        REAL(C_FLOAT),      INTENT(IN), TARGET, CONTIGUOUS :: verts(:)
+        INTEGER(C_INT64_T), INTENT(IN), TARGET, CONTIGUOUS :: hull_off(:)
+        INTEGER(C_INT32_T), INTENT(IN), TARGET, CONTIGUOUS :: pair_a(:), pair_b(:)
+        INTEGER(C_INT8_T),  INTENT(OUT), TARGET, CONTIGUOUS :: collision_(:)
+        INTEGER(C_INT32_T), INTENT(OUT), TARGET, CONTIGUOUS :: colliType_(:), status_(:)
+        REAL(C_FLOAT),      INTENT(OUT), TARGET, CONTIGUOUS :: nearest_points_(:,:,:), collision_normal_(:,:)
+        REAL(C_FLOAT),      INTENT(OUT), TARGET, CONTIGUOUS :: collision_point_(:,:), penetration_depth_(:)
+        INTEGER(C_INT) :: rc
+        rc = gjkepa_batch_f32(ctx, version_, TOL_FF_, INT(SIZE(hull_off) - 1, C_INT64_T), C_LOC(verts), C_LOC(hull_off), &
+                              INT(SIZE(pair_a), C_INT64_T), C_LOC(pair_a), C_LOC(pair_b), mode, &
+                              C_LOC(collision_), C_LOC(colliType_), C_LOC(nearest_points_), &
+                              C_LOC(collision_normal_), C_LOC(collision_point_), C_LOC(penetration_depth_), &
+                              C_LOC(status_), C_NULL_PTR, C_NULL_PTR)
+        IF (rc /= 0) ERROR STOP "GJKEPA_BATCH_R4: the CUDA narrow phase failed"
+    END SUBROUTINE GJKEPA_BATCH_R4
 
 END MODULE GCLIB_GJKEPA

@@ -353,3 +353,25 @@ def test_large_hulls_take_the_general_kernels(W, orc, engine):
         assert 0.2 < ref["collision"].mean() < 0.98
     b = W.make_mixed(8000, 0.4, seed=61, n_lo=50, n_hi=150)
     check_against_oracle(orc, engine, b, "full", lanes=(0, 4))
+
+
+def test_degenerate_hulls_points_segments_flat_and_duplicated(W, orc, engine):
+    """Inputs the reference accepts (p(n,3) assumed-shape, any n >= 1) but a hull library would reject: 1-3 vertex
+    'hulls' (point, segment, triangle), planar polygons, repeated vertices.  They leave through the initial-tetrahedron
+    exits (F:86 direction table exhausted, F:123 duplicate third point, F:157 coplanar fourth point) far more often than
+    random hulls do; flags and exit paths must still be the oracle's, bit for bit, in every kernel variant."""
+    b = W.make_mixed(40000, 0.5, seed=3, n_lo=1, n_hi=5)
+    ref = check_against_oracle(orc, engine, b, "epa")
+    seen = set(np.unique(ref["status"] & 0xff).tolist())
+    assert {1, 2, 3, 5, 6, 9, 10} <= seen, seen                       # sphere, init_cap, dup3, coplanar4, contain, coplanar, contain
+    flat = W.make_pairs("hull", 30000, 0.5, seed=4, n_vert=8)
+    v = flat.verts.reshape(-1, 3, 8)
+    v[0::2, 2, :] = v[0::2, 2, :1]                                    # body A: a planar polygon
+    check_against_oracle(orc, engine, flat, "epa")
+    v[1::2, 2, :] = v[1::2, 2, :1]                                    # both planar (parallel planes): coplanar4 for ~all
+    ref = check_against_oracle(orc, engine, flat, "gjk")
+    assert np.mean((ref["status"] & 0xff) == 5) > 0.9
+    dup = W.make_pairs("hull", 30000, 0.6, seed=5, n_vert=10)
+    v = dup.verts.reshape(-1, 3, 10)
+    v[:, :, 5:] = v[:, :, :5]                                         # every vertex twice: ties go to the first index
+    check_against_oracle(orc, engine, dup, "full", lanes=(0, "r1", "mono", "gen", 1, 4))

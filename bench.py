@@ -404,6 +404,7 @@ def main():
             "h2d_bytes_per_step": int(sum(x.nbytes for x in f_in)), "d2h_bytes_per_step": int(batch.n_pairs),
             "colliding_fraction": float(f_out["collision"].mean()),
             "api": "gjkepa_batch_f32 (C ABI, pinned host buffers; device widens to binary64, same kernels)"}
+        eng.set_max_hull_vertices(0)
     if not args.no_extra and args.workload == "cfg2" and world == 1:
         # upstream of the path: candidate pairs built on the device (gjkepa_broadphase_posed_f64) for 1M posed bodies
         # instancing 1000 resident hull(16) shapes on a jittered lattice -- the cfg5 kind of scene
@@ -444,6 +445,31 @@ def main():
             "ms_per_step": dtb * 1e3, "h2d_bytes_per_step": int(sum(x.nbytes for x in hb)),
             "d2h_bytes_per_step": int(8 * min(tot.value, cap)),
             "api": "gjkepa_broadphase_posed_f64 (C ABI, pinned host buffers; pairs passing the reference's sphere test F:1185)"}
+        # ... and the whole step in one call: poses in, contacts out (gjkepa_scene_posed_f64, GJK + EPA over the candidates)
+        ccap = 6 * nb
+        sa = torch.empty((ccap,), dtype=torch.int32, pin_memory=True); sb_ = torch.empty((ccap,), dtype=torch.int32, pin_memory=True)
+        sd = torch.empty((ccap,), dtype=torch.float64, pin_memory=True); sn = torch.empty((ccap, 3), dtype=torch.float64, pin_memory=True)
+        keep += [sa, sb_, sd, sn]
+        ncand, ncon = C.c_int64(0), C.c_int64(0)
+
+        def scene_call():
+            rc = eng._L.gjkepa_scene_posed_f64(eng._h, 1, 1.0, nb, vp(hb[0]), vp(hb[1]), 1, ccap, C.c_void_p(sa.data_ptr()),
+                                               C.c_void_p(sb_.data_ptr()), C.c_void_p(sd.data_ptr()), C.c_void_p(sn.data_ptr()),
+                                               C.c_void_p(0), C.c_void_p(0), C.c_void_p(0),
+                                               C.cast(C.byref(ncand), C.c_void_p), C.cast(C.byref(ncon), C.c_void_p))
+            eng._check(rc, "gjkepa_scene_posed_f64")
+        for _ in range(2):
+            scene_call()
+        t0 = time.perf_counter()
+        for _ in range(kb):
+            scene_call()
+        dts = (time.perf_counter() - t0) / kb
+        line["extra"]["e2e_scene_step"] = {
+            "workload": f"{nb} posed hull(16) bodies: pose application + candidate pairs + GJK/EPA over them, contacts to the host",
+            "bodies_per_s": nb / dts, "candidate_pairs": int(ncand.value), "contacts": int(ncon.value),
+            "pairs_per_s": ncand.value / dts, "contacts_per_s": ncon.value / dts, "ms_per_step": dts * 1e3,
+            "h2d_bytes_per_step": int(sum(x.nbytes for x in hb)), "d2h_bytes_per_step": int(40 * min(ncon.value, ccap)),
+            "api": "gjkepa_scene_posed_f64 (C ABI, pinned host buffers)"}
     emit(line)
     eng.close()
     if world > 1:

@@ -22,7 +22,7 @@ MODE_GJK, MODE_EPA, MODE_FULL = 0, 1, 2
 SYMBOLS = [
     "gjkepa_create", "gjkepa_destroy", "gjkepa_set_stream", "gjkepa_use_own_stream", "gjkepa_last_error",
     "gjkepa_launch_count", "gjkepa_set_lanes", "gjkepa_set_max_hull_vertices", "gjkepa_set_tuning", "gjkepa_set_profiling", "gjkepa_kernel_ms", "gjkepa_pair_f64", "gjkepa_batch_f64",
-    "gjkepa_batch_device_f64", "gjkepa_sync", "gjkepa_debug_fp64", "gjkepa_shapes_upload", "gjkepa_batch_posed_f64", "gjkepa_broadphase_f64", "gjkepa_broadphase_posed_f64", "gjkepa_batch_f32",
+    "gjkepa_batch_device_f64", "gjkepa_sync", "gjkepa_debug_fp64", "gjkepa_shapes_upload", "gjkepa_batch_posed_f64", "gjkepa_broadphase_f64", "gjkepa_broadphase_posed_f64", "gjkepa_batch_f32", "gjkepa_scene_posed_f64",
 ]
 
 
@@ -94,6 +94,9 @@ def lib() -> C.CDLL:
     L.gjkepa_batch_f32.argtypes = [vp, C.c_int32, C.c_float, C.c_int64, vp, vp, C.c_int64, vp, vp, C.c_int32,
                                    vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.gjkepa_batch_f32.restype = C.c_int
+    L.gjkepa_scene_posed_f64.argtypes = [vp, C.c_int32, C.c_double, C.c_int64, vp, vp, C.c_int32, C.c_int64,
+                                         vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.gjkepa_scene_posed_f64.restype = C.c_int
     L.gjkepa_broadphase_f64.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp]
     L.gjkepa_broadphase_f64.restype = C.c_int
     L.gjkepa_broadphase_posed_f64.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, vp, vp, vp]

@@ -256,6 +256,41 @@ class Engine:
             lambda c, pa, pb, tot: self._L.gjkepa_broadphase_posed_f64(self._h, nb, _np_ptr(body_shape), _np_ptr(pose), c, pa, pb, tot),
             "gjkepa_broadphase_posed_f64", cap or 8 * nb)
 
+    # ---- scene step: poses in, contacts out (gjkepa_scene_posed_f64) ----
+    def scene_posed(self, body_shape, pose, mode="epa", version: int = 1, tol_ff: float = 1.0, cap: int = 0) -> dict:
+        """Pose application + candidate pairs + GJK/EPA over them in one call; returns only the CONTACTS:
+        body_a, body_b (a < b, in the broad phase's order), depth, normal (mode >= "epa"), point, nearest, colli_type
+        (mode "full"), n_candidates, n_contacts.  Same results as broadphase_posed -> batch_posed -> keep collisions."""
+        mode = _MODES[mode]
+        body_shape = np.ascontiguousarray(body_shape, dtype=np.int32)
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        nb = int(body_shape.shape[0])
+        assert pose.size == 12 * nb
+        cap = int(cap) or 4 * nb
+        while True:
+            out = {"body_a": np.empty(cap, np.int32), "body_b": np.empty(cap, np.int32)}
+            if mode >= MODE_EPA:
+                out["depth"] = np.empty(cap, np.float64)
+                out["normal"] = np.empty((cap, 3), np.float64)
+            if mode >= MODE_FULL:
+                out["point"] = np.empty((cap, 3), np.float64)
+                out["nearest"] = np.empty((cap, 6), np.float64)
+                out["colli_type"] = np.empty(cap, np.int32)
+            ncand, nc = C.c_int64(0), C.c_int64(0)
+            rc = self._L.gjkepa_scene_posed_f64(
+                self._h, int(version), float(tol_ff), nb, _np_ptr(body_shape), _np_ptr(pose), mode, cap,
+                _np_ptr(out["body_a"]), _np_ptr(out["body_b"]), _np_ptr(out.get("depth")), _np_ptr(out.get("normal")),
+                _np_ptr(out.get("point")), _np_ptr(out.get("nearest")), _np_ptr(out.get("colli_type")),
+                C.cast(C.byref(ncand), C.c_void_p), C.cast(C.byref(nc), C.c_void_p))
+            self._check(rc, "gjkepa_scene_posed_f64")
+            if nc.value <= cap:
+                break
+            cap = int(nc.value)
+        n = int(nc.value)
+        out = {k: v[:n] for k, v in out.items()}
+        out["n_candidates"], out["n_contacts"] = int(ncand.value), n
+        return out
+
     # ---- DEVICE buffers (torch CUDA tensors already resident in HBM), asynchronous ----
     def batch_device(self, verts, hull_off, pair_a, pair_b, mode="full", version: int = 1,
                      tol_ff: float = 1.0, out: Optional[dict] = None, want_status: bool = True,

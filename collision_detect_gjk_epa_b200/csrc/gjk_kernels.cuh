@@ -39,6 +39,8 @@ struct BatchArgs {
     // overflow list written by the tile kernel
     int32_t *ovf_list;
     unsigned long long *ovf_count;
+    uint32_t ovf_status;        // 0: a later pass works the overflow list; else no pass follows (the caller's bound on hull
+                                // sizes promised there would be none): the pair gets this status word and flag 0
     int32_t col_doubles;        // capacity of one shared-memory column
     // EPA work list (null when not wanted)
     int32_t *wl_pair;
@@ -165,6 +167,7 @@ gjk_tile_kernel(BatchArgs a)
                 if (lane == 0) base = atomicAdd(a.ovf_count, (unsigned long long)__popc(big));
                 base = __shfl_sync(FULL, base, 0);
                 if (valid && !fits) a.ovf_list[base + __popc(big & ((1u << lane) - 1u))] = (int32_t)p;
+                if (valid && !fits && a.ovf_status) { if (a.status) a.status[p] = a.ovf_status; if (a.collision) a.collision[p] = 0; }
             }
         }
         if (fits) {
@@ -321,6 +324,7 @@ gjk_group_staged_kernel(BatchArgs a, int slot_doubles)
         if (valid && !fits && g.lane == 0) {             // larger than a slot: plain sub-warp kernel
             unsigned long long s2 = atomicAdd(a.ovf_count, 1ull);
             a.ovf_list[s2] = (int32_t)p;
+            if (a.ovf_status) { if (a.status) a.status[p] = a.ovf_status; if (a.collision) a.collision[p] = 0; }
         }
         if (fits) {
             HullViewShared A, B;

@@ -275,6 +275,7 @@ gjk_init_kernel(TwoStageArgs ta)
                 if (lane == 0) base = atomicAdd(a.ovf_count, (unsigned long long)__popc(big));
                 base = __shfl_sync(FULL, base, 0);
                 if (m.valid && !fits) a.ovf_list[base + __popc(big & ((1u << lane) - 1u))] = (int32_t)p;
+                if (m.valid && !fits && a.ovf_status) { if (a.status) a.status[p] = a.ovf_status; if (a.collision) a.collision[p] = 0; }
             }
         }
         Walk w;

@@ -83,6 +83,7 @@ gjk_init_group_kernel(TwoStageArgs ta, int slot_doubles)
         if (valid && !fits && g.lane == 0) {             // larger than a slot: plain sub-warp kernel
             unsigned long long s2 = atomicAdd(a.ovf_count, 1ull);
             a.ovf_list[s2] = (int32_t)p;
+            if (a.ovf_status) { if (a.status) a.status[p] = a.ovf_status; if (a.collision) a.collision[p] = 0; }
         }
         Walk w;
         int e = -1;

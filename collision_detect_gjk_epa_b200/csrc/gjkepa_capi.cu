@@ -15,6 +15,7 @@
 #include "pose_kernel.cuh"
 #include "broadphase.cuh"
 #include "f32_io.cuh"
+#include "scene.cuh"
 
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -57,6 +58,9 @@ struct gjkepa_ctx {
     void *d_scan_tmp = nullptr; size_t cap_scan_tmp = 0;
     void *d_stage2 = nullptr; size_t cap_stage2 = 0;
     void *d_bp = nullptr; size_t cap_bp = 0;                     // broad-phase workspace
+    int64_t bp_layout_n = -1; size_t bp_sort_tmp = 0, bp_scan_tmp = 0;
+    int32_t *d_cand_a = nullptr, *d_cand_b = nullptr; int64_t cap_cand = 0;   // scene step: candidate pairs
+    void *d_scene = nullptr; size_t cap_scene = 0;               // scene step: per-candidate results, compacted contacts
     unsigned long long *h_counters = nullptr;      // pinned
     char *h_small = nullptr, *d_small = nullptr;   // packed staging for tiny batches (pinned host mirror + device block)
     // optional per-kernel timing (CUDA events on the launching stream)
@@ -156,6 +160,9 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
     if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
     if (ctx->d_stage2) cudaFree(ctx->d_stage2);
     if (ctx->d_bp) cudaFree(ctx->d_bp);
+    if (ctx->d_cand_a) cudaFree(ctx->d_cand_a);
+    if (ctx->d_cand_b) cudaFree(ctx->d_cand_b);
+    if (ctx->d_scene) cudaFree(ctx->d_scene);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->h_small) cudaFreeHost(ctx->h_small);
     if (ctx->d_small) cudaFree(ctx->d_small);
@@ -325,6 +332,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     a.collision = collision; a.status = status;
     a.pair_list = nullptr; a.pair_list_count = nullptr;
     a.ovf_list = ctx->d_ovf; a.ovf_count = ctx->d_counters + 2; a.col_doubles = 0;
+    a.ovf_status = (ctx->max_hull_hint != 0 && ctx->max_hull_hint <= ctx->tile_max_vertices) ? GJKEPA_ST_BAD_HINT : 0u;
     a.wl_pair = want_list ? ctx->d_wl_pair : nullptr;
     a.wl_simplex = want_list ? ctx->d_wl_simplex : nullptr;
     a.wl_count = ctx->d_counters;
@@ -413,6 +421,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
             gjk::BatchArgs b = a;
             b.pair_list = ctx->d_ovf; b.pair_list_count = ctx->d_counters + 2;
             b.ovf_list = ctx->d_ovf2; b.ovf_count = ctx->d_counters + 5;
+            b.ovf_status = (hint != 0 && hint <= 64) ? GJKEPA_ST_BAD_HINT : 0u;
             int per_sm = 1;
             if (ctx->single_kernel) {
                 if (fuse) {
@@ -759,32 +768,41 @@ static int posed_world(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t *d_body_
     return GJKEPA_OK;
 }
 
-// Kb: candidate pairs of a device-resident hull store into device buffers; *h_total = number of passing pairs (synchronises)
-static int broadphase_device(gjkepa_ctx *ctx, int64_t n, const double *d_verts, const int64_t *d_hull_off,
-                             int64_t cap, int32_t *d_pa, int32_t *d_pb, int64_t *h_total)
+// Kb, first half: spheres -> grid -> sorted cell keys -> per-body counts -> offsets; *h_total = number of passing pairs
+// (synchronises).  The workspace (ctx->d_bp) then holds what broadphase_fill needs.
+struct BpLayout { size_t o_bounds, o_k0, o_k1, o_i0, o_i1, o_cnt, o_off, o_tmp, total, sort_tmp, scan_tmp; };
+static BpLayout bp_layout(int64_t n, size_t sort_tmp, size_t scan_tmp)
+{
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    BpLayout L;
+    L.sort_tmp = sort_tmp; L.scan_tmp = scan_tmp;
+    L.o_bounds = 0; L.o_k0 = al(sizeof(bp::Bounds)); L.o_k1 = L.o_k0 + al((size_t)n * 8); L.o_i0 = L.o_k1 + al((size_t)n * 8);
+    L.o_i1 = L.o_i0 + al((size_t)n * 4); L.o_cnt = L.o_i1 + al((size_t)n * 4); L.o_off = L.o_cnt + al((size_t)(n + 1) * 8);
+    L.o_tmp = L.o_off + al((size_t)(n + 1) * 8); L.total = L.o_tmp + al(sort_tmp > scan_tmp ? sort_tmp : scan_tmp);
+    return L;
+}
+static int broadphase_count(gjkepa_ctx *ctx, int64_t n, const double *d_verts, const int64_t *d_hull_off, int64_t *h_total)
 {
     cudaStream_t st = ctx->stream;
     int rc = ensure(ctx, ctx->d_sphere, ctx->cap_sphere, n);
     if (rc) return rc;
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     size_t sort_tmp = 0, scan_tmp = 0;
     CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                        (const int32_t *)nullptr, (int32_t *)nullptr, (int)n, 0, 63, st));
     CU(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const int64_t *)nullptr, (int64_t *)nullptr, (int)(n + 1), st));
-    const size_t o_bounds = 0, o_k0 = al(sizeof(bp::Bounds)), o_k1 = o_k0 + al((size_t)n * 8), o_i0 = o_k1 + al((size_t)n * 8),
-                 o_i1 = o_i0 + al((size_t)n * 4), o_cnt = o_i1 + al((size_t)n * 4), o_off = o_cnt + al((size_t)(n + 1) * 8),
-                 o_tmp = o_off + al((size_t)(n + 1) * 8), total = o_tmp + al(sort_tmp > scan_tmp ? sort_tmp : scan_tmp);
-    if (total > ctx->cap_bp) {
+    const BpLayout L = bp_layout(n, sort_tmp, scan_tmp);
+    if (L.total > ctx->cap_bp) {
         if (ctx->d_bp) { cudaFree(ctx->d_bp); ctx->d_bp = nullptr; ctx->cap_bp = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_bp, total + total / 8);
+        cudaError_t e = cudaMalloc(&ctx->d_bp, L.total + L.total / 8);
         if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc broad-phase workspace", e);
-        ctx->cap_bp = total + total / 8;
+        ctx->cap_bp = L.total + L.total / 8;
     }
+    ctx->bp_layout_n = n; ctx->bp_sort_tmp = sort_tmp; ctx->bp_scan_tmp = scan_tmp;
     char *w = (char *)ctx->d_bp;
-    bp::Bounds *d_b = (bp::Bounds *)(w + o_bounds);
-    unsigned long long *k0 = (unsigned long long *)(w + o_k0), *k1 = (unsigned long long *)(w + o_k1);
-    int32_t *i0 = (int32_t *)(w + o_i0), *i1 = (int32_t *)(w + o_i1);
-    int64_t *d_cnt = (int64_t *)(w + o_cnt), *d_offs = (int64_t *)(w + o_off);
+    bp::Bounds *d_b = (bp::Bounds *)(w + L.o_bounds);
+    unsigned long long *k0 = (unsigned long long *)(w + L.o_k0), *k1 = (unsigned long long *)(w + L.o_k1);
+    int32_t *i0 = (int32_t *)(w + L.o_i0), *i1 = (int32_t *)(w + L.o_i1);
+    int64_t *d_cnt = (int64_t *)(w + L.o_cnt), *d_offs = (int64_t *)(w + L.o_off);
     const int threads = 256;
     const unsigned blocks = (unsigned)(((n + threads - 1) / threads) < (int64_t)ctx->sm_count * 16 ? ((n + threads - 1) / threads) : (int64_t)ctx->sm_count * 16);
     gjk::hull_prep_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(d_verts, d_hull_off, n, ctx->d_sphere);
@@ -792,17 +810,39 @@ static int broadphase_device(gjkepa_ctx *ctx, int64_t n, const double *d_verts, 
     bp::bounds_kernel<<<blocks, threads, 0, st>>>(ctx->d_sphere, n, d_b);
     bp::keys_kernel<<<blocks, threads, 0, st>>>(ctx->d_sphere, n, d_b, k0, i0);
     size_t tb = sort_tmp;
-    CU(cub::DeviceRadixSort::SortPairs(w + o_tmp, tb, k0, k1, i0, i1, (int)n, 0, 63, st));
+    CU(cub::DeviceRadixSort::SortPairs(w + L.o_tmp, tb, k0, k1, i0, i1, (int)n, 0, 63, st));
     const unsigned pblocks = (unsigned)(((n + 127) / 128) < (int64_t)ctx->sm_count * 32 ? ((n + 127) / 128) : (int64_t)ctx->sm_count * 32);
     CU(cudaMemsetAsync(d_cnt + n, 0, sizeof(int64_t), st));
     bp::pairs_kernel<false><<<pblocks, 128, 0, st>>>(ctx->d_sphere, n, d_b, k1, i1, d_cnt, nullptr, 0, nullptr, nullptr);
     tb = scan_tmp;
-    CU(cub::DeviceScan::ExclusiveSum(w + o_tmp, tb, d_cnt, d_offs, (int)(n + 1), st));
-    bp::pairs_kernel<true><<<pblocks, 128, 0, st>>>(ctx->d_sphere, n, d_b, k1, i1, d_cnt, d_offs, cap, d_pa, d_pb);
-    ctx->launches += 6;
+    CU(cub::DeviceScan::ExclusiveSum(w + L.o_tmp, tb, d_cnt, d_offs, (int)(n + 1), st));
+    ctx->launches += 5;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h_total, d_offs + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return GJKEPA_OK;
+}
+// Kb, second half: the passing pairs into device buffers of `cap` entries (asynchronous)
+static int broadphase_fill(gjkepa_ctx *ctx, int64_t n, int64_t cap, int32_t *d_pa, int32_t *d_pb)
+{
+    if (n != ctx->bp_layout_n) return fail(ctx, GJKEPA_ERR_ARG, "broad-phase fill without its counting pass");
+    cudaStream_t st = ctx->stream;
+    const BpLayout L = bp_layout(n, ctx->bp_sort_tmp, ctx->bp_scan_tmp);
+    char *w = (char *)ctx->d_bp;
+    const unsigned pblocks = (unsigned)(((n + 127) / 128) < (int64_t)ctx->sm_count * 32 ? ((n + 127) / 128) : (int64_t)ctx->sm_count * 32);
+    bp::pairs_kernel<true><<<pblocks, 128, 0, st>>>(ctx->d_sphere, n, (const bp::Bounds *)(w + L.o_bounds),
+        (const unsigned long long *)(w + L.o_k1), (const int32_t *)(w + L.o_i1), (int64_t *)(w + L.o_cnt), (const int64_t *)(w + L.o_off), cap, d_pa, d_pb);
+    ++ctx->launches;
+    CU(cudaGetLastError());
+    return GJKEPA_OK;
+}
+static int broadphase_device(gjkepa_ctx *ctx, int64_t n, const double *d_verts, const int64_t *d_hull_off,
+                             int64_t cap, int32_t *d_pa, int32_t *d_pb, int64_t *h_total)
+{
+    int rc = broadphase_count(ctx, n, d_verts, d_hull_off, h_total);
+    if (rc) return rc;
+    if (cap > 0 && *h_total > 0) { rc = broadphase_fill(ctx, n, cap, d_pa, d_pb); if (rc) return rc; }
+    CU(cudaStreamSynchronize(ctx->stream));
     return GJKEPA_OK;
 }
 
@@ -878,7 +918,7 @@ int gjkepa_batch_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         if (rcw) return rcw;
     }
     const int save_hint = ctx->max_hull_hint;
-    if (save_hint == 0) ctx->max_hull_hint = (int)ctx->max_shape_verts;      // the shape store bounds the hull sizes
+    ctx->max_hull_hint = (int)ctx->max_shape_verts;      // the shape store bounds the hull sizes (a caller's hint for another store does not apply)
     int rc = gjkepa_batch_device_f64(ctx, version, tol_ff, n_bodies, ctx->d_world, d_off, n_pairs,
         (const int32_t *)(base + o_pa), (const int32_t *)(base + o_pb), mode,
         need_flags ? (uint8_t *)(base + o_col) : nullptr,
@@ -982,6 +1022,125 @@ int gjkepa_broadphase_posed_f64(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t
     int rc = posed_world(ctx, n_bodies, (const int32_t *)base, (const double *)(base + o_pose), &d_off);
     if (rc) return rc;
     return broadphase_out(ctx, n_bodies, ctx->d_world, d_off, cap, pair_a, pair_b, n_pairs);
+}
+
+// ---- scene step: poses in, contacts out ----
+int gjkepa_scene_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                           int64_t n_bodies, const int32_t *body_shape, const double *pose, int32_t mode,
+                           int64_t cap, int32_t *body_a, int32_t *body_b, double *depth, double *normal,
+                           double *point, double *nearest, int32_t *colli_type,
+                           int64_t *n_candidates, int64_t *n_contacts)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (ctx->n_shapes <= 0) return fail(ctx, GJKEPA_ERR_ARG, "no shapes uploaded (gjkepa_shapes_upload)");
+    if (n_bodies <= 0 || !body_shape || !pose || cap < 0 || !n_contacts || (cap > 0 && (!body_a || !body_b)) || n_bodies > 0x7fffffff
+        || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL)
+        return fail(ctx, GJKEPA_ERR_ARG, "bad sizes, mode or null input");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    // 1. poses to the device, world-space hull store (Kp)
+    const size_t o_pose = al((size_t)n_bodies * sizeof(int32_t)), in_total = o_pose + al((size_t)n_bodies * 12 * sizeof(double));
+    if (in_total > ctx->cap_stage2) {
+        if (ctx->d_stage2) { cudaFree(ctx->d_stage2); ctx->d_stage2 = nullptr; ctx->cap_stage2 = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_stage2, in_total + in_total / 8);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
+        ctx->cap_stage2 = in_total + in_total / 8;
+    }
+    char *sb = (char *)ctx->d_stage2;
+    CU(cudaMemcpyAsync(sb, body_shape, (size_t)n_bodies * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sb + o_pose, pose, (size_t)n_bodies * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    int64_t *d_off = nullptr;
+    int rc = posed_world(ctx, n_bodies, (const int32_t *)sb, (const double *)(sb + o_pose), &d_off);
+    if (rc) return rc;
+    // 2. candidate pairs (Kb): count, size the buffers, fill
+    int64_t total = 0;
+    rc = broadphase_count(ctx, n_bodies, ctx->d_world, d_off, &total);
+    if (rc) return rc;
+    if (n_candidates) *n_candidates = total;
+    *n_contacts = 0;
+    if (total == 0) return GJKEPA_OK;
+    if (total > 0x7fffffff) return fail(ctx, GJKEPA_ERR_ARG, "more than 2^31 candidate pairs: split the scene");
+    if (total > ctx->cap_cand) {
+        if (ctx->d_cand_a) cudaFree(ctx->d_cand_a);
+        if (ctx->d_cand_b) cudaFree(ctx->d_cand_b);
+        ctx->d_cand_a = ctx->d_cand_b = nullptr; ctx->cap_cand = 0;
+        const int64_t ncap = total + total / 8 + 1024;
+        cudaError_t e = cudaMalloc((void **)&ctx->d_cand_a, (size_t)ncap * sizeof(int32_t));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_cand_b, (size_t)ncap * sizeof(int32_t));
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc candidate pairs", e);
+        ctx->cap_cand = ncap;
+    }
+    rc = broadphase_fill(ctx, n_bodies, total, ctx->d_cand_a, ctx->d_cand_b);
+    if (rc) return rc;
+    // 3. the reference path over the candidates, results at the candidate's index in device scratch
+    const bool want_d = depth && mode >= GJKEPA_MODE_EPA, want_n = normal && mode >= GJKEPA_MODE_EPA;
+    const bool want_p = point && mode == GJKEPA_MODE_FULL, want_q = nearest && mode == GJKEPA_MODE_FULL, want_t = colli_type && mode == GJKEPA_MODE_FULL;
+    size_t sort_tmp = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const int32_t *)nullptr, (int32_t *)nullptr, (int)total, 0, 31, st));
+    const size_t o_cnt = 0, o_idx = al(sizeof(int64_t)), o_ord = o_idx + al((size_t)total * 4), o_tmp = o_ord + al((size_t)total * 4),
+                 o_dep = o_tmp + al(sort_tmp), o_nrm = o_dep + al(want_d ? (size_t)total * 8 : 0), o_pt = o_nrm + al(want_n ? (size_t)total * 24 : 0),
+                 o_nr = o_pt + al(want_p ? (size_t)total * 24 : 0), o_ty = o_nr + al(want_q ? (size_t)total * 48 : 0),
+                 sc_total = o_ty + al(want_t ? (size_t)total * 4 : 0);
+    if (sc_total > ctx->cap_scene) {
+        if (ctx->d_scene) { cudaFree(ctx->d_scene); ctx->d_scene = nullptr; ctx->cap_scene = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_scene, sc_total + sc_total / 8);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc scene scratch", e);
+        ctx->cap_scene = sc_total + sc_total / 8;
+    }
+    char *w = (char *)ctx->d_scene;
+    const int save_hint = ctx->max_hull_hint;
+    ctx->max_hull_hint = (int)ctx->max_shape_verts;      // the shape store bounds the hull sizes
+    rc = gjkepa_batch_device_f64(ctx, version, tol_ff, n_bodies, ctx->d_world, d_off, total, ctx->d_cand_a, ctx->d_cand_b, mode,
+        nullptr, want_t ? (int32_t *)(w + o_ty) : nullptr, want_q ? (double *)(w + o_nr) : nullptr, want_n ? (double *)(w + o_nrm) : nullptr,
+        want_p ? (double *)(w + o_pt) : nullptr, want_d ? (double *)(w + o_dep) : nullptr, nullptr,
+        (int64_t *)(w + o_cnt), (int32_t *)(w + o_idx));
+    ctx->max_hull_hint = save_hint;
+    if (rc) return rc;
+    int64_t nc = 0;
+    CU(cudaMemcpyAsync(&nc, w + o_cnt, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_contacts = nc;
+    const int64_t m = nc < cap ? nc : cap;
+    if (nc == 0 || m == 0) return GJKEPA_OK;
+    // 4. contacts in ascending candidate order (= lexicographic in (a, b) ... the broad phase's order), gathered densely (Ks)
+    size_t tb = sort_tmp;
+    CU(cub::DeviceRadixSort::SortKeys(w + o_tmp, tb, (const int32_t *)(w + o_idx), (int32_t *)(w + o_ord), (int)nc, 0, 31, st));
+    // dense outputs: the staging block is free again (poses are consumed)
+    const size_t c_a = 0, c_b = c_a + al((size_t)nc * 4), c_d = c_b + al((size_t)nc * 4), c_n = c_d + al(want_d ? (size_t)nc * 8 : 0),
+                 c_p = c_n + al(want_n ? (size_t)nc * 24 : 0), c_q = c_p + al(want_p ? (size_t)nc * 24 : 0), c_t = c_q + al(want_q ? (size_t)nc * 48 : 0),
+                 c_total = c_t + al(want_t ? (size_t)nc * 4 : 0);
+    if (c_total > ctx->cap_stage) {
+        if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->cap_stage = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_stage, c_total + c_total / 8);
+        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
+        ctx->cap_stage = c_total + c_total / 8;
+    }
+    char *c = (char *)ctx->d_stage;
+    scene::GatherArgs g;
+    g.order = (const int32_t *)(w + o_ord); g.n = nc; g.cand_a = ctx->d_cand_a; g.cand_b = ctx->d_cand_b;
+    g.depth = want_d ? (const double *)(w + o_dep) : nullptr; g.normal = want_n ? (const double *)(w + o_nrm) : nullptr;
+    g.point = want_p ? (const double *)(w + o_pt) : nullptr; g.nearest = want_q ? (const double *)(w + o_nr) : nullptr;
+    g.colli_type = want_t ? (const int32_t *)(w + o_ty) : nullptr;
+    g.out_a = (int32_t *)(c + c_a); g.out_b = (int32_t *)(c + c_b); g.o_depth = (double *)(c + c_d); g.o_normal = (double *)(c + c_n);
+    g.o_point = (double *)(c + c_p); g.o_nearest = (double *)(c + c_q); g.o_type = (int32_t *)(c + c_t);
+    {
+        const int threads = 256;
+        int64_t blocks = (nc + threads - 1) / threads;
+        const int64_t mx = (int64_t)ctx->sm_count * 32;
+        scene::gather_kernel<<<(unsigned)(blocks < mx ? blocks : mx), threads, 0, st>>>(g);
+        ++ctx->launches;
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(body_a, c + c_a, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(body_b, c + c_b, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    if (want_d) CU(cudaMemcpyAsync(depth, c + c_d, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    if (want_n) CU(cudaMemcpyAsync(normal, c + c_n, (size_t)m * 24, cudaMemcpyDeviceToHost, st));
+    if (want_p) CU(cudaMemcpyAsync(point, c + c_p, (size_t)m * 24, cudaMemcpyDeviceToHost, st));
+    if (want_q) CU(cudaMemcpyAsync(nearest, c + c_q, (size_t)m * 48, cudaMemcpyDeviceToHost, st));
+    if (want_t) CU(cudaMemcpyAsync(colli_type, c + c_t, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GJKEPA_OK;
 }
 
 // ---- self-test hook: the straight-line sqrt / division sequences of fp64_exact.cuh against the

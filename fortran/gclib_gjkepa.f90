@@ -16,7 +16,7 @@ MODULE GCLIB_GJKEPA
     IMPLICIT NONE
     PRIVATE
     PUBLIC :: GJKEPA, GJKEPA_BATCH, GJKEPA_CTX_CREATE, GJKEPA_CTX_DESTROY, GJKEPA_SHAPES_UPLOAD, GJKEPA_BATCH_POSED, &
-              GJKEPA_BROADPHASE, GJKEPA_BROADPHASE_POSED, GJKEPA_BATCH_R4
+              GJKEPA_BROADPHASE, GJKEPA_BROADPHASE_POSED, GJKEPA_BATCH_R4, GJKEPA_SCENE_POSED
 
     INTEGER(C_INT32_T), PARAMETER, PUBLIC :: GJKEPA_MODE_GJK = 0, GJKEPA_MODE_EPA = 1, GJKEPA_MODE_FULL = 2
 
@@ -85,6 +85,17 @@ MODULE GCLIB_GJKEPA
             INTEGER(C_INT32_T), VALUE :: version, mode
             REAL(C_FLOAT), VALUE :: tol_ff
             INTEGER(C_INT64_T), VALUE :: n_hulls, n_pairs
+            INTEGER(C_INT) :: rc
+        END FUNCTION
+        FUNCTION gjkepa_scene_posed_f64(ctx, version, tol_ff, n_bodies, body_shape, pose, mode, cap, body_a, body_b, depth, &
+                                        normal, point, nearest, colli_type, n_candidates, n_contacts) &
+                                        BIND(C, NAME="gjkepa_scene_posed_f64") RESULT(rc)
+            IMPORT :: C_PTR, C_INT, C_INT32_T, C_INT64_T, C_DOUBLE
+            TYPE(C_PTR), VALUE :: ctx, body_shape, pose, body_a, body_b, depth, normal, point, nearest, colli_type
+            INTEGER(C_INT32_T), VALUE :: version, mode
+            REAL(C_DOUBLE), VALUE :: tol_ff
+            INTEGER(C_INT64_T), VALUE :: n_bodies, cap
+            INTEGER(C_INT64_T) :: n_candidates, n_contacts
             INTEGER(C_INT) :: rc
         END FUNCTION
         FUNCTION gjkepa_broadphase_f64(ctx, n_hulls, verts, hull_off, cap, pair_a, pair_b, n_pairs) &
@@ -253,5 +264,26 @@ CONTAINS
                               C_LOC(status_), C_NULL_PTR, C_NULL_PTR)
         IF (rc /= 0) ERROR STOP "GJKEPA_BATCH_R4: the CUDA narrow phase failed"
     END SUBROUTINE GJKEPA_BATCH_R4
+
+    ! One simulation step in one call: poses in (shapes resident), CONTACTS out -- pose application, candidate pairs by the
+    ! reference's sphere test and GJKEPA over them all happen on the GPU.  Rows 1..MIN(n_contacts, SIZE(body_a)) are written:
+    ! body_a/body_b (0-based, a < b) and that pair's penetration_depth_ / collision_normal_ (mode >= GJKEPA_MODE_EPA).
+    SUBROUTINE GJKEPA_SCENE_POSED(ctx, version_, TOL_FF_, body_shape, pose, mode, body_a, body_b, &
+                                  penetration_depth_, collision_normal_, n_candidates, n_contacts)
+        TYPE(C_PTR), INTENT(IN) :: ctx
+        INTEGER*4, INTENT(IN) :: version_, mode
+        REAL*8,    INTENT(IN) :: TOL_FF_
+        INTEGER(C_INT32_T), INTENT(IN), TARGET, CONTIGUOUS :: body_shape(:)
+        REAL(C_DOUBLE),     INTENT(IN), TARGET, CONTIGUOUS :: pose(:,:)                  ! (12,n_bodies)
+        INTEGER(C_INT32_T), INTENT(OUT), TARGET, CONTIGUOUS :: body_a(:), body_b(:)
+        REAL(C_DOUBLE),     INTENT(OUT), TARGET, CONTIGUOUS :: penetration_depth_(:), collision_normal_(:,:)   ! (3,cap)
+        INTEGER(C_INT64_T), INTENT(OUT) :: n_candidates, n_contacts
+        INTEGER(C_INT) :: rc
+        rc = gjkepa_scene_posed_f64(ctx, version_, TOL_FF_, INT(SIZE(body_shape), C_INT64_T), C_LOC(body_shape), C_LOC(pose), mode, &
+                                    INT(MIN(SIZE(body_a), SIZE(body_b), SIZE(penetration_depth_)), C_INT64_T), C_LOC(body_a), &
+                                    C_LOC(body_b), C_LOC(penetration_depth_), C_LOC(collision_normal_), C_NULL_PTR, C_NULL_PTR, &
+                                    C_NULL_PTR, n_candidates, n_contacts)
+        IF (rc /= 0) ERROR STOP "GJKEPA_SCENE_POSED failed"
+    END SUBROUTINE GJKEPA_SCENE_POSED
 
 END MODULE GCLIB_GJKEPA

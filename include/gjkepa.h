@@ -60,6 +60,9 @@ typedef struct gjkepa_ctx gjkepa_ctx;
 #define GJKEPA_ST_COLD_MATH    (1u << 30)  /* diagnostic: an operand left the straight-line sqrt/div range and
                                               the block was redone with the IEEE operators (same result) */
 
+#define GJKEPA_ST_BAD_HINT     (1u << 31)  /* the pair has a hull larger than the bound given to gjkepa_set_max_hull_vertices:
+                                              NOT processed (flag 0, outputs zero); fix the bound or set it to 0 */
+
 /* ---- context: one per GPU (one process per GPU; pairs shard by index across contexts) ---- */
 int  gjkepa_create(gjkepa_ctx **ctx, int32_t device);
 int  gjkepa_destroy(gjkepa_ctx *ctx);
@@ -165,6 +168,19 @@ int gjkepa_broadphase_f64(gjkepa_ctx *ctx, int64_t n_hulls, const double *verts,
                           int64_t cap, int32_t *pair_a, int32_t *pair_b, int64_t *n_pairs);
 int gjkepa_broadphase_posed_f64(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t *body_shape, const double *pose,
                                 int64_t cap, int32_t *pair_a, int32_t *pair_b, int64_t *n_pairs);
+
+/* ---- scene step: poses in, contacts out (pose application + candidate pairs + the reference path in one call) ----
+ * For a simulation whose shapes are resident (gjkepa_shapes_upload): per step 96 B per body go to the device and only
+ * the CONTACTS come back -- the candidate list never crosses PCIe.  Equivalent, result for result, to
+ *     gjkepa_broadphase_posed_f64 -> gjkepa_batch_posed_f64 on its pairs -> keep the pairs whose collision_ is TRUE:
+ * body_a/body_b (a < b) name the colliding bodies in the broad phase's order; depth/normal (mode >= EPA) and
+ * point/nearest/colli_type (mode FULL) are GJKEPA's outputs for that pair (F:47-52); any of them may be NULL.
+ * All output arrays have `cap` rows; *n_contacts may exceed cap (then the first cap were written). */
+int gjkepa_scene_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                           int64_t n_bodies, const int32_t *body_shape, const double *pose /*12*n_bodies*/, int32_t mode,
+                           int64_t cap, int32_t *body_a, int32_t *body_b, double *depth, double *normal /*3*cap*/,
+                           double *point /*3*cap*/, double *nearest /*6*cap*/, int32_t *colli_type,
+                           int64_t *n_candidates, int64_t *n_contacts);
 
 /* self-test hook (host buffers, n elements each): the library's straight-line IEEE sqrt / division
  * sequences next to the compiler's operators; in_range bit 0 = division fast path valid, bit 1 = sqrt */

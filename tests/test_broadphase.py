@@ -96,3 +96,40 @@ def test_broadphase_over_posed_bodies(W, orc, engine):
     assert np.array_equal(ga, ha) and np.array_equal(gb, hb)
     with pytest.raises(Exception):
         engine.broadphase_posed(pb.body_shape, pb.pose[:-1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["gjk", "epa", "full"])
+def test_scene_step_equals_broadphase_then_narrow_phase(W, orc, engine, mode):
+    """gjkepa_scene_posed_f64 (poses in, contacts out) must return, row for row and bit for bit, what the separate calls
+    return: broadphase_posed -> batch_posed on its pairs -> the rows whose collision_ is TRUE; and those flags are the
+    oracle's on the posed hulls."""
+    pb = W.make_posed(n_shapes=150, n_bodies=5000, n_pairs=10, kind="hull", n_lo=4, n_hi=20, seed=11)
+    pb.pose[:, 9:] *= 0.1
+    engine.upload_shapes(pb.shape_verts, pb.shape_off)
+    engine.set_max_hull_vertices(8)          # a stale bound for ANOTHER store must not apply: the shape store knows its sizes
+    sc = engine.scene_posed(pb.body_shape, pb.pose, mode=mode)
+    engine.set_max_hull_vertices(0)
+    ga, gb = engine.broadphase_posed(pb.body_shape, pb.pose)
+    nar = engine.batch_posed(pb.body_shape, pb.pose, ga, gb, mode=mode)
+    hit = nar["collision"] > 0
+    assert sc["n_candidates"] == len(ga) and sc["n_contacts"] == int(hit.sum()) and 0.02 < hit.mean() < 0.9
+    assert np.array_equal(sc["body_a"], ga[hit]) and np.array_equal(sc["body_b"], gb[hit])
+    for k in ("depth", "normal", "point", "nearest", "colli_type"):
+        assert (k in sc) == (k in nar)
+        if k in sc:
+            assert np.array_equal(sc[k], nar[k][hit]), k
+    verts, off = orc.apply_pose(pb.shape_verts, pb.shape_off, pb.body_shape, pb.pose)
+    ref = orc.batch(verts, off, ga, gb, mode=orc.MODE_GJK)
+    assert np.array_equal(ref["collision"] > 0, hit)
+    small = engine.scene_posed(pb.body_shape, pb.pose, mode=mode, cap=7)        # too small a first guess: grows
+    assert small["n_contacts"] == sc["n_contacts"] and np.array_equal(small["body_a"], sc["body_a"])
+
+
+@pytest.mark.gpu
+def test_scene_step_without_contacts(W, engine):
+    pb = W.make_posed(n_shapes=10, n_bodies=200, n_pairs=10, kind="box", seed=12)
+    pb.pose[:, 9:] = np.arange(200)[:, None] * 100.0                          # everything far apart: no candidates
+    engine.upload_shapes(pb.shape_verts, pb.shape_off)
+    sc = engine.scene_posed(pb.body_shape, pb.pose, mode="epa")
+    assert sc["n_candidates"] == 0 and sc["n_contacts"] == 0 and len(sc["body_a"]) == 0

@@ -243,6 +243,20 @@ def test_max_hull_hint_and_overflow_to_subwarp_kernel(W, orc, engine):
         got = engine.batch_host(b8.verts, b8.hull_off, b8.pair_a, b8.pair_b, mode="gjk")
         assert np.array_equal(got["collision"], ref8["collision"])
         assert np.array_equal(got["status"] & 0xffff, ref8["status"] & 0xffff)
+    # a bound the data violates: pairs with a larger hull are NOT processed and say so (GJKEPA_ST_BAD_HINT), the others
+    # keep their results -- never a silent miss
+    BAD_HINT = np.uint32(1 << 31)
+    sizes = np.diff(b.hull_off)
+    for hint, limit in ((12, 12), (16, 16), (30, 30)):
+        engine.set_max_hull_vertices(hint)
+        got = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="epa")
+        over = (sizes[b.pair_a] > limit) | (sizes[b.pair_b] > limit)
+        flagged = (got["status"] & BAD_HINT) != 0
+        assert not flagged[~over].any() and not got["collision"][flagged].any() and np.all(got["depth"][flagged] == 0.0)
+        ok = ~flagged
+        assert np.array_equal(got["collision"][ok], ref["collision"][ok])
+        assert np.array_equal(got["status"][ok] & 0xffff, ref["status"][ok] & 0xffff)
+        assert 0 < flagged.sum() <= over.sum()          # a pair over the bound that still fits its column is simply processed
     engine.set_max_hull_vertices(0)
 
 

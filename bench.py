@@ -383,6 +383,28 @@ def main():
             "h2d_bytes_per_step": int(sum(x.nbytes for x in hp)), "d2h_bytes_per_step": int(pb.n_pairs),
             "colliding_fraction": float(po["collision"].mean()),
             "api": "gjkepa_batch_posed_f64 (C ABI, pinned host buffers; pose applied on the device)"}
+    if not args.no_extra and world == 1:
+        # the same device-resident step with the opt-in shortcut E1 (GJKEPA_TUNE_EARLY_OUT: flags identical, exit paths of
+        # separated pairs differ; the headline above is the parity build, shortcut off)
+        eng.set_max_hull_vertices(int(np.diff(batch.hull_off).max()))
+        eng.set_tuning(eng.TUNE_EARLY_OUT, 1)
+        oe = None
+        for _ in range(3):
+            oe = eng.batch_device(*d_in, mode=mode, out=oe, want_status=False)
+        torch.cuda.synchronize()
+        ke = max(3, min(args.steps, 50))
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(ke):
+            oe = eng.batch_device(*d_in, mode=mode, out=oe, want_status=False)
+        g1.record()
+        torch.cuda.synchronize()
+        eng.set_tuning(eng.TUNE_EARLY_OUT, 0)
+        mse = g0.elapsed_time(g1) / ke
+        line.setdefault("extra", {})["early_out_e1"] = {
+            "workload": desc, "ms_per_step": mse, "value": batch.n_pairs / mse * 1e3, "unit": UNIT,
+            "flags_identical_to_parity_build": bool(torch.equal(oe["collision"], out["collision"])),
+            "note": "opt-in GJKEPA_TUNE_EARLY_OUT: the walk of a separated pair ends when a support value proves separation"}
     if not args.no_extra and args.workload == "cfg2" and world == 1:
         # fp32 mode: the same cfg2 step through gjkepa_batch_f32 (float hull store over PCIe, binary64 kernels on the device)
         t32, v32 = pin(batch.verts.astype(np.float32)); keep.append(t32)

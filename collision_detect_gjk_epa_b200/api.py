@@ -18,7 +18,7 @@ from ._lib import MODE_EPA, MODE_FULL, MODE_GJK
 EXIT_NAMES = {
     0: "none", 1: "sphere", 2: "init_cap", 3: "dup3", 4: "tri_origin", 5: "coplanar4",
     6: "init_contain", 7: "loop_cap", 8: "loop_collinear", 9: "loop_coplanar",
-    10: "loop_contain", 11: "loop_stall", 12: "stop",
+    10: "loop_contain", 11: "loop_stall", 12: "stop", 13: "early_out",
 }
 ST_EPA_CAP, ST_STOP, ST_HULL_FAIL, ST_BAD_VERSION, ST_H1, ST_TOPO_WARN = (
     1 << 24, 1 << 25, 1 << 26, 1 << 27, 1 << 28, 1 << 29)
@@ -73,7 +73,7 @@ class Engine:
     def set_max_hull_vertices(self, n: int):
         self._check(self._L.gjkepa_set_max_hull_vertices(self._h, int(n)), "gjkepa_set_max_hull_vertices")
 
-    TUNE_WALK_REFILL, TUNE_SINGLE_KERNEL, TUNE_EPA_GENERAL, TUNE_TILE_MAX_VERTICES = 1, 2, 3, 4
+    TUNE_WALK_REFILL, TUNE_SINGLE_KERNEL, TUNE_EPA_GENERAL, TUNE_TILE_MAX_VERTICES, TUNE_EARLY_OUT = 1, 2, 3, 4, 5
 
     def set_tuning(self, key: int, value: int):
         """GJKEPA_TUNE_* knobs of include/gjkepa.h (walk re-pack threshold, single-kernel A/B switch)."""

@@ -36,7 +36,8 @@ namespace gjk {
 enum : int {
     EXIT_SPHERE = 1, EXIT_INIT_CAP = 2, EXIT_DUP3 = 3, EXIT_TRI_ORIGIN = 4, EXIT_COPLANAR4 = 5,
     EXIT_INIT_CONTAIN = 6, EXIT_LOOP_CAP = 7, EXIT_LOOP_COLLINEAR = 8, EXIT_LOOP_COPLANAR = 9,
-    EXIT_LOOP_CONTAIN = 10, EXIT_LOOP_STALL = 11, EXIT_STOP = 12
+    EXIT_LOOP_CONTAIN = 10, EXIT_LOOP_STALL = 11, EXIT_STOP = 12,
+    EXIT_EARLY_OUT = 13          // not a reference exit: opt-in shortcut E1 below (a support value proves separation)
 };
 GJK_HD bool exit_is_collision(int e) { return e == EXIT_TRI_ORIGIN || e == EXIT_INIT_CONTAIN || e == EXIT_LOOP_CONTAIN; }
 
@@ -480,7 +481,17 @@ struct GjkOut {
 // the simplex before the update; simplex_last_2 is rebuilt, in the rare case row 4 already matches, from
 // the vertex the previous update dropped (D1) and the face it kept (k1).
 // =====================================================================================================
-enum : unsigned { WF_FIRST = 2u, WF_HAVE2 = 8u, WF_COLD = 16u, WF_STOP = 32u, WF_STALL = 64u };
+enum : unsigned { WF_FIRST = 2u, WF_HAVE2 = 8u, WF_COLD = 16u, WF_STOP = 32u, WF_STALL = 64u, WF_EARLY = 128u };
+
+// Shortcut E1 (opt-in, default off).  A support point s = support(d) along a unit direction d with
+// s.d < -m proves the Minkowski difference lies in the half-space x.d < -m: the origin is outside, the hulls are at least
+// m apart.  The reference can only answer TRUE with the origin inside -- or within its 1e-8 on-face band of -- a
+// tetrahedron of Minkowski-difference points, and every other exit of it is FALSE, so it answers FALSE for such a pair
+// whichever way its walk goes on; leaving here changes the exit path and the iteration count, not the flag.  (Caveat kept
+// from the survey: IS_INSIDE_PF tests the band on an XY projection, so a face within ~1e-8/m rad of vertical with the
+// origin within 1e-8 of its plane could give a spurious TRUE the shortcut would not reproduce; m is 100x the band.)
+constexpr double EARLY_OUT_MARGIN = 1.0e-6;
+GJK_HD bool early_separated(Vec3 s, Vec3 d) { return dot3(s, d) < -EARLY_OUT_MARGIN; }
 
 struct Walk {
     Vec3 S[4];          // simplex rows (same in every lane of the group)
@@ -552,11 +563,11 @@ inline void shadow_history_check(Walk &w, int k, Vec3 sp, bool have2)
 
 // Initial tetrahedron.  Returns the exit path, or 0 with `w` ready for the first walk_round.
 template <class G, class HV>
-GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, const Sphere &sb, Walk &w)
+GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, const Sphere &sb, Walk &w, bool early = false)
 {
     const Vec3 O = v3(0.0, 0.0, 0.0);
     w.S[0] = w.S[1] = w.S[2] = w.S[3] = O;
-    w.qk = O; w.mk = 0.0; w.D1 = O; w.k1 = 2; w.iters = 0; w.n_support = 0; w.fl = WF_FIRST;
+    w.qk = O; w.mk = 0.0; w.D1 = O; w.k1 = 2; w.iters = 0; w.n_support = 0; w.fl = WF_FIRST | (early ? WF_EARLY : 0u);
 
     if (!sphere_hit(sa, sb)) return EXIT_SPHERE;                              // F:76-77
     int it = 0;
@@ -565,6 +576,7 @@ GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, cons
         if (it > 99) return EXIT_INIT_CAP;                                    // F:86
         support_both(g, A, B, dir_table(it - 1), w.S[0], w.S[1]);            // F:94-103
         w.n_support += 2;
+        if (early && (early_separated(w.S[0], dir_table(it - 1)) || early_separated(w.S[1], neg(dir_table(it - 1))))) return EXIT_EARLY_OUT;
         if (!close3(w.S[0], w.S[1])) break;                                  // F:106
     }
     Vec3 dir;
@@ -575,6 +587,7 @@ GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, cons
         if (dir.x != dir.x) { dir = vec_pl_tail<MathCold>(w.S[0], ab, dab); w.fl |= WF_COLD; }   // NaN marks "redo exactly"
     }
     w.S[2] = support(g, A, B, dir); ++w.n_support;                           // F:119
+    if (early && early_separated(w.S[2], dir)) return EXIT_EARLY_OUT;
     if (close3(w.S[2], w.S[0]) || close3(w.S[2], w.S[1])) return EXIT_DUP3;  // F:123
 
     Vec3 c3 = cross3(w.S[1] - w.S[0], w.S[2] - w.S[1]);                      // F:132-135
@@ -596,6 +609,7 @@ GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, cons
         if (dt < 0.0) dir = neg(dir);                                        // F:151
     }
     w.S[3] = support(g, A, B, dir); ++w.n_support;                           // F:154
+    if (early && early_separated(w.S[3], dir)) return EXIT_EARLY_OUT;
     {   // DIST_PF_SIGN(S3, (S0,S1,S2)), F:157, with UNINML's own zero rule (F:1392)
         bool nz = fabs(c3.x) > 1.0e-12 || fabs(c3.y) > 1.0e-12 || fabs(c3.z) > 1.0e-12;
         Vec3 n = nz ? q3 : O;
@@ -691,7 +705,9 @@ template <class G, class HV>
 GJK_HD int walk_step(const G &g, const HV &A, const HV &B, Walk &w, const Pick &pk, bool live)
 {
     const int k = pk.k;
-    const Vec3 sp = support(g, A, B, pk.flip ? neg(pk.qk) : pk.qk);         // F:1127
+    const Vec3 dirk = pk.flip ? neg(pk.qk) : pk.qk;
+    const Vec3 sp = support(g, A, B, dirk);                                 // F:1127
+    const bool sep = (w.fl & WF_EARLY) != 0u && early_separated(sp, dirk);
     ++w.n_support;
     const bool have2 = (w.fl & WF_HAVE2) != 0u;
 #if defined(GJK_SHADOW_HISTORY) && !defined(__CUDA_ARCH__)
@@ -706,11 +722,12 @@ GJK_HD int walk_step(const G &g, const HV &A, const HV &B, Walk &w, const Pick &
     w.S[2] = sel(k != 2, w.S[3], w.S[2]);
     w.S[3] = sp;
     w.qk = pk.qk; w.mk = pk.mk;
-    w.fl = (w.fl & (WF_COLD | WF_STOP)) | WF_HAVE2 | (stall ? WF_STALL : 0u);   // from now on simplex_last_2 exists
+    w.fl = (w.fl & (WF_COLD | WF_STOP | WF_EARLY)) | WF_HAVE2 | (stall ? WF_STALL : 0u);   // from now on simplex_last_2 exists
     // degenerate cases against the kept face, F:199-206
     int e = 0;
     if (pk.mk < 1.0e-8) e = EXIT_LOOP_COLLINEAR;
     else if (fabs(dot3(sp - w.S[0], pk.qk)) < 1.0e-8) e = EXIT_LOOP_COPLANAR;
+    else if (sep) e = EXIT_EARLY_OUT;                                       // reference exits first: same status when both apply
     return e;
 }
 
@@ -727,10 +744,10 @@ GJK_HD int walk_round(const G &g, const HV &A, const HV &B, Walk &w)
 // F:140 path, hazard H1).  All lanes of the group return the same values.
 template <class G, class HV>
 GJK_HD GjkOut gjk_pair(const G &g, const HV &A, const HV &B,
-                       const Sphere &sa, const Sphere &sb, Vec3 *S)
+                       const Sphere &sa, const Sphere &sb, Vec3 *S, bool early = false)
 {
     Walk w;
-    int e = gjk_init(g, A, B, sa, sb, w);
+    int e = gjk_init(g, A, B, sa, sb, w, early);
     while (e == 0) e = walk_round(g, A, B, w);
     GjkOut o;
     o.exit_path = e; o.iters = w.iters; o.n_support = w.n_support;

@@ -39,6 +39,7 @@ struct BatchArgs {
     // overflow list written by the tile kernel
     int32_t *ovf_list;
     unsigned long long *ovf_count;
+    int32_t early_out;          // 1 = shortcut E1 (gjk_core.cuh): exit as soon as a support value proves separation
     uint32_t ovf_status;        // 0: a later pass works the overflow list; else no pass follows (the caller's bound on hull
                                 // sizes promised there would be none): the pair gets this status word and flag 0
     int32_t col_doubles;        // capacity of one shared-memory column
@@ -178,7 +179,7 @@ gjk_tile_kernel(BatchArgs a)
             if (FUSE) { sa = hull_sphere(A); sb = hull_sphere(B); }
             else      { sa = a.sphere[ha];   sb = a.sphere[hb]; }
             Vec3 S[4];
-            const GjkOut o = gjk_pair(g, A, B, sa, sb, S);
+            const GjkOut o = gjk_pair(g, A, B, sa, sb, S, a.early_out != 0);
             const bool coll = exit_is_collision(o.exit_path);
             if (a.collision) a.collision[p] = coll ? 1 : 0;
             if (a.status) a.status[p] = pack_status(o);
@@ -211,7 +212,7 @@ gjk_group_kernel(BatchArgs a)
         if (FUSE) { sa = group_sphere(g, A); sb = group_sphere(g, B); }
         else      { sa = a.sphere[ha];          sb = a.sphere[hb]; }
         Vec3 S[4];
-        const GjkOut o = gjk_pair(g, A, B, sa, sb, S);
+        const GjkOut o = gjk_pair(g, A, B, sa, sb, S, a.early_out != 0);
         const bool coll = exit_is_collision(o.exit_path);
         if (g.lane == 0) {
             if (a.collision) a.collision[p] = coll ? 1 : 0;
@@ -334,7 +335,7 @@ gjk_group_staged_kernel(BatchArgs a, int slot_doubles)
             if (FUSE) { sa = group_sphere(g, A); sb = group_sphere(g, B); }
             else      { sa = a.sphere[ha];          sb = a.sphere[hb]; }
             Vec3 S[4];
-            const GjkOut o = gjk_pair(g, A, B, sa, sb, S);
+            const GjkOut o = gjk_pair(g, A, B, sa, sb, S, a.early_out != 0);
             const bool coll = exit_is_collision(o.exit_path);
             if (g.lane == 0) {
                 if (a.collision) a.collision[p] = coll ? 1 : 0;

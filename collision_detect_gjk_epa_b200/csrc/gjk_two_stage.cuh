@@ -287,7 +287,7 @@ gjk_init_kernel(TwoStageArgs ta)
             Sphere sa, sb;
             if (FUSE) { sa = hull_sphere_t2(A); sb = hull_sphere_t2(B); }
             else      { sa = a.sphere[m.ha];    sb = a.sphere[m.hb]; }
-            e = gjk_init(g, A, B, sa, sb, w);
+            e = gjk_init(g, A, B, sa, sb, w, a.early_out != 0);
             if (e > 0) {
                 if (a.collision) a.collision[p] = exit_is_collision(e) ? 1 : 0;
                 if (a.status) a.status[p] = pack_status_walk(e, w);
@@ -391,7 +391,7 @@ gjk_walk_kernel(TwoStageArgs ta)
                     w.qk = v3(f[12 * cap], f[13 * cap], f[14 * cap]);
                     w.mk = f[15 * cap];
                     w.D1 = v3(0.0, 0.0, 0.0); w.k1 = 2; w.iters = 0; w.n_support = 4;
-                    w.fl = WF_FIRST | ((sfln & SEED_COLD) ? WF_COLD : 0u);
+                    w.fl = WF_FIRST | ((sfln & SEED_COLD) ? WF_COLD : 0u) | (a.early_out ? WF_EARLY : 0u);
                     p = sp_;
                     A.n = nA; A.h = hA;
                     B.col = col + 3 * hA * T2_PITCH; B.n = nB; B.h = hB;

@@ -94,7 +94,7 @@ gjk_init_group_kernel(TwoStageArgs ta, int slot_doubles)
             Sphere sa, sb;
             if (FUSE) { sa = group_sphere(g, A); sb = group_sphere(g, B); }
             else      { sa = a.sphere[ha];       sb = a.sphere[hb]; }
-            e = gjk_init(g, A, B, sa, sb, w);
+            e = gjk_init(g, A, B, sa, sb, w, a.early_out != 0);
             if (e > 0) {
                 const bool coll = exit_is_collision(e);
                 if (g.lane == 0) {
@@ -240,7 +240,7 @@ gjk_walk_group_kernel(TwoStageArgs ta, int slot_doubles)
                     w.qk = v3(f[12 * cap], f[13 * cap], f[14 * cap]);
                     w.mk = f[15 * cap];
                     w.D1 = v3(0.0, 0.0, 0.0); w.k1 = 2; w.iters = 0; w.n_support = 4;
-                    w.fl = WF_FIRST | ((sfln & SEED_COLD) ? WF_COLD : 0u);
+                    w.fl = WF_FIRST | ((sfln & SEED_COLD) ? WF_COLD : 0u) | (a.early_out ? WF_EARLY : 0u);
                     p = sp_;
                     A.x = slot; A.y = slot + nA; A.z = slot + 2 * nA; A.n = nA;
                     B.x = slot + 3 * nA; B.y = B.x + nB; B.z = B.y + nB; B.n = nB;

@@ -41,6 +41,7 @@ struct gjkepa_ctx {
     int walk_refill = 8;           // K1w re-packs a warp when this many lanes are idle
     bool single_kernel = false;    // monolithic tile kernel instead of K1i + K1w
     bool epa_general = false;      // general EPA kernel only (no linked-mesh fast path)
+    int early_out = 0;             // shortcut E1 (opt-in): see gjk_core.cuh
     int tile_max_vertices = 16;    // largest hull the thread-per-pair kernels stage (larger ones: 4-lane kernels)
     double *d_seed_f64 = nullptr; int32_t *d_seed_pair = nullptr; uint32_t *d_seed_fl = nullptr; int64_t *d_seed_off = nullptr; int64_t cap_seed = 0;
     int32_t *d_ovf = nullptr; int64_t cap_ovf = 0;
@@ -225,6 +226,7 @@ int gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value)
         ctx->tile_max_vertices = value;
         return GJKEPA_OK;
     }
+    if (key == GJKEPA_TUNE_EARLY_OUT) { ctx->early_out = value != 0; return GJKEPA_OK; }
     return GJKEPA_ERR_ARG;
 }
 
@@ -332,6 +334,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     a.collision = collision; a.status = status;
     a.pair_list = nullptr; a.pair_list_count = nullptr;
     a.ovf_list = ctx->d_ovf; a.ovf_count = ctx->d_counters + 2; a.col_doubles = 0;
+    a.early_out = ctx->early_out;
     a.ovf_status = (ctx->max_hull_hint != 0 && ctx->max_hull_hint <= ctx->tile_max_vertices) ? GJKEPA_ST_BAD_HINT : 0u;
     a.wl_pair = want_list ? ctx->d_wl_pair : nullptr;
     a.wl_simplex = want_list ? ctx->d_wl_simplex : nullptr;

@@ -94,6 +94,13 @@ int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
 #define GJKEPA_TUNE_SINGLE_KERNEL  2
 #define GJKEPA_TUNE_EPA_GENERAL    3
 #define GJKEPA_TUNE_TILE_MAX_VERTICES 4   /* 4..16 (default 16): largest hull run one thread per pair; larger ones get 4 lanes */
+/* EARLY_OUT (default 0 = the parity build): 1 = shortcut E1.  The walk leaves as soon as one of its own support points s
+ * along a unit direction d has s.d < -1e-6, which proves the hulls are apart; the reference answers FALSE for every
+ * such pair (all its failure exits are FALSE, TRUE needs the origin inside or within 1e-8 of a tetrahedron of
+ * Minkowski points), so the FLAGS are unchanged -- tests/test_gpu_parity.py checks that on every workload -- while the
+ * exit path of those pairs reads GJKEPA_EXIT_EARLY_OUT and the walk is ~2x shorter for separated pairs. */
+#define GJKEPA_TUNE_EARLY_OUT      5
+#define GJKEPA_EXIT_EARLY_OUT      13
 int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);
 
 /* ---- replaces CALL GJKEPA(...) (F:39-52): one pair, every scalar by reference, HOST arrays ----

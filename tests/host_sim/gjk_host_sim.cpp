@@ -5,9 +5,9 @@
 #include "../../collision_detect_gjk_epa_b200/csrc/gjk_core.cuh"
 #include <cstring>
 
-extern "C" void hostsim_gjk_batch(const double *verts, const int64_t *hull_off, int64_t n_pairs,
-                                  const int32_t *pa, const int32_t *pb,
-                                  uint8_t *collision, uint32_t *status, int32_t *n_support, double *simplex)
+static void gjk_batch_impl(const double *verts, const int64_t *hull_off, int64_t n_pairs,
+                           const int32_t *pa, const int32_t *pb,
+                           uint8_t *collision, uint32_t *status, int32_t *n_support, double *simplex, bool early)
 {
     using namespace gjk;
 #pragma omp parallel for schedule(dynamic, 1024)
@@ -19,7 +19,7 @@ extern "C" void hostsim_gjk_batch(const double *verts, const int64_t *hull_off, 
         Sphere sa = hull_sphere(A), sb = hull_sphere(B);
         Lanes<1> g;
         Vec3 S[4];
-        GjkOut o = gjk_pair(g, A, B, sa, sb, S);
+        GjkOut o = gjk_pair(g, A, B, sa, sb, S, early);
         collision[i] = exit_is_collision(o.exit_path) ? 1 : 0;
         status[i] = (uint32_t)o.exit_path | ((uint32_t)o.iters << 8) | (o.stop_flag ? (1u << 25) : 0u)
                   | (o.exit_path == EXIT_TRI_ORIGIN ? (1u << 28) : 0u);
@@ -27,6 +27,17 @@ extern "C" void hostsim_gjk_batch(const double *verts, const int64_t *hull_off, 
         if (simplex) std::memcpy(simplex + 12 * i, S, 12 * sizeof(double));
     }
 }
+
+extern "C" void hostsim_gjk_batch(const double *verts, const int64_t *hull_off, int64_t n_pairs,
+                                  const int32_t *pa, const int32_t *pb,
+                                  uint8_t *collision, uint32_t *status, int32_t *n_support, double *simplex)
+{ gjk_batch_impl(verts, hull_off, n_pairs, pa, pb, collision, status, n_support, simplex, false); }
+
+// the same walk with the opt-in shortcut E1 (GJKEPA_TUNE_EARLY_OUT): flags must not change, exit paths and counts may
+extern "C" void hostsim_gjk_batch_early(const double *verts, const int64_t *hull_off, int64_t n_pairs,
+                                        const int32_t *pa, const int32_t *pb,
+                                        uint8_t *collision, uint32_t *status, int32_t *n_support, double *simplex)
+{ gjk_batch_impl(verts, hull_off, n_pairs, pa, pb, collision, status, n_support, simplex, true); }
 
 // Unit hook for the stall test F:219-234: the product keeps only the vertex the previous update dropped
 // and the face it kept; the test harness passes explicit simplex_last_1 / simplex_last_2 arrays as the

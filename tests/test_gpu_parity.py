@@ -20,6 +20,7 @@ def configure(eng, variant):
     eng.set_tuning(eng.TUNE_SINGLE_KERNEL, 1 if variant == "mono" else 0)
     eng.set_tuning(eng.TUNE_EPA_GENERAL, 1 if variant == "gen" else 0)
     eng.set_tuning(eng.TUNE_WALK_REFILL, int(variant[1:]) if isinstance(variant, str) and variant[0] == "r" else 8)
+    eng.set_tuning(eng.TUNE_EARLY_OUT, 0)                  # the parity build; test_early_out_* switches it on
     eng.set_lanes(variant if isinstance(variant, int) else 0)
 
 
@@ -389,3 +390,30 @@ def test_degenerate_hulls_points_segments_flat_and_duplicated(W, orc, engine):
     v = dup.verts.reshape(-1, 3, 10)
     v[:, :, 5:] = v[:, :, :5]                                         # every vertex twice: ties go to the first index
     check_against_oracle(orc, engine, dup, "full", lanes=(0, "r1", "mono", "gen", 1, 4))
+
+
+def test_early_out_e1_keeps_every_flag_and_every_contact(W, orc, engine):
+    """GJKEPA_TUNE_EARLY_OUT = 1 (shortcut E1, opt-in): a support value s.d < -1e-6 ends the walk of a separated pair.
+    Against the oracle, which has no shortcut: flags identical on every pair and in every kernel family; pairs that do
+    not take the shortcut keep their exit path and iteration count; contacts keep depth and normal."""
+    cases = [(W.make_pairs("box8", 200000, 1.0, seed=41), 8, "epa"), (W.make_pairs("hull", 60000, 0.85, seed=42, n_vert=32), 32, "epa"),
+             (W.make_mixed(40000, 0.6, seed=43), 0, "epa"), (W.make_mixed(40000, 0.5, seed=44, n_lo=1, n_hi=5), 0, "gjk"),
+             (W.make_shared_store(20000, 150000, n_vert=16, seed=45), 16, "full"), (W.make_touching_mix(40000, seed=46), 20, "epa"),
+             (W.make_pairs("hull", 20000, 1.5, seed=47, n_vert=100), 0, "gjk")]
+    for b, hint, mode in cases:
+        ref = orc.batch(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=orc.MODE_EPA)
+        for variant in (0, "mono", 1, 4):
+            configure(engine, variant)
+            engine.set_tuning(engine.TUNE_EARLY_OUT, 1)
+            engine.set_max_hull_vertices(hint)
+            got = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=mode)
+            assert np.array_equal(got["collision"], ref["collision"]), (b.name, variant)
+            e1 = (got["status"] & 0xff) == 13
+            assert e1.sum() > 0 and not ref["collision"][e1].any()
+            assert np.array_equal(got["status"][~e1] & 0xffff, ref["status"][~e1] & 0xffff)
+            if mode != "gjk":
+                hit = (ref["collision"] > 0) & ((ref["status"] >> 24) == 0)
+                assert np.all(np.abs(got["depth"][hit] - ref["depth"][hit]) <= DEPTH_RTOL * np.maximum(ref["depth"][hit], 1.0))
+                assert np.all(got["depth"][~(ref["collision"] > 0)] == 0.0)
+    engine.set_tuning(engine.TUNE_EARLY_OUT, 0)
+    engine.set_max_hull_vertices(0)

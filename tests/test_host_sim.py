@@ -7,11 +7,11 @@ import numpy as np
 import pytest
 
 
-def run_sim(lib, b):
+def run_sim(lib, b, early=False):
     n = b.n_pairs
     col = np.zeros(n, np.uint8); st = np.zeros(n, np.uint32); ns = np.zeros(n, np.int32); sx = np.zeros((n, 12))
     P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-    lib.hostsim_gjk_batch(P(b.verts, C.c_double), P(b.hull_off, C.c_int64), C.c_int64(n),
+    (lib.hostsim_gjk_batch_early if early else lib.hostsim_gjk_batch)(P(b.verts, C.c_double), P(b.hull_off, C.c_int64), C.c_int64(n),
                           P(b.pair_a, C.c_int32), P(b.pair_b, C.c_int32),
                           P(col, C.c_uint8), P(st, C.c_uint32), P(ns, C.c_int32), P(sx, C.c_double))
     return col, st, ns, sx
@@ -98,3 +98,27 @@ def test_walk_history_bookkeeping_matches_explicit_arrays(W, host_sim):
     checks, mism = C.c_longlong(0), C.c_longlong(0)
     host_sim.hostsim_shadow_counts(C.byref(checks), C.byref(mism))
     assert checks.value > 200000 and mism.value == 0
+
+
+@pytest.mark.parametrize("maker,kw", [
+    ("make_pairs", dict(kind="box8", n_pairs=300000, sigma=1.0, seed=31)),
+    ("make_pairs", dict(kind="box8", n_pairs=100000, sigma=2.0, seed=32)),
+    ("make_pairs", dict(kind="hull", n_pairs=60000, sigma=0.85, n_vert=32, seed=33)),
+    ("make_pairs", dict(kind="hull", n_pairs=60000, sigma=1.2, n_vert=16, seed=34)),
+    ("make_mixed", dict(n_pairs=40000, sigma=0.8, seed=35)),
+    ("make_mixed", dict(n_pairs=40000, sigma=0.5, seed=36, n_lo=1, n_hi=5)),
+    ("make_shared_store", dict(n_bodies=20000, n_pairs=200000, n_vert=16, seed=37)),
+    ("make_touching_mix", dict(n_pairs=40000, seed=38)),
+])
+def test_early_out_e1_never_changes_a_flag(orc, W, host_sim, maker, kw):
+    """Shortcut E1 (GJKEPA_TUNE_EARLY_OUT, default off): a support value s.d < -1e-6 proves separation.
+    Flags must equal the oracle's (which has no shortcut) on every pair; only pairs the oracle calls non-colliding may
+    leave through it, and they leave EARLIER (fewer supports)."""
+    b = getattr(W, maker)(**kw)
+    col, st, ns, _ = run_sim(host_sim, b, early=True)
+    o = orc.batch(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=orc.MODE_GJK)
+    assert np.array_equal(col, o["collision"])
+    e1 = (st & 0xff) == 13
+    assert e1.sum() > 0 and not o["collision"][e1].any()
+    assert np.array_equal(st[~e1] & 0xffff, o["status"][~e1] & 0xffff)       # everything else untouched
+    assert np.all(ns[e1] <= o["n_support"][e1]) and ns[e1].sum() < o["n_support"][e1].sum()

@@ -8,8 +8,9 @@
 //   spheres (K0)  ->  bounds: lower corner and largest radius (block reductions + atomics on ordered keys)
 //   ->  cell of each centre, cell size h = (2 r_max + 1)(1 + 1e-9): two passing bodies are at most h apart, so their
 //       cells differ by at most one step per axis  ->  sort bodies by cell key (cub radix sort)
-//   ->  per body: binary-search the key range of each of its 27 neighbour cells in the sorted list, test the
-//       candidates; a counting pass, an exclusive scan and a filling pass give a deterministic pair order.
+//   ->  per body: binary-search its neighbour cells in the sorted list -- the three cells of a row along x have
+//       consecutive keys, so 9 searches cover the 27 cells (27 single-cell searches when the scene is more than 2^21
+//       cells across and keys alias) -- and test the candidates; a counting pass, an exclusive scan and a filling pass give a deterministic pair order.
 #pragma once
 #include "gjk_kernels.cuh"
 
@@ -17,7 +18,7 @@ namespace bp {
 
 using gjk::Sphere;
 
-struct Bounds { unsigned long long min_key[3]; unsigned long long max_r_key; };      // order-preserving keys of doubles
+struct Bounds { unsigned long long min_key[3]; unsigned long long max_r_key; unsigned long long max_key[3]; };   // order-preserving keys of doubles
 
 __device__ __forceinline__ unsigned long long dkey(double v)
 {   // monotone map double -> uint64 (-0 canonicalised)
@@ -37,16 +38,18 @@ __host__ __device__ __forceinline__ double dkey_inv(unsigned long long k)
 __global__ void bounds_init_kernel(Bounds *b)
 {
     b->min_key[0] = b->min_key[1] = b->min_key[2] = ~0ull; b->max_r_key = 0ull;
+    b->max_key[0] = b->max_key[1] = b->max_key[2] = 0ull;
 }
 
 __global__ void __launch_bounds__(256)
 bounds_kernel(const Sphere *__restrict__ s, int64_t n, Bounds *b)
 {
-    unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, kr = 0ull;
+    unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, kr = 0ull, m0 = 0ull, m1 = 0ull, m2 = 0ull;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const Sphere v = s[i];
         const unsigned long long a0 = dkey(v.cx), a1 = dkey(v.cy), a2 = dkey(v.cz), ar = dkey(v.r);
         k0 = a0 < k0 ? a0 : k0; k1 = a1 < k1 ? a1 : k1; k2 = a2 < k2 ? a2 : k2; kr = ar > kr ? ar : kr;
+        m0 = a0 > m0 ? a0 : m0; m1 = a1 > m1 ? a1 : m1; m2 = a2 > m2 ? a2 : m2;
     }
     for (int o = 16; o > 0; o >>= 1) {
         unsigned long long t;
@@ -54,19 +57,27 @@ bounds_kernel(const Sphere *__restrict__ s, int64_t n, Bounds *b)
         t = __shfl_xor_sync(0xffffffffu, k1, o); k1 = t < k1 ? t : k1;
         t = __shfl_xor_sync(0xffffffffu, k2, o); k2 = t < k2 ? t : k2;
         t = __shfl_xor_sync(0xffffffffu, kr, o); kr = t > kr ? t : kr;
+        t = __shfl_xor_sync(0xffffffffu, m0, o); m0 = t > m0 ? t : m0;
+        t = __shfl_xor_sync(0xffffffffu, m1, o); m1 = t > m1 ? t : m1;
+        t = __shfl_xor_sync(0xffffffffu, m2, o); m2 = t > m2 ? t : m2;
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMin(&b->min_key[0], k0); atomicMin(&b->min_key[1], k1); atomicMin(&b->min_key[2], k2); atomicMax(&b->max_r_key, kr);
+        atomicMax(&b->max_key[0], m0); atomicMax(&b->max_key[1], m1); atomicMax(&b->max_key[2], m2);
     }
 }
 
-struct Grid { double ox, oy, oz, h; };
+struct Grid { double ox, oy, oz, h; long long nx, ny, nz; bool exact; };   // n*: largest cell index per axis; exact: keys never alias
 __device__ __forceinline__ Grid grid_of(const Bounds *b)
 {
     Grid g;
     g.ox = dkey_inv(b->min_key[0]); g.oy = dkey_inv(b->min_key[1]); g.oz = dkey_inv(b->min_key[2]);
     const double rmax = dkey_inv(b->max_r_key);
     g.h = (2.0 * rmax + 1.0) * (1.0 + 1.0e-9);
+    g.nx = (long long)floor((dkey_inv(b->max_key[0]) - g.ox) / g.h);
+    g.ny = (long long)floor((dkey_inv(b->max_key[1]) - g.oy) / g.h);
+    g.nz = (long long)floor((dkey_inv(b->max_key[2]) - g.oz) / g.h);
+    g.exact = g.nx < 0x1ffffe && g.ny < 0x1ffffe && g.nz < 0x1ffffe && g.nx >= 0 && g.ny >= 0 && g.nz >= 0;
     return g;
 }
 // 21 bits per axis: scenes up to 2M cells across; beyond that cells alias (still correct: aliasing only adds candidates
@@ -116,6 +127,24 @@ pairs_kernel(const Sphere *__restrict__ s, int64_t n, const Bounds *__restrict__
         cell_of(g, si, ix, iy, iz);
         int64_t cnt = 0;
         const int64_t out0 = FILL ? offsets[t] : 0;
+        if (g.exact) {
+            // every body's cell index lies in [0, n*] (floor is monotone), so rows outside are empty and the three cells
+            // of a row along x are one run of consecutive keys
+            const long long xlo = ix > 0 ? ix - 1 : 0, xhi = ix < g.nx ? ix + 1 : g.nx;
+            for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) {
+                const long long cy = iy + dy, cz = iz + dz;
+                if (cy < 0 || cy > g.ny || cz < 0 || cz > g.nz) continue;
+                const unsigned long long klo = cell_key(xlo, cy, cz), khi = cell_key(xhi, cy, cz);
+                for (int64_t u = lower_bound(skeys, n, klo); u < n && skeys[u] <= khi; ++u) {
+                    const int32_t j = sids[u];
+                    if (j <= i) continue;
+                    if (gjk::sphere_hit(si, s[j])) {                 // F:1185, the reference's own test
+                        if (FILL) { const int64_t o = out0 + cnt; if (o < cap) { pair_a[o] = i; pair_b[o] = j; } }
+                        ++cnt;
+                    }
+                }
+            }
+        } else {
         unsigned long long seen[27]; int n_seen = 0;             // aliased neighbour keys may repeat: search each key once
         for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) {
             const unsigned long long key = cell_key(ix + dx, iy + dy, iz + dz);
@@ -131,6 +160,7 @@ pairs_kernel(const Sphere *__restrict__ s, int64_t n, const Bounds *__restrict__
                     ++cnt;
                 }
             }
+        }
         }
         if (!FILL) counts[t] = cnt;
     }

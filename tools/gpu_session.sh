@@ -11,6 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 export CHECK=0 LANES=0
 WL=cfg2 MODE=gjk ncu --set full --clock-control none --import-source on -k regex:gjk_ -s 8 -c 2 -f -o $out/prof_${tag}_gjk_cfg2 python tools/quick_time.py > $out/ncu_a_$tag.log 2>&1
 WL=cfg3 MODE=epa ncu --set full --clock-control none --import-source on -k "regex:gjk_.*group|epa3" -s 12 -c 3 -f -o $out/prof_${tag}_cfg3 python tools/quick_time.py > $out/ncu_b_$tag.log 2>&1
+SEEDS=${SOAK_SEEDS:-10} python tools/soak.py > $out/soak_$tag.log 2>&1; tail -1 $out/soak_$tag.log
 python - <<PY
 import json
 for w in ["cfg2","cfg3","cfg4","cfg5"]:

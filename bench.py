@@ -193,6 +193,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the GJK/EPA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from collision_detect_gjk_epa_b200 import shard as _shard
+    numa = _shard.bind_to_gpu_numa(local_rank)       # pinned buffers on the GPU's own NUMA node (undone before the CPU baseline)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -330,12 +332,17 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    line["config"]["host_numa_node"] = numa[0] if numa else None      # process + pinned buffers bound to the GPU's NUMA node
     if not args.no_cpu:
         sample = min(n, 1_000_000)
+        if numa:
+            os.sched_setaffinity(0, numa[1])             # the CPU baseline gets every host core back
         rate, used, ns, _, dt = cpu_rate(batch, mode, sample, repeats=2)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": used, "kind": "port",
                                 "sample": f"first {ns} pairs of the same workload, best of 2 ({dt:.2f} s); C restatement "
                                           "of GCLIB_GJKEPA.f90 (no Fortran compiler in the image), OpenMP over pairs"}
+        if numa:
+            _shard.bind_to_gpu_numa(local_rank)
     if not args.no_extra and args.workload == "cfg2" and world == 1:
         # secondary headline: GJK+EPA contacts/s on cfg3 (1M pairs of 32-vertex hulls)
         b3, m3, d3 = make_workload("cfg3", args.pairs, seed=12345)
@@ -409,7 +416,9 @@ def main():
         # fp32 mode: the same cfg2 step through gjkepa_batch_f32 (float hull store over PCIe, binary64 kernels on the device)
         t32, v32 = pin(batch.verts.astype(np.float32)); keep.append(t32)
         f_in = [v32, h_in[1], h_in[2], h_in[3]]
-        f_out = {"collision": h_out["collision"]}
+        t32o = torch.empty((batch.n_pairs,), dtype=torch.uint8, pin_memory=True); keep.append(t32o)
+        f_out = {"collision": t32o.numpy()}
+        flags64 = h_out["collision"].copy()              # what gjkepa_batch_f64 returned for the same pairs (e2e leg above)
         eng.set_max_hull_vertices(int(np.diff(batch.hull_off).max()))
         for _ in range(2):
             eng.batch_host_f32(*f_in, mode="gjk", out=f_out)
@@ -425,6 +434,7 @@ def main():
             "value": batch.n_pairs / dtf, "unit": UNIT, "ms_per_step": dtf * 1e3,
             "h2d_bytes_per_step": int(sum(x.nbytes for x in f_in)), "d2h_bytes_per_step": int(batch.n_pairs),
             "colliding_fraction": float(f_out["collision"].mean()),
+            "flag_mismatch_rate_vs_f64": float(np.mean(f_out["collision"] != flags64)),
             "api": "gjkepa_batch_f32 (C ABI, pinned host buffers; device widens to binary64, same kernels)"}
         eng.set_max_hull_vertices(0)
     if not args.no_extra and args.workload == "cfg2" and world == 1:
@@ -486,6 +496,18 @@ def main():
         for _ in range(kb):
             scene_call()
         dts = (time.perf_counter() - t0) / kb
+        eng.set_tuning(eng.TUNE_EARLY_OUT, 1)            # the same step with shortcut E1 (most candidates are separated)
+        nc0 = int(ncon.value)
+        for _ in range(2):
+            scene_call()
+        t0 = time.perf_counter()
+        for _ in range(kb):
+            scene_call()
+        dts1 = (time.perf_counter() - t0) / kb
+        eng.set_tuning(eng.TUNE_EARLY_OUT, 0)
+        nc1 = int(ncon.value)
+        scene_call()                                     # back on the parity build for the numbers below
+        line["extra"]["e2e_scene_step_early_out"] = {"ms_per_step": dts1 * 1e3, "contacts": nc1, "same_contact_count": nc1 == nc0}
         line["extra"]["e2e_scene_step"] = {
             "workload": f"{nb} posed hull(16) bodies: pose application + candidate pairs + GJK/EPA over them, contacts to the host",
             "bodies_per_s": nb / dts, "candidate_pairs": int(ncand.value), "contacts": int(ncon.value),

@@ -85,3 +85,36 @@ class ShardedEngine:
             out["contacts"] = gather_contacts(*compact_contacts(out["collision"], out["depth"], out["normal"], lo),
                                               group=self.group)
         return out
+
+
+def bind_to_gpu_numa(device_index: int):
+    """One process per GPU: run this process (and so first-touch its pinned host buffers) on the CPU cores of the NUMA node
+    the GPU hangs off.  With 8 ranks on a two-socket box, half of them would otherwise stream their H2D copies from the
+    other socket's memory.  Best effort: returns (node, previous_affinity) or None when the topology cannot be read or the
+    cpuset forbids it; `os.sched_setaffinity(0, previous_affinity)` undoes it."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        prev = os.sched_getaffinity(0)
+        use = cpus & prev
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return node, prev
+    except Exception:
+        return None

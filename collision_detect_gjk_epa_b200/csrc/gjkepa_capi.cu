@@ -90,6 +90,18 @@ static bool debug_sync_enabled() { static const bool on = [] { const char *e = g
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, GJKEPA_ERR_CUDA, #call, e_); } while (0)
 
+// grow-on-demand device block (contents are not kept): 12.5 % slack so that slowly growing batches do not reallocate
+static int grow_bytes(gjkepa_ctx *ctx, void *&p, size_t &cap, size_t need, const char *what)
+{
+    if (need <= cap) return GJKEPA_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    const size_t want = need + need / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, what, e);
+    cap = want;
+    return GJKEPA_OK;
+}
+
 template <typename T>
 int ensure(gjkepa_ctx *ctx, T *&p, int64_t &cap, int64_t need)
 {
@@ -599,12 +611,7 @@ int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     size_t o_dep   = o_pt + al(point ? (size_t)n_pairs * 3 * sizeof(double) : 0);
     size_t o_st    = o_dep + al(depth ? (size_t)n_pairs * sizeof(double) : 0);
     size_t total   = o_st + al(status ? (size_t)n_pairs * sizeof(uint32_t) : 0);
-    if (total > ctx->cap_stage) {
-        if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->cap_stage = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_stage, total + total / 8);
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
-        ctx->cap_stage = total + total / 8;
-    }
+    if (int rcg = grow_bytes(ctx, ctx->d_stage, ctx->cap_stage, total, "cudaMalloc staging")) return rcg;
     char *base = (char *)ctx->d_stage;
     CU(cudaMemcpyAsync(base + o_verts, verts, (size_t)n_vert * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_off, hull_off, (size_t)(n_hulls + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
@@ -676,12 +683,7 @@ int gjkepa_batch_f32(gjkepa_ctx *ctx, int32_t version, float tol_ff,
     size_t o_r64   = o_st + al(status ? (size_t)n_pairs * sizeof(uint32_t) : 0);
     size_t o_r32   = o_r64 + al(r_all * sizeof(double));
     size_t total   = o_r32 + al(r_all * sizeof(float));
-    if (total > ctx->cap_stage) {
-        if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->cap_stage = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_stage, total + total / 8);
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
-        ctx->cap_stage = total + total / 8;
-    }
+    if (int rcg = grow_bytes(ctx, ctx->d_stage, ctx->cap_stage, total, "cudaMalloc staging")) return rcg;
     char *base = (char *)ctx->d_stage;
     CU(cudaMemcpyAsync(base + o_v32, verts, (size_t)n_vert * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_off, hull_off, (size_t)(n_hulls + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
@@ -904,12 +906,7 @@ int gjkepa_batch_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     size_t o_dep   = o_pt + al(point ? (size_t)n_pairs * 3 * sizeof(double) : 0);
     size_t o_st    = o_dep + al(depth ? (size_t)n_pairs * sizeof(double) : 0);
     size_t total   = o_st + al(status ? (size_t)n_pairs * sizeof(uint32_t) : 0);
-    if (total > ctx->cap_stage2) {
-        if (ctx->d_stage2) { cudaFree(ctx->d_stage2); ctx->d_stage2 = nullptr; ctx->cap_stage2 = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_stage2, total + total / 8);
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
-        ctx->cap_stage2 = total + total / 8;
-    }
+    if (int rcg = grow_bytes(ctx, ctx->d_stage2, ctx->cap_stage2, total, "cudaMalloc staging")) return rcg;
     char *base = (char *)ctx->d_stage2;
     CU(cudaMemcpyAsync(base + o_shape, body_shape, (size_t)n_bodies * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_pose, pose, (size_t)n_bodies * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -989,12 +986,7 @@ int gjkepa_broadphase_f64(gjkepa_ctx *ctx, int64_t n_hulls, const double *verts,
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const int64_t n_vert = hull_off[n_hulls];
     const size_t o_off = al((size_t)n_vert * 24), total = o_off + al((size_t)(n_hulls + 1) * 8);
-    if (total > ctx->cap_stage) {
-        if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->cap_stage = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_stage, total + total / 8);
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
-        ctx->cap_stage = total + total / 8;
-    }
+    if (int rcg = grow_bytes(ctx, ctx->d_stage, ctx->cap_stage, total, "cudaMalloc staging")) return rcg;
     char *base = (char *)ctx->d_stage;
     CU(cudaMemcpyAsync(base, verts, (size_t)n_vert * 24, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_off, hull_off, (size_t)(n_hulls + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1012,12 +1004,7 @@ int gjkepa_broadphase_posed_f64(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t
     cudaStream_t st = ctx->stream;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t o_pose = al((size_t)n_bodies * sizeof(int32_t)), total = o_pose + al((size_t)n_bodies * 12 * sizeof(double));
-    if (total > ctx->cap_stage2) {
-        if (ctx->d_stage2) { cudaFree(ctx->d_stage2); ctx->d_stage2 = nullptr; ctx->cap_stage2 = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_stage2, total + total / 8);
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
-        ctx->cap_stage2 = total + total / 8;
-    }
+    if (int rcg = grow_bytes(ctx, ctx->d_stage2, ctx->cap_stage2, total, "cudaMalloc staging")) return rcg;
     char *base = (char *)ctx->d_stage2;
     CU(cudaMemcpyAsync(base, body_shape, (size_t)n_bodies * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(base + o_pose, pose, (size_t)n_bodies * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1044,12 +1031,7 @@ int gjkepa_scene_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     // 1. poses to the device, world-space hull store (Kp)
     const size_t o_pose = al((size_t)n_bodies * sizeof(int32_t)), in_total = o_pose + al((size_t)n_bodies * 12 * sizeof(double));
-    if (in_total > ctx->cap_stage2) {
-        if (ctx->d_stage2) { cudaFree(ctx->d_stage2); ctx->d_stage2 = nullptr; ctx->cap_stage2 = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_stage2, in_total + in_total / 8);
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
-        ctx->cap_stage2 = in_total + in_total / 8;
-    }
+    if (int rcg = grow_bytes(ctx, ctx->d_stage2, ctx->cap_stage2, in_total, "cudaMalloc staging")) return rcg;
     char *sb = (char *)ctx->d_stage2;
     CU(cudaMemcpyAsync(sb, body_shape, (size_t)n_bodies * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(sb + o_pose, pose, (size_t)n_bodies * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1085,12 +1067,7 @@ int gjkepa_scene_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                  o_dep = o_tmp + al(sort_tmp), o_nrm = o_dep + al(want_d ? (size_t)total * 8 : 0), o_pt = o_nrm + al(want_n ? (size_t)total * 24 : 0),
                  o_nr = o_pt + al(want_p ? (size_t)total * 24 : 0), o_ty = o_nr + al(want_q ? (size_t)total * 48 : 0),
                  sc_total = o_ty + al(want_t ? (size_t)total * 4 : 0);
-    if (sc_total > ctx->cap_scene) {
-        if (ctx->d_scene) { cudaFree(ctx->d_scene); ctx->d_scene = nullptr; ctx->cap_scene = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_scene, sc_total + sc_total / 8);
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc scene scratch", e);
-        ctx->cap_scene = sc_total + sc_total / 8;
-    }
+    if (int rcg = grow_bytes(ctx, ctx->d_scene, ctx->cap_scene, sc_total, "cudaMalloc scene scratch")) return rcg;
     char *w = (char *)ctx->d_scene;
     const int save_hint = ctx->max_hull_hint;
     ctx->max_hull_hint = (int)ctx->max_shape_verts;      // the shape store bounds the hull sizes
@@ -1113,12 +1090,7 @@ int gjkepa_scene_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     const size_t c_a = 0, c_b = c_a + al((size_t)nc * 4), c_d = c_b + al((size_t)nc * 4), c_n = c_d + al(want_d ? (size_t)nc * 8 : 0),
                  c_p = c_n + al(want_n ? (size_t)nc * 24 : 0), c_q = c_p + al(want_p ? (size_t)nc * 24 : 0), c_t = c_q + al(want_q ? (size_t)nc * 48 : 0),
                  c_total = c_t + al(want_t ? (size_t)nc * 4 : 0);
-    if (c_total > ctx->cap_stage) {
-        if (ctx->d_stage) { cudaFree(ctx->d_stage); ctx->d_stage = nullptr; ctx->cap_stage = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_stage, c_total + c_total / 8);
-        if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc staging", e);
-        ctx->cap_stage = c_total + c_total / 8;
-    }
+    if (int rcg = grow_bytes(ctx, ctx->d_stage, ctx->cap_stage, c_total, "cudaMalloc staging")) return rcg;
     char *c = (char *)ctx->d_stage;
     scene::GatherArgs g;
     g.order = (const int32_t *)(w + o_ord); g.n = nc; g.cand_a = ctx->d_cand_a; g.cand_b = ctx->d_cand_b;

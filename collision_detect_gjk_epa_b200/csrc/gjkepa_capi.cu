@@ -332,8 +332,8 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     const bool prof = ctx->profiling;
     // K0
     if (!fuse) {
-        int threads = 256;
-        int64_t blocks = (n_hulls + threads - 1) / threads;
+        const int threads = gjk::PREP_WARPS * 32;
+        const int64_t blocks = (n_hulls + gjk::PREP_WARPS * 32 - 1) / (gjk::PREP_WARPS * 32);
         if (prof) CU(cudaEventRecord(ctx->ev[0], st));
         gjk::hull_prep_kernel<<<(unsigned)blocks, threads, 0, st>>>(verts, hull_off, n_hulls, ctx->d_sphere);
         if (prof) { CU(cudaEventRecord(ctx->ev[1], st)); ctx->ev_valid[0] = true; }
@@ -810,7 +810,7 @@ static int broadphase_count(gjkepa_ctx *ctx, int64_t n, const double *d_verts, c
     int64_t *d_cnt = (int64_t *)(w + L.o_cnt), *d_offs = (int64_t *)(w + L.o_off);
     const int threads = 256;
     const unsigned blocks = (unsigned)(((n + threads - 1) / threads) < (int64_t)ctx->sm_count * 16 ? ((n + threads - 1) / threads) : (int64_t)ctx->sm_count * 16);
-    gjk::hull_prep_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(d_verts, d_hull_off, n, ctx->d_sphere);
+    gjk::hull_prep_kernel<<<(unsigned)((n + gjk::PREP_WARPS * 32 - 1) / (gjk::PREP_WARPS * 32)), gjk::PREP_WARPS * 32, 0, st>>>(d_verts, d_hull_off, n, ctx->d_sphere);
     bp::bounds_init_kernel<<<1, 1, 0, st>>>(d_b);
     bp::bounds_kernel<<<blocks, threads, 0, st>>>(ctx->d_sphere, n, d_b);
     bp::keys_kernel<<<blocks, threads, 0, st>>>(ctx->d_sphere, n, d_b, k0, i0);

@@ -63,7 +63,11 @@ typedef struct gjkepa_ctx gjkepa_ctx;
 #define GJKEPA_ST_BAD_HINT     (1u << 31)  /* the pair has a hull larger than the bound given to gjkepa_set_max_hull_vertices:
                                               NOT processed (flag 0, outputs zero); fix the bound or set it to 0 */
 
-/* ---- context: one per GPU (one process per GPU; pairs shard by index across contexts) ---- */
+/* ---- context: one per GPU (one process per GPU; pairs shard by index across contexts) ----
+ * Threading: a context owns its stream and its workspace and is used by ONE host thread at a time (several contexts on
+ * one device may run from several threads).  gjkepa_pair_f64 is safe to call from any number of threads, OpenMP
+ * threads included -- the reference is callable from an !$OMP PARALLEL DO (THREADPRIVATE scratch, F:55-60) -- but its
+ * callers take turns on one process-wide context: a host loop over pairs belongs in gjkepa_batch_f64. */
 int  gjkepa_create(gjkepa_ctx **ctx, int32_t device);
 int  gjkepa_destroy(gjkepa_ctx *ctx);
 /* A new context launches on its own non-blocking stream.  gjkepa_set_stream switches to the

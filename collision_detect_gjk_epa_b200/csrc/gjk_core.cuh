@@ -596,7 +596,8 @@ GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, cons
         bool ok = true;
         md3 = MathFast::nrm(c3, ok);
         q3 = MathFast::dv(c3, md3, ok);
-        if (!ok) { w.fl |= WF_COLD; bool dummy = true; md3 = MathCold::nrm(c3, dummy); q3 = (md3 > 0.0) ? MathCold::dv(c3, md3, dummy) : O; }
+        // cold redo with the IEEE operators; a NaN norm divides as IEEE does (c3 / NaN), only an exactly zero one is skipped
+        if (!ok) { w.fl |= WF_COLD; bool dummy = true; md3 = MathCold::nrm(c3, dummy); q3 = (md3 == 0.0) ? O : MathCold::dv(c3, md3, dummy); }
     }
     dir = (md3 < 1.0e-12) ? O : q3;                                          // UTZVEC
     // the triangle is face (1,2,3) of the tetrahedron to come: (S1-S2)x(S2-S3) has the operands of c3 with
@@ -680,7 +681,10 @@ GJK_HD int walk_test(const G &g, Walk &w, Pick &pk, bool live)
             uk = dot3(q, refp);
         }
         const bool flp = sk < 0.0;
-        const double wv = flp ? uk : negd(uk);                              // DOT(-nml, simplex_(ref,:) - O)
+        double wv = flp ? uk : negd(uk);                                    // DOT(-nml, simplex_(ref,:) - O)
+        // MAXLOC split over lanes must stay the sequential rule (face 0 seeds, later faces need a strict >) when a value is
+        // NaN, or the lanes would disagree on the winner: a NaN on face 0 wins outright, a NaN elsewhere never does
+        if (L > 1 && wv != wv) wv = (f == 0) ? HUGE_VAL : -HUGE_VAL;
         if (j == 0 || wv > wbest) { wbest = wv; fbest = f; qbest = q; mbest = F.md[j]; flbest = flp; }   // MAXLOC: first maximum
     }
     g.argmax_first(wbest, fbest);
@@ -698,6 +702,15 @@ GJK_HD int walk_test(const G &g, Walk &w, Pick &pk, bool live)
     else if (w.iters + 1 > 50) { w.iters = 50; e = EXIT_LOOP_CAP; }         // F:186
     else ++w.iters;
     return e;
+}
+
+// F:203 calls DIST_PF_SIGN, whose UNINML (F:1392) returns the zero vector unless some |cross component| > 1e-12, and a
+// zero normal is the reference's READ/STOP path (F:1369).  With finite vertices that cannot follow a norm >= 1e-8; with
+// Inf/NaN vertices it can (norm NaN passes F:199, every component NaN fails F:1392).  Cold: only a NaN norm gets here.
+GJK_HD_NOINLINE bool walk_stop_nan(Vec3 s0, Vec3 s1, Vec3 s2)
+{
+    const Vec3 c = cross3(s1 - s0, s2 - s1);
+    return !(fabs(c.x) > 1.0e-12 || fabs(c.y) > 1.0e-12 || fabs(c.z) > 1.0e-12);
 }
 
 // second half: support along the chosen face's normal, new tetrahedron (in place), degenerate cases.
@@ -726,6 +739,7 @@ GJK_HD int walk_step(const G &g, const HV &A, const HV &B, Walk &w, const Pick &
     // degenerate cases against the kept face, F:199-206
     int e = 0;
     if (pk.mk < 1.0e-8) e = EXIT_LOOP_COLLINEAR;
+    else if (pk.mk != pk.mk && live && walk_stop_nan(w.S[0], w.S[1], w.S[2])) { w.fl |= WF_STOP; e = EXIT_STOP; }
     else if (fabs(dot3(sp - w.S[0], pk.qk)) < 1.0e-8) e = EXIT_LOOP_COPLANAR;
     else if (sep) e = EXIT_EARLY_OUT;                                       // reference exits first: same status when both apply
     return e;

@@ -420,7 +420,7 @@ gjk_walk_kernel(TwoStageArgs ta)
         const int e = e1 ? e1 : e2;
         if (active && e) {
             if (a.collision) a.collision[p] = coll ? 1 : 0;
-            if (a.status) a.status[p] = (uint32_t)e | ((uint32_t)iters_out << 8) | ((w.fl & WF_COLD) ? (1u << 30) : 0u);
+            if (a.status) a.status[p] = (uint32_t)e | ((uint32_t)iters_out << 8) | ((w.fl & WF_COLD) ? (1u << 30) : 0u) | (e == EXIT_STOP ? (1u << 25) : 0u);
             active = false;
         }
         __syncwarp();

@@ -234,3 +234,38 @@ CONFIGS = {
     "cfg4": (make_mixed, dict(sigma=0.25), "epa"),
     "cfg4deep": (make_pairs, dict(kind="hull", n_vert=64, sigma=0.05), "epa"),
 }
+
+
+def make_nonfinite(kind: str, n_pairs: int = 20000, n_vert: int = 8, seed: int = 11) -> PairBatch:
+    """Random hull pairs with a tenth of the bodies corrupted: one coordinate NaN ("nan") or +-Inf ("inf"), every
+    coordinate Inf ("infall"), scaled by 1e300 / 1e150 / 1e-160 ("huge2" / "huge" / "tiny"), or all zero ("zero");
+    "tiny2" scales everything by 1e-300 and "far" shifts everything by 1e12.  Garbage in -- the reference would print
+    and STOP on some of it -- but the flag path is still fully defined arithmetic, so the kernels must follow the oracle."""
+    b = make_pairs("hull", n_pairs, 0.7, seed=seed, n_vert=n_vert)
+    rng = np.random.default_rng(seed + 1000)
+    v = b.verts.reshape(-1, 3, n_vert)
+    m = len(v)
+    idx = rng.integers(0, m, size=m // 10)
+    ax, vx = rng.integers(0, 3, len(idx)), rng.integers(0, n_vert, len(idx))
+    if kind == "nan":
+        v[idx, ax, vx] = np.nan
+    elif kind == "inf":
+        v[idx, ax, vx] = np.inf * rng.choice([-1.0, 1.0], len(idx))
+    elif kind == "infall":
+        v[idx] = np.inf
+    elif kind == "huge2":
+        v[idx] *= 1e300
+    elif kind == "huge":
+        v[idx] *= 1e150
+    elif kind == "tiny":
+        v[idx] *= 1e-160
+    elif kind == "tiny2":
+        v *= 1e-300
+    elif kind == "far":
+        v += 1e12
+    elif kind == "zero":
+        v[idx] = 0.0
+    else:
+        raise ValueError(kind)
+    b.name = f"nonfinite_{kind}"
+    return b

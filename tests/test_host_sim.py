@@ -122,3 +122,19 @@ def test_early_out_e1_never_changes_a_flag(orc, W, host_sim, maker, kw):
     assert e1.sum() > 0 and not o["collision"][e1].any()
     assert np.array_equal(st[~e1] & 0xffff, o["status"][~e1] & 0xffff)       # everything else untouched
     assert np.all(ns[e1] <= o["n_support"][e1]) and ns[e1].sum() < o["n_support"][e1].sum()
+
+
+@pytest.mark.parametrize("kind", ["nan", "inf", "infall", "huge2", "huge", "tiny", "tiny2", "far", "zero"])
+@pytest.mark.parametrize("n_vert", [8, 20])
+def test_core_follows_the_oracle_on_nonfinite_and_extreme_inputs(orc, W, host_sim, kind, n_vert):
+    """NaN / Inf / overflowing / underflowing vertices: every shortcut of the core (shared face normals, one-pass +-d
+    supports, sqrt of the max instead of max of sqrt, ...) must still give the oracle's flags, exit paths and support
+    counts.  Inf inputs reach the reference's READ/STOP inside the loop (F:203 -> F:1392 -> F:1369), defined as FALSE +
+    STOP status by the oracle."""
+    b = W.make_nonfinite(kind, 20000, n_vert, seed=n_vert)
+    with np.errstate(all="ignore"):
+        col, st, ns, _ = run_sim(host_sim, b)
+        o = orc.batch(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=orc.MODE_GJK)
+    assert np.array_equal(col, o["collision"])
+    assert np.array_equal(st & 0xffff, o["status"] & 0xffff)
+    assert np.array_equal(ns, o["n_support"])

@@ -285,6 +285,8 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     mode &= ~GJKEPA_MODE_NO_CLEAR_;
     if (n_pairs < 0 || n_hulls < 0 || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL)
         return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or mode");
+    if (n_pairs > 0x7fffffffLL || n_hulls > 0x7fffffffLL)      // pair and hull numbers travel as int32 (pair lists, work lists)
+        return fail(ctx, GJKEPA_ERR_ARG, "more than 2^31-1 pairs or hulls in one call: split the batch");
     if (n_pairs > 0 && (!verts || !hull_off || !pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

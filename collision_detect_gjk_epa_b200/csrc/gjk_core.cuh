@@ -487,7 +487,8 @@ enum : unsigned { WF_FIRST = 2u, WF_HAVE2 = 8u, WF_COLD = 16u, WF_STOP = 32u, WF
 // s.d < -m proves the Minkowski difference lies in the half-space x.d < -m: the origin is outside, the hulls are at least
 // m apart.  The reference can only answer TRUE with the origin inside -- or within its 1e-8 on-face band of -- a
 // tetrahedron of Minkowski-difference points, and every other exit of it is FALSE, so it answers FALSE for such a pair
-// whichever way its walk goes on; leaving here changes the exit path and the iteration count, not the flag.  (Caveat kept
+// whichever way its walk goes on; leaving here changes the exit path and the iteration count, not the flag.  The same
+// argument makes the envelope-sphere test (F:76-77) redundant for the flag, so E1 drops it and its two passes over the hulls.  (Caveat kept
 // from the survey: IS_INSIDE_PF tests the band on an XY projection, so a face within ~1e-8/m rad of vertical with the
 // origin within 1e-8 of its plane could give a spurious TRUE the shortcut would not reproduce; m is 100x the band.)
 constexpr double EARLY_OUT_MARGIN = 1.0e-6;
@@ -569,7 +570,9 @@ GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, cons
     w.S[0] = w.S[1] = w.S[2] = w.S[3] = O;
     w.qk = O; w.mk = 0.0; w.D1 = O; w.k1 = 2; w.iters = 0; w.n_support = 0; w.fl = WF_FIRST | (early ? WF_EARLY : 0u);
 
-    if (!sphere_hit(sa, sb)) return EXIT_SPHERE;                              // F:76-77
+    // F:76-77.  With shortcut E1 the test is skipped (and the spheres need not be computed): the spheres enclose the hulls, so a
+    // miss means the hulls are more than 1.0 apart, which the walk finds out on its own -- same flag, different exit path
+    if (!early && !sphere_hit(sa, sb)) return EXIT_SPHERE;
     int it = 0;
     for (;;) {
         ++it;

@@ -285,8 +285,11 @@ gjk_init_kernel(TwoStageArgs ta)
             A.col = col; A.n = nA; A.h = hA;
             B.col = col + 3 * hA * T2_PITCH; B.n = nB; B.h = hB;
             Sphere sa, sb;
-            if (FUSE) { sa = hull_sphere_t2(A); sb = hull_sphere_t2(B); }
-            else      { sa = a.sphere[m.ha];    sb = a.sphere[m.hb]; }
+            sa.cx = sa.cy = sa.cz = sa.r = 0.0; sb = sa;
+            if (!a.early_out) {                              // E1 skips the sphere test (gjk_init)
+                if (FUSE) { sa = hull_sphere_t2(A); sb = hull_sphere_t2(B); }
+                else      { sa = a.sphere[m.ha];    sb = a.sphere[m.hb]; }
+            }
             e = gjk_init(g, A, B, sa, sb, w, a.early_out != 0);
             if (e > 0) {
                 if (a.collision) a.collision[p] = exit_is_collision(e) ? 1 : 0;

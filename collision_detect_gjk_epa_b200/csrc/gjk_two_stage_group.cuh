@@ -92,8 +92,9 @@ gjk_init_group_kernel(TwoStageArgs ta, int slot_doubles)
             A.x = slot; A.y = slot + GA.n; A.z = slot + 2 * GA.n; A.n = GA.n;
             B.x = slot + 3 * GA.n; B.y = B.x + GB.n; B.z = B.y + GB.n; B.n = GB.n;
             Sphere sa, sb;
-            if (FUSE) { sa = group_sphere(g, A); sb = group_sphere(g, B); }
-            else      { sa = a.sphere[ha];       sb = a.sphere[hb]; }
+            if (a.early_out) { sa.cx = sa.cy = sa.cz = sa.r = 0.0; sb = sa; }     // E1 skips the sphere test (gjk_init)
+            else if (FUSE) { sa = group_sphere(g, A); sb = group_sphere(g, B); }
+            else           { sa = a.sphere[ha];       sb = a.sphere[hb]; }
             e = gjk_init(g, A, B, sa, sb, w, a.early_out != 0);
             if (e > 0) {
                 const bool coll = exit_is_collision(e);

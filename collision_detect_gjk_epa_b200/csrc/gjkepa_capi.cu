@@ -332,8 +332,8 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
 
     ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = false;
     const bool prof = ctx->profiling;
-    // K0
-    if (!fuse) {
+    // K0 (not needed under shortcut E1, which drops the sphere test)
+    if (!fuse && !(ctx->early_out && use_tile && !ctx->single_kernel)) {
         const int threads = gjk::PREP_WARPS * 32;
         const int64_t blocks = (n_hulls + gjk::PREP_WARPS * 32 - 1) / (gjk::PREP_WARPS * 32);
         if (prof) CU(cudaEventRecord(ctx->ev[0], st));

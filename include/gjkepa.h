@@ -102,7 +102,9 @@ int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
  * along a unit direction d has s.d < -1e-6, which proves the hulls are apart; the reference answers FALSE for every
  * such pair (all its failure exits are FALSE, TRUE needs the origin inside or within 1e-8 of a tetrahedron of
  * Minkowski points), so the FLAGS are unchanged -- tests/test_gpu_parity.py checks that on every workload -- while the
- * exit path of those pairs reads GJKEPA_EXIT_EARLY_OUT and the walk is ~2x shorter for separated pairs. */
+ * exit path of those pairs reads GJKEPA_EXIT_EARLY_OUT and the walk is ~2x shorter for separated pairs.  The envelope-
+ * sphere test (F:76-77) is dropped as well under this knob -- a sphere miss implies separation, which the walk detects --
+ * so GJKEPA_EXIT_SPHERE is not reported either. */
 #define GJKEPA_TUNE_EARLY_OUT      5
 #define GJKEPA_EXIT_EARLY_OUT      13
 int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);

@@ -119,9 +119,12 @@ def test_early_out_e1_never_changes_a_flag(orc, W, host_sim, maker, kw):
     o = orc.batch(b.verts, b.hull_off, b.pair_a, b.pair_b, mode=orc.MODE_GJK)
     assert np.array_equal(col, o["collision"])
     e1 = (st & 0xff) == 13
-    assert e1.sum() > 0 and not o["collision"][e1].any()
-    assert np.array_equal(st[~e1] & 0xffff, o["status"][~e1] & 0xffff)       # everything else untouched
-    assert np.all(ns[e1] <= o["n_support"][e1]) and ns[e1].sum() < o["n_support"][e1].sum()
+    sph = (o["status"] & 0xff) == 1                                          # E1 also drops the sphere test: these walk on
+    assert e1.sum() > 0 and not o["collision"][e1].any() and not col[sph].any()
+    keep = ~e1 & ~sph
+    assert np.array_equal(st[keep] & 0xffff, o["status"][keep] & 0xffff)     # everything else untouched
+    w = e1 & ~sph
+    assert np.all(ns[w] <= o["n_support"][w]) and ns[w].sum() < o["n_support"][w].sum()
 
 
 @pytest.mark.parametrize("kind", ["nan", "inf", "infall", "huge2", "huge", "tiny", "tiny2", "far", "zero"])

@@ -69,6 +69,8 @@ class ClockSampler(threading.Thread):
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self._halt = threading.Event()
+        self.live = threading.Event()       # samples are taken only while a timed region runs
+        self.live.set()
         self.ok = False
         try:
             import pynvml
@@ -92,6 +94,9 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
         }
         while not self._halt.is_set():
+            if not self.live.is_set():
+                time.sleep(self.period)
+                continue
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -233,7 +238,7 @@ def main():
         step_device()
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    sampler.live.clear()
     ms_total = e0.elapsed_time(e1)
     launches = eng.launch_count()
     # per-kernel durations: one more (untimed) profiled step gives a per-launch sample of each kernel
@@ -280,11 +285,13 @@ def main():
     for _ in range(2):
         eng.batch_host(*h_in, mode=mode, out=h_out)
     barrier()
+    sampler.live.set()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         eng.batch_host(*h_in, mode=mode, out=h_out)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()      # sampled through both timed regions (device-resident steps, then end-to-end steps)
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

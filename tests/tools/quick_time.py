@@ -3,7 +3,7 @@
 import os, sys
 from pathlib import Path
 import numpy as np
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 import torch
 from collision_detect_gjk_epa_b200 import Engine, workloads as W

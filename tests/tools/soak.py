@@ -4,7 +4,7 @@ Flags and GJK status words bit-exact, depths within 1e-9 relative.  Prints one l
 import os, sys, time
 from pathlib import Path
 import numpy as np
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 from collision_detect_gjk_epa_b200 import Engine, workloads as W
 from oracle import orc

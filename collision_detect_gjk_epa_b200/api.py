@@ -259,7 +259,7 @@ class Engine:
     # ---- scene step: poses in, contacts out (gjkepa_scene_posed_f64) ----
     def scene_posed(self, body_shape, pose, mode="epa", version: int = 1, tol_ff: float = 1.0, cap: int = 0) -> dict:
         """Pose application + candidate pairs + GJK/EPA over them in one call; returns only the CONTACTS:
-        body_a, body_b (a < b, in the broad phase's order), depth, normal (mode >= "epa"), point, nearest, colli_type
+        body_a, body_b (a < b, rows sorted by (body_a, body_b)), depth, normal (mode >= "epa"), point, nearest, colli_type
         (mode "full"), n_candidates, n_contacts.  Same results as broadphase_posed -> batch_posed -> keep collisions."""
         mode = _MODES[mode]
         body_shape = np.ascontiguousarray(body_shape, dtype=np.int32)

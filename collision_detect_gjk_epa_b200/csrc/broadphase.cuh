@@ -18,7 +18,7 @@ namespace bp {
 
 using gjk::Sphere;
 
-struct Bounds { unsigned long long min_key[3]; unsigned long long max_r_key; unsigned long long max_key[3]; };   // order-preserving keys of doubles
+struct Bounds { unsigned long long min_key[3]; unsigned long long max_r_key; unsigned long long max_key[3]; double slack; };   // order-preserving keys of doubles
 
 __device__ __forceinline__ unsigned long long dkey(double v)
 {   // monotone map double -> uint64 (-0 canonicalised)
@@ -35,8 +35,10 @@ __host__ __device__ __forceinline__ double dkey_inv(unsigned long long k)
 #endif
 }
 
-__global__ void bounds_init_kernel(Bounds *b)
+// slack: the absolute term of the sphere test, 1.0 in the reference (F:1185)
+__global__ void bounds_init_kernel(Bounds *b, double slack)
 {
+    b->slack = slack;
     b->min_key[0] = b->min_key[1] = b->min_key[2] = ~0ull; b->max_r_key = 0ull;
     b->max_key[0] = b->max_key[1] = b->max_key[2] = 0ull;
 }
@@ -67,13 +69,14 @@ bounds_kernel(const Sphere *__restrict__ s, int64_t n, Bounds *b)
     }
 }
 
-struct Grid { double ox, oy, oz, h; long long nx, ny, nz; bool exact; };   // n*: largest cell index per axis; exact: keys never alias
+struct Grid { double ox, oy, oz, h, slack; long long nx, ny, nz; bool exact; };   // n*: largest cell index per axis; exact: keys never alias
 __device__ __forceinline__ Grid grid_of(const Bounds *b)
 {
     Grid g;
     g.ox = dkey_inv(b->min_key[0]); g.oy = dkey_inv(b->min_key[1]); g.oz = dkey_inv(b->min_key[2]);
     const double rmax = dkey_inv(b->max_r_key);
-    g.h = (2.0 * rmax + 1.0) * (1.0 + 1.0e-9);
+    g.slack = b->slack;
+    g.h = (2.0 * rmax + g.slack) * (1.0 + 1.0e-9);
     g.nx = (long long)floor((dkey_inv(b->max_key[0]) - g.ox) / g.h);
     g.ny = (long long)floor((dkey_inv(b->max_key[1]) - g.oy) / g.h);
     g.nz = (long long)floor((dkey_inv(b->max_key[2]) - g.oz) / g.h);
@@ -101,6 +104,12 @@ keys_kernel(const Sphere *__restrict__ s, int64_t n, const Bounds *__restrict__ 
         keys[i] = cell_key(ix, iy, iz);
         ids[i] = (int32_t)i;
     }
+}
+
+// F:1185 with the absolute term as a parameter: NORM2(mp1 - mp2) <= r1 + r2 + slack (slack = 1.0: gjk::sphere_hit, bit for bit)
+__device__ __forceinline__ bool sphere_pass(const Sphere &a, const Sphere &b, double slack)
+{
+    return gjk::norm3(gjk::v3(a.cx, a.cy, a.cz) - gjk::v3(b.cx, b.cy, b.cz)) <= gjk::add(gjk::add(a.r, b.r), slack);
 }
 
 __device__ __forceinline__ int64_t lower_bound(const unsigned long long *k, int64_t n, unsigned long long v)
@@ -138,7 +147,7 @@ pairs_kernel(const Sphere *__restrict__ s, int64_t n, const Bounds *__restrict__
                 for (int64_t u = lower_bound(skeys, n, klo); u < n && skeys[u] <= khi; ++u) {
                     const int32_t j = sids[u];
                     if (j <= i) continue;
-                    if (gjk::sphere_hit(si, s[j])) {                 // F:1185, the reference's own test
+                    if (sphere_pass(si, s[j], g.slack)) {             // F:1185, the reference's own test
                         if (FILL) { const int64_t o = out0 + cnt; if (o < cap) { pair_a[o] = i; pair_b[o] = j; } }
                         ++cnt;
                     }
@@ -155,7 +164,7 @@ pairs_kernel(const Sphere *__restrict__ s, int64_t n, const Bounds *__restrict__
             for (int64_t u = lower_bound(skeys, n, key); u < n && skeys[u] == key; ++u) {
                 const int32_t j = sids[u];
                 if (j <= i) continue;
-                if (gjk::sphere_hit(si, s[j])) {                     // F:1185, the reference's own test
+                if (sphere_pass(si, s[j], g.slack)) {                 // F:1185, the reference's own test
                     if (FILL) { const int64_t o = out0 + cnt; if (o < cap) { pair_a[o] = i; pair_b[o] = j; } }
                     ++cnt;
                 }

@@ -9,7 +9,7 @@
 namespace scene {
 
 struct GatherArgs {
-    const int32_t *order;                // colliding candidates, ascending
+    const int32_t *order;                // colliding candidates, in (body a, body b) order
     int64_t n;
     const int32_t *cand_a, *cand_b;
     const double *depth, *normal, *point, *nearest;   // per candidate (normal/point 3, nearest 6 doubles); may be null
@@ -18,6 +18,18 @@ struct GatherArgs {
     double *o_depth, *o_normal, *o_point, *o_nearest;
     int32_t *o_type;
 };
+
+// sort key of a contact: (body a, body b) -- the contact list comes out in lexicographic order whatever order the broad
+// phase found the candidates in
+__global__ void __launch_bounds__(256)
+contact_keys_kernel(const int32_t *__restrict__ idx, int64_t n, const int32_t *__restrict__ cand_a, const int32_t *__restrict__ cand_b,
+                    unsigned long long *__restrict__ keys)
+{
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx[k];
+        keys[k] = ((unsigned long long)(uint32_t)cand_a[i] << 32) | (unsigned long long)(uint32_t)cand_b[i];
+    }
+}
 
 __global__ void __launch_bounds__(256)
 gather_kernel(GatherArgs g)

@@ -186,7 +186,7 @@ int gjkepa_broadphase_posed_f64(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t
  * For a simulation whose shapes are resident (gjkepa_shapes_upload): per step 96 B per body go to the device and only
  * the CONTACTS come back -- the candidate list never crosses PCIe.  Equivalent, result for result, to
  *     gjkepa_broadphase_posed_f64 -> gjkepa_batch_posed_f64 on its pairs -> keep the pairs whose collision_ is TRUE:
- * body_a/body_b (a < b) name the colliding bodies in the broad phase's order; depth/normal (mode >= EPA) and
+ * body_a/body_b (a < b) name the colliding bodies, rows sorted by (body_a, body_b); depth/normal (mode >= EPA) and
  * point/nearest/colli_type (mode FULL) are GJKEPA's outputs for that pair (F:47-52); any of them may be NULL.
  * All output arrays have `cap` rows; *n_contacts may exceed cap (then the first cap were written). */
 int gjkepa_scene_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,

@@ -114,14 +114,24 @@ def test_scene_step_equals_broadphase_then_narrow_phase(W, orc, engine, mode):
     nar = engine.batch_posed(pb.body_shape, pb.pose, ga, gb, mode=mode)
     hit = nar["collision"] > 0
     assert sc["n_candidates"] == len(ga) and sc["n_contacts"] == int(hit.sum()) and 0.02 < hit.mean() < 0.9
-    assert np.array_equal(sc["body_a"], ga[hit]) and np.array_equal(sc["body_b"], gb[hit])
+    order = np.lexsort((gb[hit], ga[hit]))                                   # the scene step sorts its rows by (body_a, body_b)
+    assert np.array_equal(sc["body_a"], ga[hit][order]) and np.array_equal(sc["body_b"], gb[hit][order])
     for k in ("depth", "normal", "point", "nearest", "colli_type"):
         assert (k in sc) == (k in nar)
         if k in sc:
-            assert np.array_equal(sc[k], nar[k][hit]), k
+            assert np.array_equal(sc[k], nar[k][hit][order]), k
     verts, off = orc.apply_pose(pb.shape_verts, pb.shape_off, pb.body_shape, pb.pose)
     ref = orc.batch(verts, off, ga, gb, mode=orc.MODE_GJK)
     assert np.array_equal(ref["collision"] > 0, hit)
+    # shortcut E1 (opt-in): candidates shrink to the pairs whose spheres really touch, separated pairs leave early -- the
+    # contact list must not change by a bit
+    engine.set_tuning(engine.TUNE_EARLY_OUT, 1)
+    fast = engine.scene_posed(pb.body_shape, pb.pose, mode=mode)
+    engine.set_tuning(engine.TUNE_EARLY_OUT, 0)
+    assert fast["n_candidates"] < sc["n_candidates"] and fast["n_contacts"] == sc["n_contacts"]
+    for k in ("body_a", "body_b", "depth", "normal", "point", "nearest", "colli_type"):
+        if k in sc:
+            assert np.array_equal(fast[k], sc[k]), k
     small = engine.scene_posed(pb.body_shape, pb.pose, mode=mode, cap=7)        # too small a first guess: grows
     assert small["n_contacts"] == sc["n_contacts"] and np.array_equal(small["body_a"], sc["body_a"])
 

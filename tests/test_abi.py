@@ -46,5 +46,9 @@ def test_product_does_not_touch_the_oracle():
     bad = re.compile(r"(from\s+oracle|import\s+oracle|oracle/|gjkepa_oracle|orc_gjkepa|liborc)")
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("Makefile")):
         assert not bad.search(p.read_text()), p
+    # developer tools outside tests/ do not use it either (gen_dirtable.py only WRITES the direction table both sides include)
+    imp = re.compile(r"(from\s+oracle|import\s+oracle)")
+    for p in (ROOT / "tools").glob("*.py"):
+        assert not imp.search(p.read_text()), p
     out = __import__("subprocess").run(["ldd", str(pkg / "libgjkepa_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out

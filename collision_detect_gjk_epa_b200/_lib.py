@@ -17,12 +17,14 @@ CSRC = _PKG / "csrc"
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM = 0, 1, 2, 3
 MODE_GJK, MODE_EPA, MODE_FULL = 0, 1, 2
+MODE_COMPACT = 16
 
 # every symbol include/gjkepa.h declares
 SYMBOLS = [
     "gjkepa_create", "gjkepa_destroy", "gjkepa_set_stream", "gjkepa_use_own_stream", "gjkepa_last_error",
     "gjkepa_launch_count", "gjkepa_set_lanes", "gjkepa_set_max_hull_vertices", "gjkepa_set_tuning", "gjkepa_set_profiling", "gjkepa_kernel_ms", "gjkepa_pair_f64", "gjkepa_batch_f64",
     "gjkepa_batch_device_f64", "gjkepa_sync", "gjkepa_debug_fp64", "gjkepa_shapes_upload", "gjkepa_batch_posed_f64", "gjkepa_broadphase_f64", "gjkepa_broadphase_posed_f64", "gjkepa_batch_f32", "gjkepa_scene_posed_f64",
+    "gjkepa_create_multi", "gjkepa_device_count", "gjkepa_host_register", "gjkepa_host_unregister", "gjkepa_store_upload", "gjkepa_batch_resident_f64",
 ]
 
 
@@ -56,6 +58,19 @@ def lib() -> C.CDLL:
     vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
     L.gjkepa_create.argtypes = [C.POINTER(vp), C.c_int32]
     L.gjkepa_create.restype = C.c_int
+    L.gjkepa_create_multi.argtypes = [C.POINTER(vp), ip, C.c_int32]
+    L.gjkepa_create_multi.restype = C.c_int
+    L.gjkepa_device_count.argtypes = [vp]
+    L.gjkepa_device_count.restype = C.c_int32
+    L.gjkepa_host_register.argtypes = [vp, C.c_int64]
+    L.gjkepa_host_register.restype = C.c_int
+    L.gjkepa_host_unregister.argtypes = [vp]
+    L.gjkepa_host_unregister.restype = C.c_int
+    L.gjkepa_store_upload.argtypes = [vp, C.c_int64, vp, vp]
+    L.gjkepa_store_upload.restype = C.c_int
+    L.gjkepa_batch_resident_f64.argtypes = [vp, C.c_int32, C.c_double, C.c_int64, vp, vp, C.c_int32,
+                                            vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.gjkepa_batch_resident_f64.restype = C.c_int
     L.gjkepa_destroy.argtypes = [vp]
     L.gjkepa_destroy.restype = C.c_int
     L.gjkepa_set_stream.argtypes = [vp, vp]

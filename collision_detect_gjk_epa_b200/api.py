@@ -36,18 +36,27 @@ def _np_ptr(a: Optional[np.ndarray]):
 
 
 class Engine:
-    """One narrow-phase context bound to one GPU (wraps gjkepa_create/gjkepa_destroy)."""
+    """One narrow-phase context: bound to one GPU (gjkepa_create), or spread over several GPUs of the box
+    (``devices=[...]`` or ``devices="all"`` -> gjkepa_create_multi: the host-buffer batch calls then split the pair
+    list into one contiguous range per device and every device copies its results into the caller's arrays)."""
 
-    def __init__(self, device: int = 0, lanes: int = 0):
+    def __init__(self, device: int = 0, lanes: int = 0, devices=None):
         self._L = _lib.lib()
         h = C.c_void_p()
-        rc = self._L.gjkepa_create(C.byref(h), int(device))
+        if devices is not None:
+            devs = [] if devices == "all" else [int(d) for d in devices]
+            arr = (C.c_int32 * max(len(devs), 1))(*devs)
+            rc = self._L.gjkepa_create_multi(C.byref(h), arr if devs else None, len(devs))
+            device = devs[0] if devs else 0
+        else:
+            rc = self._L.gjkepa_create(C.byref(h), int(device))
         if rc != _lib.OK or not h:
             raise GjkEpaError(
                 f"gjkepa_create(device={device}) failed with code {rc}: no usable sm_100a CUDA device "
                 "(this package has no CPU fallback)")
         self._h = h
         self.device = int(device)
+        self.n_devices = int(self._L.gjkepa_device_count(h))
         if lanes:
             self.set_lanes(lanes)
 
@@ -73,10 +82,10 @@ class Engine:
     def set_max_hull_vertices(self, n: int):
         self._check(self._L.gjkepa_set_max_hull_vertices(self._h, int(n)), "gjkepa_set_max_hull_vertices")
 
-    TUNE_WALK_REFILL, TUNE_SINGLE_KERNEL, TUNE_EPA_GENERAL, TUNE_TILE_MAX_VERTICES, TUNE_EARLY_OUT = 1, 2, 3, 4, 5
+    TUNE_WALK_REFILL, TUNE_SINGLE_KERNEL, TUNE_EPA_GENERAL, TUNE_TILE_MAX_VERTICES, TUNE_EARLY_OUT, TUNE_HOST_CHUNKS = 1, 2, 3, 4, 5, 6
 
     def set_tuning(self, key: int, value: int):
-        """GJKEPA_TUNE_* knobs of include/gjkepa.h (walk re-pack threshold, single-kernel A/B switch)."""
+        """GJKEPA_TUNE_* knobs of include/gjkepa.h (walk re-pack threshold, single-kernel A/B switch, host chunks)."""
         self._check(self._L.gjkepa_set_tuning(self._h, int(key), int(value)), "gjkepa_set_tuning")
 
     def set_stream(self, cuda_stream: int):
@@ -97,43 +106,55 @@ class Engine:
     def launch_count(self, reset: bool = False) -> int:
         return int(self._L.gjkepa_launch_count(self._h, 1 if reset else 0))
 
+    # ---- the output block of a host-buffer batch call and the call itself (shared by the four entry points) ----
+    @staticmethod
+    def _host_out(n: int, mode: int, real, want_status: bool, want_contacts: bool, compact: bool) -> dict:
+        out = {"collision": np.empty(n, np.uint8)}
+        if want_status:
+            out["status"] = np.empty(n, np.uint32)
+        if mode >= MODE_EPA:
+            out["depth"] = np.empty(n, real)
+            out["normal"] = np.empty((n, 3), real)
+        if mode >= MODE_FULL:
+            out["colli_type"] = np.empty(n, np.int32)
+            out["nearest"] = np.empty((n, 6), real)
+            out["point"] = np.empty((n, 3), real)
+        if want_contacts or compact:
+            out["contact_index"] = np.empty(n, np.int32)
+        return out
+
+    def _host_call(self, fn, what: str, head: tuple, n: int, mode: int, real, out, want_status, want_contacts, compact) -> dict:
+        if out is None:
+            out = self._host_out(n, mode, real, want_status, want_contacts, compact)
+        for k in ("depth", "normal", "nearest", "point"):
+            assert k not in out or out[k].dtype == real, f"{k} must be {np.dtype(real).name}"
+        counted = want_contacts or compact or "contact_index" in out
+        nc = C.c_int64(0)
+        rc = fn(self._h, *head, mode | (_lib.MODE_COMPACT if compact else 0),
+                _np_ptr(out.get("collision")), _np_ptr(out.get("colli_type")), _np_ptr(out.get("nearest")),
+                _np_ptr(out.get("normal")), _np_ptr(out.get("point")), _np_ptr(out.get("depth")),
+                _np_ptr(out.get("status")),
+                C.cast(C.byref(nc), C.c_void_p) if counted else C.c_void_p(0),
+                _np_ptr(out.get("contact_index")))
+        self._check(rc, what)
+        if counted:
+            out["n_contacts"] = int(nc.value)
+        return out
+
     # ---- HOST buffers (numpy): copies in, runs, copies out -- the reference-facing call ----
     def batch_host(self, verts, hull_off, pair_a, pair_b, mode="full", version: int = 1,
                    tol_ff: float = 1.0, out: Optional[dict] = None, want_status: bool = True,
-                   want_contacts: bool = False) -> dict:
+                   want_contacts: bool = False, compact: bool = False) -> dict:
+        """gjkepa_batch_f64.  compact=True (GJKEPA_MODE_COMPACT): depth/normal/point/nearest/colli_type/status hold one
+        row per CONTACT (pair contact_index[k], ascending; n_contacts rows are meaningful), collision stays per pair."""
         mode = _MODES[mode]
         verts = np.ascontiguousarray(verts, dtype=np.float64)
         hull_off = np.ascontiguousarray(hull_off, dtype=np.int64)
         pair_a = np.ascontiguousarray(pair_a, dtype=np.int32)
         pair_b = np.ascontiguousarray(pair_b, dtype=np.int32)
-        n = int(pair_a.shape[0])
-        nh = int(hull_off.shape[0] - 1)
-        if out is None:
-            out = {"collision": np.empty(n, np.uint8)}
-            if want_status:
-                out["status"] = np.empty(n, np.uint32)
-            if mode >= MODE_EPA:
-                out["depth"] = np.empty(n, np.float64)
-                out["normal"] = np.empty((n, 3), np.float64)
-            if mode >= MODE_FULL:
-                out["colli_type"] = np.empty(n, np.int32)
-                out["nearest"] = np.empty((n, 6), np.float64)
-                out["point"] = np.empty((n, 3), np.float64)
-            if want_contacts:
-                out["contact_index"] = np.empty(n, np.int32)
-        nc = C.c_int64(0)
-        rc = self._L.gjkepa_batch_f64(
-            self._h, int(version), float(tol_ff), nh, _np_ptr(verts), _np_ptr(hull_off), n,
-            _np_ptr(pair_a), _np_ptr(pair_b), mode,
-            _np_ptr(out.get("collision")), _np_ptr(out.get("colli_type")), _np_ptr(out.get("nearest")),
-            _np_ptr(out.get("normal")), _np_ptr(out.get("point")), _np_ptr(out.get("depth")),
-            _np_ptr(out.get("status")),
-            C.cast(C.byref(nc), C.c_void_p) if want_contacts else C.c_void_p(0),
-            _np_ptr(out.get("contact_index")))
-        self._check(rc, "gjkepa_batch_f64")
-        if want_contacts:
-            out["n_contacts"] = int(nc.value)
-        return out
+        n, nh = int(pair_a.shape[0]), int(hull_off.shape[0] - 1)
+        head = (int(version), float(tol_ff), nh, _np_ptr(verts), _np_ptr(hull_off), n, _np_ptr(pair_a), _np_ptr(pair_b))
+        return self._host_call(self._L.gjkepa_batch_f64, "gjkepa_batch_f64", head, n, mode, np.float64, out, want_status, want_contacts, compact)
 
     # ---- fp32 mode: binary32 at the boundary (gjkepa_batch_f32) ----
     def batch_host_f32(self, verts, hull_off, pair_a, pair_b, mode="full", version: int = 1, tol_ff: float = 1.0,
@@ -146,36 +167,28 @@ class Engine:
         hull_off = np.ascontiguousarray(hull_off, dtype=np.int64)
         pair_a = np.ascontiguousarray(pair_a, dtype=np.int32)
         pair_b = np.ascontiguousarray(pair_b, dtype=np.int32)
+        n, nh = int(pair_a.shape[0]), int(hull_off.shape[0] - 1)
+        head = (int(version), float(tol_ff), nh, _np_ptr(verts), _np_ptr(hull_off), n, _np_ptr(pair_a), _np_ptr(pair_b))
+        return self._host_call(self._L.gjkepa_batch_f32, "gjkepa_batch_f32", head, n, mode, np.float32, out, want_status, want_contacts, False)
+
+    # ---- hull store resident on the device(s): pair lists in, results out (gjkepa_store_upload / gjkepa_batch_resident_f64) ----
+    def upload_store(self, verts, hull_off):
+        """World-space hull store copied to every device of the context once (envelope spheres computed there)."""
+        verts = np.ascontiguousarray(verts, dtype=np.float64)
+        hull_off = np.ascontiguousarray(hull_off, dtype=np.int64)
+        self._check(self._L.gjkepa_store_upload(self._h, int(hull_off.shape[0] - 1), _np_ptr(verts), _np_ptr(hull_off)), "gjkepa_store_upload")
+
+    def batch_resident(self, pair_a, pair_b, mode="full", version: int = 1, tol_ff: float = 1.0, out: Optional[dict] = None,
+                       want_status: bool = True, want_contacts: bool = False, compact: bool = False) -> dict:
+        """batch_host against the uploaded store: 8 B per pair go to the device, the results (or, with compact=True,
+        only the contacts' rows) come back."""
+        mode = _MODES[mode]
+        pair_a = np.ascontiguousarray(pair_a, dtype=np.int32)
+        pair_b = np.ascontiguousarray(pair_b, dtype=np.int32)
         n = int(pair_a.shape[0])
-        nh = int(hull_off.shape[0] - 1)
-        if out is None:
-            out = {"collision": np.empty(n, np.uint8)}
-            if want_status:
-                out["status"] = np.empty(n, np.uint32)
-            if mode >= MODE_EPA:
-                out["depth"] = np.empty(n, np.float32)
-                out["normal"] = np.empty((n, 3), np.float32)
-            if mode >= MODE_FULL:
-                out["colli_type"] = np.empty(n, np.int32)
-                out["nearest"] = np.empty((n, 6), np.float32)
-                out["point"] = np.empty((n, 3), np.float32)
-            if want_contacts:
-                out["contact_index"] = np.empty(n, np.int32)
-        for k in ("depth", "normal", "nearest", "point"):
-            assert k not in out or out[k].dtype == np.float32, f"{k} must be float32"
-        nc = C.c_int64(0)
-        rc = self._L.gjkepa_batch_f32(
-            self._h, int(version), float(tol_ff), nh, _np_ptr(verts), _np_ptr(hull_off), n,
-            _np_ptr(pair_a), _np_ptr(pair_b), mode,
-            _np_ptr(out.get("collision")), _np_ptr(out.get("colli_type")), _np_ptr(out.get("nearest")),
-            _np_ptr(out.get("normal")), _np_ptr(out.get("point")), _np_ptr(out.get("depth")),
-            _np_ptr(out.get("status")),
-            C.cast(C.byref(nc), C.c_void_p) if want_contacts else C.c_void_p(0),
-            _np_ptr(out.get("contact_index")))
-        self._check(rc, "gjkepa_batch_f32")
-        if want_contacts:
-            out["n_contacts"] = int(nc.value)
-        return out
+        head = (int(version), float(tol_ff), n, _np_ptr(pair_a), _np_ptr(pair_b))
+        return self._host_call(self._L.gjkepa_batch_resident_f64, "gjkepa_batch_resident_f64", head, n, mode, np.float64, out,
+                               want_status, want_contacts, compact)
 
     # ---- shapes resident on the device, poses per call (gjkepa_shapes_upload / gjkepa_batch_posed_f64) ----
     def upload_shapes(self, shape_verts, shape_off):
@@ -186,7 +199,7 @@ class Engine:
                     "gjkepa_shapes_upload")
 
     def batch_posed(self, body_shape, pose, pair_a, pair_b, mode="full", version: int = 1, tol_ff: float = 1.0,
-                    out: Optional[dict] = None, want_status: bool = True, want_contacts: bool = False) -> dict:
+                    out: Optional[dict] = None, want_status: bool = True, want_contacts: bool = False, compact: bool = False) -> dict:
         """pose: (n_bodies, 12) = R row-major (9) + t (3); world vertex = ((r00*x + r01*y) + r02*z) + tx, applied on
         the device.  pair_a / pair_b are body numbers.  HOST buffers in and out."""
         mode = _MODES[mode]
@@ -196,32 +209,9 @@ class Engine:
         pair_b = np.ascontiguousarray(pair_b, dtype=np.int32)
         nb, n = int(body_shape.shape[0]), int(pair_a.shape[0])
         assert pose.size == 12 * nb
-        if out is None:
-            out = {"collision": np.empty(n, np.uint8)}
-            if want_status:
-                out["status"] = np.empty(n, np.uint32)
-            if mode >= MODE_EPA:
-                out["depth"] = np.empty(n, np.float64)
-                out["normal"] = np.empty((n, 3), np.float64)
-            if mode >= MODE_FULL:
-                out["colli_type"] = np.empty(n, np.int32)
-                out["nearest"] = np.empty((n, 6), np.float64)
-                out["point"] = np.empty((n, 3), np.float64)
-            if want_contacts:
-                out["contact_index"] = np.empty(n, np.int32)
-        nc = C.c_int64(0)
-        rc = self._L.gjkepa_batch_posed_f64(
-            self._h, int(version), float(tol_ff), nb, _np_ptr(body_shape), _np_ptr(pose), n,
-            _np_ptr(pair_a), _np_ptr(pair_b), mode,
-            _np_ptr(out.get("collision")), _np_ptr(out.get("colli_type")), _np_ptr(out.get("nearest")),
-            _np_ptr(out.get("normal")), _np_ptr(out.get("point")), _np_ptr(out.get("depth")),
-            _np_ptr(out.get("status")),
-            C.cast(C.byref(nc), C.c_void_p) if want_contacts else C.c_void_p(0),
-            _np_ptr(out.get("contact_index")))
-        self._check(rc, "gjkepa_batch_posed_f64")
-        if want_contacts:
-            out["n_contacts"] = int(nc.value)
-        return out
+        head = (int(version), float(tol_ff), nb, _np_ptr(body_shape), _np_ptr(pose), n, _np_ptr(pair_a), _np_ptr(pair_b))
+        return self._host_call(self._L.gjkepa_batch_posed_f64, "gjkepa_batch_posed_f64", head, n, mode, np.float64, out,
+                               want_status, want_contacts, compact)
 
     # ---- candidate pairs on the device (gjkepa_broadphase_f64 / gjkepa_broadphase_posed_f64) ----
     def _broadphase(self, call, what: str, cap: int):
@@ -299,6 +289,8 @@ class Engine:
         mode = _MODES[mode]
         dev = verts.device
         assert dev.type == "cuda" and verts.dtype == torch.float64 and hull_off.dtype == torch.int64
+        assert self.n_devices == 1 and dev.index == self.device, "tensors must live on the engine's own device"
+        assert all(t.device == dev for t in (hull_off, pair_a, pair_b)), "all inputs on one device"
         assert pair_a.dtype == torch.int32 and pair_b.dtype == torch.int32
         n = int(pair_a.shape[0])
         nh = int(hull_off.shape[0] - 1)

@@ -24,9 +24,20 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+constexpr int hostb_max_chunks = 64;
+struct HostPipe;       // host_batch.inl: chunked copy/compute pipeline of the host-buffer entries
+struct MultiDev;       // host_batch.inl: one child context + worker thread per device
 
 struct gjkepa_ctx {
     int device = 0;
@@ -68,6 +79,14 @@ struct gjkepa_ctx {
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid[3] = {false, false, false};      // K0, K1, K3 recorded by the last batch
+    // envelope spheres computed ahead of the batch (resident store, or once per host batch that is run in chunks): K0 is skipped
+    const gjk::Sphere *ext_sphere = nullptr;
+    // resident world-space hull store (gjkepa_store_upload)
+    double *d_store_verts = nullptr; int64_t *d_store_off = nullptr; gjk::Sphere *d_store_sphere = nullptr;
+    int64_t n_store_hulls = 0; int store_max_verts = 0;
+    int host_chunks = 0;           // chunks per host batch (0 = automatic)
+    HostPipe *pipe = nullptr;      // created on first use
+    MultiDev *multi = nullptr;     // gjkepa_create_multi: this context only fans out to its children
 };
 
 namespace {
@@ -89,6 +108,14 @@ static bool debug_sync_enabled() { static const bool on = [] { const char *e = g
     if (e_ != cudaSuccess) { fprintf(stderr, "gjkepa: kernel %s failed: %s\n", name, cudaGetErrorString(e_)); return fail(ctx, GJKEPA_ERR_CUDA, name, e_); } } } while (0)
 
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, GJKEPA_ERR_CUDA, #call, e_); } while (0)
+
+// every entry point runs on its context's device and hands the calling thread's current device back on return
+struct DeviceKeep {
+    int prev = -1;
+    DeviceKeep() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceKeep() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(c) DeviceKeep keep_device_; CU(cudaSetDevice((c)->device))
 
 // grow-on-demand device block (contents are not kept): 12.5 % slack so that slowly growing batches do not reallocate
 static int grow_bytes(gjkepa_ctx *ctx, void *&p, size_t &cap, size_t need, const char *what)
@@ -114,7 +141,15 @@ int ensure(gjkepa_ctx *ctx, T *&p, int64_t &cap, int64_t need)
     return GJKEPA_OK;
 }
 
+void pipe_free(gjkepa_ctx *ctx);        // host_batch.inl
+void multi_free(gjkepa_ctx *ctx);
+
 }  // namespace
+
+// a multi-device context forwards a setter to every child
+#define FORWARD_MULTI(call_on_k) do { if (ctx->multi) { int rc_ = GJKEPA_OK; for (gjkepa_ctx *k : multi_kids(ctx)) { int q_ = (call_on_k); if (q_ && !rc_) rc_ = q_; } return rc_; } } while (0)
+static const std::vector<gjkepa_ctx *> &multi_kids(const gjkepa_ctx *ctx);
+static gjkepa_ctx *first_kid(const gjkepa_ctx *ctx);
 
 extern "C" {
 
@@ -153,8 +188,14 @@ int gjkepa_create(gjkepa_ctx **out, int32_t device)
 int gjkepa_destroy(gjkepa_ctx *ctx)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
+    if (ctx->multi) { multi_free(ctx); delete ctx; return GJKEPA_OK; }
+    DeviceKeep keep_device_;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    pipe_free(ctx);
+    if (ctx->d_store_verts) cudaFree(ctx->d_store_verts);
+    if (ctx->d_store_off) cudaFree(ctx->d_store_off);
+    if (ctx->d_store_sphere) cudaFree(ctx->d_store_sphere);
     if (ctx->d_sphere) cudaFree(ctx->d_sphere);
     if (ctx->d_wl_pair) cudaFree(ctx->d_wl_pair);
     if (ctx->d_wl_simplex) cudaFree(ctx->d_wl_simplex);
@@ -188,6 +229,7 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
 int gjkepa_set_stream(gjkepa_ctx *ctx, void *s)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
+    if (ctx->multi) return fail(ctx, GJKEPA_ERR_ARG, "a multi-device context runs on its own streams");
     ctx->stream = (cudaStream_t)s;          // taken literally: NULL is CUDA's legacy default stream
     return GJKEPA_OK;
 }
@@ -195,6 +237,7 @@ int gjkepa_set_stream(gjkepa_ctx *ctx, void *s)
 int gjkepa_use_own_stream(gjkepa_ctx *ctx)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
+    if (ctx->multi) return GJKEPA_OK;
     ctx->stream = ctx->own_stream;
     return GJKEPA_OK;
 }
@@ -204,6 +247,7 @@ const char *gjkepa_last_error(const gjkepa_ctx *ctx) { return ctx ? ctx->err.c_s
 int64_t gjkepa_launch_count(const gjkepa_ctx *ctx, int32_t reset)
 {
     if (!ctx) return -1;
+    if (ctx->multi) { int64_t t = 0; for (gjkepa_ctx *k : multi_kids(ctx)) t += gjkepa_launch_count(k, reset); return t; }
     int64_t n = ctx->launches;
     if (reset) const_cast<gjkepa_ctx *>(ctx)->launches = 0;
     return n;
@@ -212,6 +256,7 @@ int64_t gjkepa_launch_count(const gjkepa_ctx *ctx, int32_t reset)
 int gjkepa_set_lanes(gjkepa_ctx *ctx, int32_t lanes)
 {
     if (!ctx || !(lanes == 0 || lanes == 1 || lanes == 2 || lanes == 4)) return GJKEPA_ERR_ARG;
+    FORWARD_MULTI(gjkepa_set_lanes(k, lanes));
     ctx->lanes = lanes;
     return GJKEPA_OK;
 }
@@ -219,6 +264,7 @@ int gjkepa_set_lanes(gjkepa_ctx *ctx, int32_t lanes)
 int gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n)
 {
     if (!ctx || n < 0) return GJKEPA_ERR_ARG;
+    FORWARD_MULTI(gjkepa_set_max_hull_vertices(k, n));
     ctx->max_hull_hint = n;
     return GJKEPA_OK;
 }
@@ -226,6 +272,12 @@ int gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n)
 int gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
+    FORWARD_MULTI(gjkepa_set_tuning(k, key, value));
+    if (key == GJKEPA_TUNE_HOST_CHUNKS) {
+        if (value < 0 || value > hostb_max_chunks) return GJKEPA_ERR_ARG;
+        ctx->host_chunks = value;
+        return GJKEPA_OK;
+    }
     if (key == GJKEPA_TUNE_WALK_REFILL) {
         if (value < 1 || value > 32) return GJKEPA_ERR_ARG;
         ctx->walk_refill = value;
@@ -245,6 +297,7 @@ int gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value)
 int gjkepa_set_profiling(gjkepa_ctx *ctx, int32_t on)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
+    FORWARD_MULTI(gjkepa_set_profiling(k, on));
     ctx->profiling = on != 0;
     return GJKEPA_OK;
 }
@@ -252,7 +305,16 @@ int gjkepa_set_profiling(gjkepa_ctx *ctx, int32_t on)
 int gjkepa_kernel_ms(gjkepa_ctx *ctx, double *ms)
 {
     if (!ctx || !ms) return GJKEPA_ERR_ARG;
-    CU(cudaSetDevice(ctx->device));
+    if (ctx->multi) {               // devices run side by side: the slowest one per kernel
+        ms[0] = ms[1] = ms[2] = 0.0;
+        for (gjkepa_ctx *k : multi_kids(ctx)) {
+            double t[3];
+            if (int rc = gjkepa_kernel_ms(k, t)) return rc;
+            for (int i = 0; i < 3; ++i) ms[i] = t[i] > ms[i] ? t[i] : ms[i];
+        }
+        return GJKEPA_OK;
+    }
+    ON_DEVICE(ctx);
     for (int k = 0; k < 3; ++k) {
         ms[k] = 0.0;
         if (!ctx->ev_valid[k]) continue;
@@ -267,7 +329,8 @@ int gjkepa_kernel_ms(gjkepa_ctx *ctx, double *ms)
 int gjkepa_sync(gjkepa_ctx *ctx)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
-    CU(cudaSetDevice(ctx->device));
+    FORWARD_MULTI(gjkepa_sync(k));
+    ON_DEVICE(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
     return GJKEPA_OK;
 }
@@ -281,6 +344,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                             uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
+    if (ctx->multi) return fail(ctx, GJKEPA_ERR_ARG, "device buffers belong to one GPU: use a single-device context");
     const bool no_clear = (mode & GJKEPA_MODE_NO_CLEAR_) != 0;
     mode &= ~GJKEPA_MODE_NO_CLEAR_;
     if (n_pairs < 0 || n_hulls < 0 || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL)
@@ -288,7 +352,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     if (n_pairs > 0x7fffffffLL || n_hulls > 0x7fffffffLL)      // pair and hull numbers travel as int32 (pair lists, work lists)
         return fail(ctx, GJKEPA_ERR_ARG, "more than 2^31-1 pairs or hulls in one call: split the batch");
     if (n_pairs > 0 && (!verts || !hull_off || !pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
-    CU(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     cudaStream_t st = ctx->stream;
 
     // outputs of non-colliding pairs are zero (F:65-71)
@@ -307,9 +371,10 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
 
     // pair-private hulls (every hull used by ~one pair): the GJK kernels compute the envelope spheres
     // themselves from the vertices they stage anyway; shared stores get one K0 pass per batch
-    const bool fuse = n_hulls >= n_pairs;
+    const gjk::Sphere *ext = ctx->ext_sphere;          // spheres of this store are already on the device
+    const bool fuse = !ext && n_hulls >= n_pairs;
     int rc = GJKEPA_OK;
-    if (!fuse) { rc = ensure(ctx, ctx->d_sphere, ctx->cap_sphere, n_hulls); if (rc) return rc; }
+    if (!fuse && !ext) { rc = ensure(ctx, ctx->d_sphere, ctx->cap_sphere, n_hulls); if (rc) return rc; }
     const bool want_list = (mode >= GJKEPA_MODE_EPA) || n_contacts || contact_index;
     if (want_list) {
         if (n_pairs > ctx->cap_wl) {
@@ -333,7 +398,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = false;
     const bool prof = ctx->profiling;
     // K0 (not needed under shortcut E1, which drops the sphere test)
-    if (!fuse && !(ctx->early_out && use_tile && !ctx->single_kernel)) {
+    if (!fuse && !ext && !(ctx->early_out && use_tile && !ctx->single_kernel)) {
         const int threads = gjk::PREP_WARPS * 32;
         const int64_t blocks = (n_hulls + gjk::PREP_WARPS * 32 - 1) / (gjk::PREP_WARPS * 32);
         if (prof) CU(cudaEventRecord(ctx->ev[0], st));
@@ -343,7 +408,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     }
     // K1
     gjk::BatchArgs a;
-    a.verts = verts; a.hull_off = hull_off; a.sphere = ctx->d_sphere;
+    a.verts = verts; a.hull_off = hull_off; a.sphere = ext ? ext : ctx->d_sphere;
     a.pair_a = pair_a; a.pair_b = pair_b; a.n_pairs = n_pairs; a.n_hulls = n_hulls;
     a.collision = collision; a.status = status;
     a.pair_list = nullptr; a.pair_list_count = nullptr;
@@ -537,201 +602,6 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     return GJKEPA_OK;
 }
 
-int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
-                     int64_t n_hulls, const double *verts, const int64_t *hull_off,
-                     int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
-                     uint8_t *collision, int32_t *colli_type, double *nearest,
-                     double *normal, double *point, double *depth,
-                     uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
-{
-    if (!ctx) return GJKEPA_ERR_ARG;
-    if (n_pairs < 0 || n_hulls < 0) return fail(ctx, GJKEPA_ERR_ARG, "bad sizes");
-    if (n_pairs > 0 && (!verts || !hull_off || !pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    if (n_pairs == 0) { if (n_contacts) *n_contacts = 0; return GJKEPA_OK; }
-
-    const int64_t n_vert = hull_off[n_hulls];
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const bool need_flags = collision || contact_index || n_contacts;
-    {   // Tiny batches (the drop-in single-pair call): every copy or memset is ~10 us of driver time, so inputs travel
-        // as ONE block from a pinned mirror, all outputs come back as ONE block, one memset clears them.
-        constexpr size_t SMALL = 96 * 1024;
-        auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
-        const size_t i_verts = 0, i_off = a16((size_t)n_vert * 24), i_pa = i_off + a16((size_t)(n_hulls + 1) * 8),
-                     i_pb = i_pa + a16((size_t)n_pairs * 4), in_bytes = i_pb + a16((size_t)n_pairs * 4);
-        const size_t q_col = in_bytes, q_type = q_col + a16((size_t)n_pairs), q_near = q_type + a16((size_t)n_pairs * 4),
-                     q_nrm = q_near + a16((size_t)n_pairs * 48), q_pt = q_nrm + a16((size_t)n_pairs * 24),
-                     q_dep = q_pt + a16((size_t)n_pairs * 24), q_st = q_dep + a16((size_t)n_pairs * 8),
-                     all_bytes = q_st + a16((size_t)n_pairs * 4);
-        if (n_pairs <= 256 && all_bytes <= SMALL) {
-            if (!ctx->h_small) {
-                cudaError_t e = cudaHostAlloc((void **)&ctx->h_small, SMALL, cudaHostAllocDefault);
-                if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_small, SMALL);
-                if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "small staging", e);
-            }
-            char *h = ctx->h_small, *d = ctx->d_small;
-            std::memcpy(h + i_verts, verts, (size_t)n_vert * 24);
-            std::memcpy(h + i_off, hull_off, (size_t)(n_hulls + 1) * 8);
-            std::memcpy(h + i_pa, pair_a, (size_t)n_pairs * 4);
-            std::memcpy(h + i_pb, pair_b, (size_t)n_pairs * 4);
-            CU(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
-            CU(cudaMemsetAsync(d + q_col, 0, all_bytes - q_col, st));           // F:65-71 for every output at once
-            int rc = gjkepa_batch_device_f64(ctx, version, tol_ff, n_hulls, (const double *)(d + i_verts), (const int64_t *)(d + i_off),
-                n_pairs, (const int32_t *)(d + i_pa), (const int32_t *)(d + i_pb), mode | GJKEPA_MODE_NO_CLEAR_,
-                (uint8_t *)(d + q_col), colli_type ? (int32_t *)(d + q_type) : nullptr, nearest ? (double *)(d + q_near) : nullptr,
-                normal ? (double *)(d + q_nrm) : nullptr, point ? (double *)(d + q_pt) : nullptr, depth ? (double *)(d + q_dep) : nullptr,
-                status ? (uint32_t *)(d + q_st) : nullptr, nullptr, nullptr);
-            if (rc) return rc;
-            CU(cudaMemcpyAsync(h + q_col, d + q_col, all_bytes - q_col, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            const uint8_t *hf = (const uint8_t *)(h + q_col);
-            if (collision) std::memcpy(collision, hf, (size_t)n_pairs);
-            if (colli_type) std::memcpy(colli_type, h + q_type, (size_t)n_pairs * 4);
-            if (nearest) std::memcpy(nearest, h + q_near, (size_t)n_pairs * 48);
-            if (normal) std::memcpy(normal, h + q_nrm, (size_t)n_pairs * 24);
-            if (point) std::memcpy(point, h + q_pt, (size_t)n_pairs * 24);
-            if (depth) std::memcpy(depth, h + q_dep, (size_t)n_pairs * 8);
-            if (status) std::memcpy(status, h + q_st, (size_t)n_pairs * 4);
-            if (n_contacts || contact_index) {
-                int64_t cnt = 0;
-                for (int64_t i = 0; i < n_pairs; ++i) if (hf[i]) { if (contact_index) contact_index[cnt] = (int32_t)i; ++cnt; }
-                if (n_contacts) *n_contacts = cnt;
-            }
-            return GJKEPA_OK;
-        }
-    }
-    size_t o_verts = 0;
-    size_t o_off   = o_verts + al((size_t)n_vert * 3 * sizeof(double));
-    size_t o_pa    = o_off + al((size_t)(n_hulls + 1) * sizeof(int64_t));
-    size_t o_pb    = o_pa + al((size_t)n_pairs * sizeof(int32_t));
-    size_t o_col   = o_pb + al((size_t)n_pairs * sizeof(int32_t));
-    size_t o_type  = o_col + al(need_flags ? (size_t)n_pairs : 0);
-    size_t o_near  = o_type + al(colli_type ? (size_t)n_pairs * sizeof(int32_t) : 0);
-    size_t o_nrm   = o_near + al(nearest ? (size_t)n_pairs * 6 * sizeof(double) : 0);
-    size_t o_pt    = o_nrm + al(normal ? (size_t)n_pairs * 3 * sizeof(double) : 0);
-    size_t o_dep   = o_pt + al(point ? (size_t)n_pairs * 3 * sizeof(double) : 0);
-    size_t o_st    = o_dep + al(depth ? (size_t)n_pairs * sizeof(double) : 0);
-    size_t total   = o_st + al(status ? (size_t)n_pairs * sizeof(uint32_t) : 0);
-    if (int rcg = grow_bytes(ctx, ctx->d_stage, ctx->cap_stage, total, "cudaMalloc staging")) return rcg;
-    char *base = (char *)ctx->d_stage;
-    CU(cudaMemcpyAsync(base + o_verts, verts, (size_t)n_vert * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_off, hull_off, (size_t)(n_hulls + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_pa, pair_a, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_pb, pair_b, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-
-    int rc = gjkepa_batch_device_f64(ctx, version, tol_ff, n_hulls,
-        (const double *)(base + o_verts), (const int64_t *)(base + o_off), n_pairs,
-        (const int32_t *)(base + o_pa), (const int32_t *)(base + o_pb), mode,
-        need_flags ? (uint8_t *)(base + o_col) : nullptr,
-        colli_type ? (int32_t *)(base + o_type) : nullptr,
-        nearest ? (double *)(base + o_near) : nullptr,
-        normal ? (double *)(base + o_nrm) : nullptr,
-        point ? (double *)(base + o_pt) : nullptr,
-        depth ? (double *)(base + o_dep) : nullptr,
-        status ? (uint32_t *)(base + o_st) : nullptr, nullptr, nullptr);
-    if (rc) return rc;
-
-    std::vector<uint8_t> tmp_flags;
-    uint8_t *h_flags = collision;
-    if (need_flags && !h_flags) { tmp_flags.resize((size_t)n_pairs); h_flags = tmp_flags.data(); }
-    if (need_flags) CU(cudaMemcpyAsync(h_flags, base + o_col, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
-    if (colli_type) CU(cudaMemcpyAsync(colli_type, base + o_type, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (nearest)    CU(cudaMemcpyAsync(nearest, base + o_near, (size_t)n_pairs * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (normal)     CU(cudaMemcpyAsync(normal, base + o_nrm, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (point)      CU(cudaMemcpyAsync(point, base + o_pt, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (depth)      CU(cudaMemcpyAsync(depth, base + o_dep, (size_t)n_pairs * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (status)     CU(cudaMemcpyAsync(status, base + o_st, (size_t)n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-
-    if (n_contacts || contact_index) {
-        int64_t c = 0;
-        for (int64_t i = 0; i < n_pairs; ++i)
-            if (h_flags[i]) { if (contact_index) contact_index[c] = (int32_t)i; ++c; }
-        if (n_contacts) *n_contacts = c;
-    }
-    return GJKEPA_OK;
-}
-
-// ---- binary32 at the boundary: float hull store in, float results out; the device widens and runs the binary64 kernels ----
-int gjkepa_batch_f32(gjkepa_ctx *ctx, int32_t version, float tol_ff,
-                     int64_t n_hulls, const float *verts, const int64_t *hull_off,
-                     int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
-                     uint8_t *collision, int32_t *colli_type, float *nearest,
-                     float *normal, float *point, float *depth,
-                     uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
-{
-    if (!ctx) return GJKEPA_ERR_ARG;
-    if (n_pairs < 0 || n_hulls < 0) return fail(ctx, GJKEPA_ERR_ARG, "bad sizes");
-    if (n_pairs > 0 && (!verts || !hull_off || !pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
-    CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    if (n_pairs == 0) { if (n_contacts) *n_contacts = 0; return GJKEPA_OK; }
-
-    const int64_t n_vert = hull_off[n_hulls];
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const bool need_flags = collision || contact_index || n_contacts;
-    // double results, back to back so ONE narrowing launch covers them: nearest | normal | point | depth
-    const size_t r_near = 0, r_nrm = r_near + (nearest ? (size_t)n_pairs * 6 : 0), r_pt = r_nrm + (normal ? (size_t)n_pairs * 3 : 0),
-                 r_dep = r_pt + (point ? (size_t)n_pairs * 3 : 0), r_all = r_dep + (depth ? (size_t)n_pairs : 0);     // elements
-    size_t o_v32   = 0;
-    size_t o_verts = o_v32 + al((size_t)n_vert * 3 * sizeof(float));
-    size_t o_off   = o_verts + al((size_t)n_vert * 3 * sizeof(double));
-    size_t o_pa    = o_off + al((size_t)(n_hulls + 1) * sizeof(int64_t));
-    size_t o_pb    = o_pa + al((size_t)n_pairs * sizeof(int32_t));
-    size_t o_col   = o_pb + al((size_t)n_pairs * sizeof(int32_t));
-    size_t o_type  = o_col + al(need_flags ? (size_t)n_pairs : 0);
-    size_t o_st    = o_type + al(colli_type ? (size_t)n_pairs * sizeof(int32_t) : 0);
-    size_t o_r64   = o_st + al(status ? (size_t)n_pairs * sizeof(uint32_t) : 0);
-    size_t o_r32   = o_r64 + al(r_all * sizeof(double));
-    size_t total   = o_r32 + al(r_all * sizeof(float));
-    if (int rcg = grow_bytes(ctx, ctx->d_stage, ctx->cap_stage, total, "cudaMalloc staging")) return rcg;
-    char *base = (char *)ctx->d_stage;
-    CU(cudaMemcpyAsync(base + o_v32, verts, (size_t)n_vert * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_off, hull_off, (size_t)(n_hulls + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_pa, pair_a, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_pb, pair_b, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    const int threads = 256;
-    auto grid = [&](int64_t work) { int64_t b = (work + threads - 1) / threads; const int64_t m = (int64_t)ctx->sm_count * 16;
-                                    return (unsigned)(b < 1 ? 1 : (b > m ? m : b)); };
-    f32io::widen_kernel<<<grid(n_vert * 3 / 4 + 1), threads, 0, st>>>((const float *)(base + o_v32), (double *)(base + o_verts), n_vert * 3);
-    ++ctx->launches;
-    CU(cudaGetLastError());
-    double *r64 = (double *)(base + o_r64);
-    int rc = gjkepa_batch_device_f64(ctx, version, (double)tol_ff, n_hulls,
-        (const double *)(base + o_verts), (const int64_t *)(base + o_off), n_pairs,
-        (const int32_t *)(base + o_pa), (const int32_t *)(base + o_pb), mode,
-        need_flags ? (uint8_t *)(base + o_col) : nullptr,
-        colli_type ? (int32_t *)(base + o_type) : nullptr,
-        nearest ? r64 + r_near : nullptr, normal ? r64 + r_nrm : nullptr, point ? r64 + r_pt : nullptr, depth ? r64 + r_dep : nullptr,
-        status ? (uint32_t *)(base + o_st) : nullptr, nullptr, nullptr);
-    if (rc) return rc;
-    float *r32 = (float *)(base + o_r32);
-    if (r_all > 0) {
-        f32io::narrow_kernel<<<grid((int64_t)r_all / 2 + 1), threads, 0, st>>>(r64, r32, (int64_t)r_all);
-        ++ctx->launches;
-        CU(cudaGetLastError());
-    }
-    std::vector<uint8_t> tmp_flags;
-    uint8_t *h_flags = collision;
-    if (need_flags && !h_flags) { tmp_flags.resize((size_t)n_pairs); h_flags = tmp_flags.data(); }
-    if (need_flags) CU(cudaMemcpyAsync(h_flags, base + o_col, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
-    if (colli_type) CU(cudaMemcpyAsync(colli_type, base + o_type, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (nearest)    CU(cudaMemcpyAsync(nearest, r32 + r_near, (size_t)n_pairs * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (normal)     CU(cudaMemcpyAsync(normal, r32 + r_nrm, (size_t)n_pairs * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (point)      CU(cudaMemcpyAsync(point, r32 + r_pt, (size_t)n_pairs * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (depth)      CU(cudaMemcpyAsync(depth, r32 + r_dep, (size_t)n_pairs * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (status)     CU(cudaMemcpyAsync(status, base + o_st, (size_t)n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (n_contacts || contact_index) {
-        int64_t c = 0;
-        for (int64_t i = 0; i < n_pairs; ++i)
-            if (h_flags[i]) { if (contact_index) contact_index[c] = (int32_t)i; ++c; }
-        if (n_contacts) *n_contacts = c;
-    }
-    return GJKEPA_OK;
-}
-
 // Kp: world-space hull store of n_bodies posed shapes (device inputs), left in ctx->d_world; *d_off_out = its offsets
 static int posed_world(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t *d_body_shape, const double *d_pose, int64_t **d_off_out)
 {
@@ -858,13 +728,14 @@ int gjkepa_shapes_upload(gjkepa_ctx *ctx, int64_t n_shapes, const double *shape_
 {
     if (!ctx) return GJKEPA_ERR_ARG;
     if (n_shapes <= 0 || !shape_verts || !shape_off || shape_off[0] != 0) return fail(ctx, GJKEPA_ERR_ARG, "bad shape store");
+    FORWARD_MULTI(gjkepa_shapes_upload(k, n_shapes, shape_verts, shape_off));
     int64_t mx = 0;
     for (int64_t i = 0; i < n_shapes; ++i) {
         const int64_t n = shape_off[i + 1] - shape_off[i];
         if (n <= 0) return fail(ctx, GJKEPA_ERR_ARG, "empty shape");
         if (n > mx) mx = n;
     }
-    CU(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_shape_verts) { cudaFree(ctx->d_shape_verts); ctx->d_shape_verts = nullptr; }
     if (ctx->d_shape_off) { cudaFree(ctx->d_shape_off); ctx->d_shape_off = nullptr; }
@@ -879,6 +750,120 @@ int gjkepa_shapes_upload(gjkepa_ctx *ctx, int64_t n_shapes, const double *shape_
     return GJKEPA_OK;
 }
 
+}  // extern "C"
+
+#include "host_batch.inl"
+
+static const std::vector<gjkepa_ctx *> &multi_kids(const gjkepa_ctx *ctx) { return ctx->multi->kids; }
+static gjkepa_ctx *first_kid(const gjkepa_ctx *ctx) { return ctx->multi->kids[0]; }
+
+extern "C" {
+
+int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                     int64_t n_hulls, const double *verts, const int64_t *hull_off,
+                     int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
+                     uint8_t *collision, int32_t *colli_type, double *nearest,
+                     double *normal, double *point, double *depth,
+                     uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    const bool compact = (mode & GJKEPA_MODE_COMPACT) != 0;
+    mode &= ~GJKEPA_MODE_COMPACT;
+    if (n_pairs < 0 || n_hulls < 0 || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL) return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or mode");
+    if (n_pairs > 0x7fffffffLL || n_hulls > 0x7fffffffLL) return fail(ctx, GJKEPA_ERR_ARG, "more than 2^31-1 pairs or hulls in one call: split the batch");
+    if (n_pairs > 0 && (!verts || !hull_off || !pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
+    if (n_pairs == 0) { if (n_contacts) *n_contacts = 0; return GJKEPA_OK; }
+    if (!ctx->multi && !compact) {
+        ON_DEVICE(ctx);
+        cudaStream_t st = ctx->stream;
+        const int64_t n_vert = hull_off[n_hulls];
+        {   // Tiny batches (the drop-in single-pair call): every copy or memset is ~10 us of driver time, so inputs travel
+            // as ONE block from a pinned mirror, all outputs come back as ONE block, one memset clears them.
+            constexpr size_t SMALL = 96 * 1024;
+            auto a16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+            const size_t i_verts = 0, i_off = a16((size_t)n_vert * 24), i_pa = i_off + a16((size_t)(n_hulls + 1) * 8),
+                         i_pb = i_pa + a16((size_t)n_pairs * 4), in_bytes = i_pb + a16((size_t)n_pairs * 4);
+            const size_t q_col = in_bytes, q_type = q_col + a16((size_t)n_pairs), q_near = q_type + a16((size_t)n_pairs * 4),
+                         q_nrm = q_near + a16((size_t)n_pairs * 48), q_pt = q_nrm + a16((size_t)n_pairs * 24),
+                         q_dep = q_pt + a16((size_t)n_pairs * 24), q_st = q_dep + a16((size_t)n_pairs * 8),
+                         all_bytes = q_st + a16((size_t)n_pairs * 4);
+            if (n_pairs <= 256 && all_bytes <= SMALL) {
+                if (!ctx->h_small) {
+                    cudaError_t e = cudaHostAlloc((void **)&ctx->h_small, SMALL, cudaHostAllocDefault);
+                    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_small, SMALL);
+                    if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "small staging", e);
+                }
+                char *h = ctx->h_small, *d = ctx->d_small;
+                std::memcpy(h + i_verts, verts, (size_t)n_vert * 24);
+                std::memcpy(h + i_off, hull_off, (size_t)(n_hulls + 1) * 8);
+                std::memcpy(h + i_pa, pair_a, (size_t)n_pairs * 4);
+                std::memcpy(h + i_pb, pair_b, (size_t)n_pairs * 4);
+                CU(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
+                CU(cudaMemsetAsync(d + q_col, 0, all_bytes - q_col, st));           // F:65-71 for every output at once
+                int rc = gjkepa_batch_device_f64(ctx, version, tol_ff, n_hulls, (const double *)(d + i_verts), (const int64_t *)(d + i_off),
+                    n_pairs, (const int32_t *)(d + i_pa), (const int32_t *)(d + i_pb), mode | GJKEPA_MODE_NO_CLEAR_,
+                    (uint8_t *)(d + q_col), colli_type ? (int32_t *)(d + q_type) : nullptr, nearest ? (double *)(d + q_near) : nullptr,
+                    normal ? (double *)(d + q_nrm) : nullptr, point ? (double *)(d + q_pt) : nullptr, depth ? (double *)(d + q_dep) : nullptr,
+                    status ? (uint32_t *)(d + q_st) : nullptr, nullptr, nullptr);
+                if (rc) return rc;
+                CU(cudaMemcpyAsync(h + q_col, d + q_col, all_bytes - q_col, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                const uint8_t *hf = (const uint8_t *)(h + q_col);
+                if (collision) std::memcpy(collision, hf, (size_t)n_pairs);
+                if (colli_type) std::memcpy(colli_type, h + q_type, (size_t)n_pairs * 4);
+                if (nearest) std::memcpy(nearest, h + q_near, (size_t)n_pairs * 48);
+                if (normal) std::memcpy(normal, h + q_nrm, (size_t)n_pairs * 24);
+                if (point) std::memcpy(point, h + q_pt, (size_t)n_pairs * 24);
+                if (depth) std::memcpy(depth, h + q_dep, (size_t)n_pairs * 8);
+                if (status) std::memcpy(status, h + q_st, (size_t)n_pairs * 4);
+                if (n_contacts || contact_index) {
+                    int64_t cnt = 0;
+                    for (int64_t i = 0; i < n_pairs; ++i) if (hf[i]) { if (contact_index) contact_index[cnt] = (int32_t)i; ++cnt; }
+                    if (n_contacts) *n_contacts = cnt;
+                }
+                return GJKEPA_OK;
+            }
+        }
+    }
+    Req r;
+    r.version = version; r.tol_ff = tol_ff; r.mode = mode; r.compact = compact; r.src = SRC_HOST;
+    r.n_hulls = n_hulls; r.verts = verts; r.hull_off = hull_off; r.n_pairs = n_pairs; r.pair_a = pair_a; r.pair_b = pair_b;
+    r.collision = collision; r.colli_type = colli_type; r.nearest = nearest; r.normal = normal; r.point = point; r.depth = depth;
+    r.status = status; r.n_contacts = n_contacts; r.contact_index = contact_index;
+    return run_request(ctx, r);
+}
+
+// ---- binary32 at the boundary: float hull store in, float results out; the device widens and runs the binary64 kernels ----
+int gjkepa_batch_f32(gjkepa_ctx *ctx, int32_t version, float tol_ff,
+                     int64_t n_hulls, const float *verts, const int64_t *hull_off,
+                     int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
+                     uint8_t *collision, int32_t *colli_type, float *nearest,
+                     float *normal, float *point, float *depth,
+                     uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (n_pairs < 0 || n_hulls < 0 || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL) return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or mode");
+    if (n_pairs > 0x7fffffffLL || n_hulls > 0x7fffffffLL) return fail(ctx, GJKEPA_ERR_ARG, "more than 2^31-1 pairs or hulls in one call: split the batch");
+    if (n_pairs > 0 && (!verts || !hull_off || !pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
+    Req r;
+    r.version = version; r.tol_ff = (double)tol_ff; r.mode = mode; r.src = SRC_HOST_F32; r.f32 = true;
+    r.n_hulls = n_hulls; r.verts = verts; r.hull_off = hull_off; r.n_pairs = n_pairs; r.pair_a = pair_a; r.pair_b = pair_b;
+    r.collision = collision; r.colli_type = colli_type; r.nearest = nearest; r.normal = normal; r.point = point; r.depth = depth;
+    r.status = status; r.n_contacts = n_contacts; r.contact_index = contact_index;
+    return run_request(ctx, r);
+}
+
+// a body_shape entry outside the shape store would become an empty hull (NaN sphere, poisoned broad-phase bounds): refuse it
+static int check_body_shapes(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t *body_shape)
+{
+    const int64_t ns = ctx->multi ? ctx->multi->kids[0]->n_shapes : ctx->n_shapes;
+    if (ns <= 0) return fail(ctx, GJKEPA_ERR_ARG, "no shapes uploaded (gjkepa_shapes_upload)");
+    int bad = 0;
+    for (int64_t b = 0; b < n_bodies; ++b) bad |= (body_shape[b] < 0) | (body_shape[b] >= ns);
+    if (bad) return fail(ctx, GJKEPA_ERR_ARG, "body_shape names a shape outside the uploaded store");
+    return GJKEPA_OK;
+}
+
 int gjkepa_batch_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                            int64_t n_bodies, const int32_t *body_shape, const double *pose,
                            int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
@@ -887,70 +872,133 @@ int gjkepa_batch_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                            uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
-    if (ctx->n_shapes <= 0) return fail(ctx, GJKEPA_ERR_ARG, "no shapes uploaded (gjkepa_shapes_upload)");
-    if (n_pairs < 0 || n_bodies <= 0 || !body_shape || !pose) return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or null input");
+    const bool compact = (mode & GJKEPA_MODE_COMPACT) != 0;
+    mode &= ~GJKEPA_MODE_COMPACT;
+    if (n_pairs < 0 || n_bodies <= 0 || !body_shape || !pose || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL || n_bodies > 0x7fffffffLL || n_pairs > 0x7fffffffLL)
+        return fail(ctx, GJKEPA_ERR_ARG, "bad sizes, mode or null input");
     if (n_pairs > 0 && (!pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
-    CU(cudaSetDevice(ctx->device));
+    if (int rc = check_body_shapes(ctx, n_bodies, body_shape)) return rc;
+    Req r;
+    r.version = version; r.tol_ff = tol_ff; r.mode = mode; r.compact = compact; r.src = SRC_POSED;
+    r.n_bodies = n_bodies; r.body_shape = body_shape; r.pose = pose; r.n_pairs = n_pairs; r.pair_a = pair_a; r.pair_b = pair_b;
+    r.collision = collision; r.colli_type = colli_type; r.nearest = nearest; r.normal = normal; r.point = point; r.depth = depth;
+    r.status = status; r.n_contacts = n_contacts; r.contact_index = contact_index;
+    return run_request(ctx, r);
+}
+
+// ---- world-space hull store resident on the device(s): pair lists in, results out ----
+static int store_upload_one(gjkepa_ctx *ctx, int64_t n_hulls, const double *verts, const int64_t *hull_off, int max_verts)
+{
+    ON_DEVICE(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_store_verts) { cudaFree(ctx->d_store_verts); ctx->d_store_verts = nullptr; }
+    if (ctx->d_store_off) { cudaFree(ctx->d_store_off); ctx->d_store_off = nullptr; }
+    if (ctx->d_store_sphere) { cudaFree(ctx->d_store_sphere); ctx->d_store_sphere = nullptr; }
+    ctx->n_store_hulls = 0;
+    const int64_t v0 = hull_off[0], nv = hull_off[n_hulls] - v0;
+    cudaError_t e = cudaMalloc((void **)&ctx->d_store_verts, (size_t)nv * 24 + 256);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_store_off, (size_t)(n_hulls + 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_store_sphere, (size_t)n_hulls * sizeof(gjk::Sphere));
+    if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc hull store", e);
     cudaStream_t st = ctx->stream;
-    if (n_pairs == 0) { if (n_contacts) *n_contacts = 0; return GJKEPA_OK; }
-
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const bool need_flags = collision || contact_index || n_contacts;
-    size_t o_shape = 0;
-    size_t o_pose  = o_shape + al((size_t)n_bodies * sizeof(int32_t));
-    size_t o_pa    = o_pose + al((size_t)n_bodies * 12 * sizeof(double));
-    size_t o_pb    = o_pa + al((size_t)n_pairs * sizeof(int32_t));
-    size_t o_col   = o_pb + al((size_t)n_pairs * sizeof(int32_t));
-    size_t o_type  = o_col + al(need_flags ? (size_t)n_pairs : 0);
-    size_t o_near  = o_type + al(colli_type ? (size_t)n_pairs * sizeof(int32_t) : 0);
-    size_t o_nrm   = o_near + al(nearest ? (size_t)n_pairs * 6 * sizeof(double) : 0);
-    size_t o_pt    = o_nrm + al(normal ? (size_t)n_pairs * 3 * sizeof(double) : 0);
-    size_t o_dep   = o_pt + al(point ? (size_t)n_pairs * 3 * sizeof(double) : 0);
-    size_t o_st    = o_dep + al(depth ? (size_t)n_pairs * sizeof(double) : 0);
-    size_t total   = o_st + al(status ? (size_t)n_pairs * sizeof(uint32_t) : 0);
-    if (int rcg = grow_bytes(ctx, ctx->d_stage2, ctx->cap_stage2, total, "cudaMalloc staging")) return rcg;
-    char *base = (char *)ctx->d_stage2;
-    CU(cudaMemcpyAsync(base + o_shape, body_shape, (size_t)n_bodies * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_pose, pose, (size_t)n_bodies * 12 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_pa, pair_a, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(base + o_pb, pair_b, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    int64_t *d_off = nullptr;
-    {
-        int rcw = posed_world(ctx, n_bodies, (const int32_t *)(base + o_shape), (const double *)(base + o_pose), &d_off);
-        if (rcw) return rcw;
+    CU(cudaMemcpyAsync(ctx->d_store_verts, verts + 3 * v0, (size_t)nv * 24, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_store_off, hull_off, (size_t)(n_hulls + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (v0 != 0) {
+        hostb::rebase_kernel<<<(unsigned)((n_hulls + 256) / 256 < 4096 ? (n_hulls + 256) / 256 : 4096), 256, 0, st>>>(nullptr, nullptr, 0, 0, ctx->d_store_off, n_hulls + 1, v0);
+        ++ctx->launches;
     }
-    const int save_hint = ctx->max_hull_hint;
-    ctx->max_hull_hint = (int)ctx->max_shape_verts;      // the shape store bounds the hull sizes (a caller's hint for another store does not apply)
-    int rc = gjkepa_batch_device_f64(ctx, version, tol_ff, n_bodies, ctx->d_world, d_off, n_pairs,
-        (const int32_t *)(base + o_pa), (const int32_t *)(base + o_pb), mode,
-        need_flags ? (uint8_t *)(base + o_col) : nullptr,
-        colli_type ? (int32_t *)(base + o_type) : nullptr,
-        nearest ? (double *)(base + o_near) : nullptr,
-        normal ? (double *)(base + o_nrm) : nullptr,
-        point ? (double *)(base + o_pt) : nullptr,
-        depth ? (double *)(base + o_dep) : nullptr,
-        status ? (uint32_t *)(base + o_st) : nullptr, nullptr, nullptr);
-    ctx->max_hull_hint = save_hint;
-    if (rc) return rc;
-
-    std::vector<uint8_t> tmp_flags;
-    uint8_t *h_flags = collision;
-    if (need_flags && !h_flags) { tmp_flags.resize((size_t)n_pairs); h_flags = tmp_flags.data(); }
-    if (need_flags) CU(cudaMemcpyAsync(h_flags, base + o_col, (size_t)n_pairs, cudaMemcpyDeviceToHost, st));
-    if (colli_type) CU(cudaMemcpyAsync(colli_type, base + o_type, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (nearest)    CU(cudaMemcpyAsync(nearest, base + o_near, (size_t)n_pairs * 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (normal)     CU(cudaMemcpyAsync(normal, base + o_nrm, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (point)      CU(cudaMemcpyAsync(point, base + o_pt, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (depth)      CU(cudaMemcpyAsync(depth, base + o_dep, (size_t)n_pairs * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (status)     CU(cudaMemcpyAsync(status, base + o_st, (size_t)n_pairs * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (int rc = spheres_for(ctx, ctx->d_store_verts, ctx->d_store_off, n_hulls, ctx->d_store_sphere, st)) return rc;
     CU(cudaStreamSynchronize(st));
-    if (n_contacts || contact_index) {
-        int64_t cnt = 0;
-        for (int64_t i = 0; i < n_pairs; ++i)
-            if (h_flags[i]) { if (contact_index) contact_index[cnt] = (int32_t)i; ++cnt; }
-        if (n_contacts) *n_contacts = cnt;
-    }
+    ctx->n_store_hulls = n_hulls; ctx->store_max_verts = max_verts;
     return GJKEPA_OK;
+}
+
+int gjkepa_store_upload(gjkepa_ctx *ctx, int64_t n_hulls, const double *verts, const int64_t *hull_off)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    if (n_hulls <= 0 || n_hulls > 0x7fffffffLL || !verts || !hull_off) return fail(ctx, GJKEPA_ERR_ARG, "bad hull store");
+    int64_t mx = 0;
+    for (int64_t h = 0; h < n_hulls; ++h) {
+        const int64_t n = hull_off[h + 1] - hull_off[h];
+        if (n <= 0) return fail(ctx, GJKEPA_ERR_ARG, "empty hull in the store");
+        mx = n > mx ? n : mx;
+    }
+    if (mx > 0x7fffffff) return fail(ctx, GJKEPA_ERR_ARG, "hull too large");
+    const int mxi = (int)mx;
+    if (ctx->multi)      // replicated: every device copies the store over its own PCIe link, in parallel
+        return ctx->multi->all(ctx, [=](int, gjkepa_ctx *k) { return store_upload_one(k, n_hulls, verts, hull_off, mxi); });
+    return store_upload_one(ctx, n_hulls, verts, hull_off, mxi);
+}
+
+int gjkepa_batch_resident_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                              int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
+                              uint8_t *collision, int32_t *colli_type, double *nearest,
+                              double *normal, double *point, double *depth,
+                              uint32_t *status, int64_t *n_contacts, int32_t *contact_index)
+{
+    if (!ctx) return GJKEPA_ERR_ARG;
+    const bool compact = (mode & GJKEPA_MODE_COMPACT) != 0;
+    mode &= ~GJKEPA_MODE_COMPACT;
+    if (n_pairs < 0 || n_pairs > 0x7fffffffLL || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL) return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or mode");
+    if (n_pairs > 0 && (!pair_a || !pair_b)) return fail(ctx, GJKEPA_ERR_ARG, "null input");
+    const gjkepa_ctx *c0 = ctx->multi ? ctx->multi->kids[0] : ctx;
+    if (c0->n_store_hulls <= 0) return fail(ctx, GJKEPA_ERR_ARG, "no hull store uploaded (gjkepa_store_upload)");
+    Req r;
+    r.version = version; r.tol_ff = tol_ff; r.mode = mode; r.compact = compact; r.src = SRC_RESIDENT;
+    r.n_pairs = n_pairs; r.pair_a = pair_a; r.pair_b = pair_b;
+    r.collision = collision; r.colli_type = colli_type; r.nearest = nearest; r.normal = normal; r.point = point; r.depth = depth;
+    r.status = status; r.n_contacts = n_contacts; r.contact_index = contact_index;
+    return run_request(ctx, r);
+}
+
+// ---- one context over several devices ----
+int gjkepa_create_multi(gjkepa_ctx **out, const int32_t *devices, int32_t n_devices)
+{
+    if (!out) return GJKEPA_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return GJKEPA_ERR_CUDA;
+    if (n_devices < 0 || n_devices > 64) return GJKEPA_ERR_ARG;
+    std::vector<int32_t> devs;
+    if (n_devices == 0 || !devices) { for (int i = 0; i < ndev; ++i) devs.push_back(i); }      // every visible device
+    else devs.assign(devices, devices + n_devices);
+    gjkepa_ctx *ctx = new gjkepa_ctx();
+    ctx->multi = new MultiDev();
+    ctx->device = devs[0];
+    DeviceKeep keep_device_;
+    for (int32_t d : devs) {
+        gjkepa_ctx *k = nullptr;
+        const int rc = gjkepa_create(&k, d);
+        if (rc) { multi_free(ctx); delete ctx; return rc; }
+        ctx->multi->kids.push_back(k);
+    }
+    ctx->sm_count = ctx->multi->kids[0]->sm_count;
+    for (size_t i = 0; i < devs.size(); ++i) {
+        MultiDev::Worker *w = new MultiDev::Worker();
+        ctx->multi->workers.push_back(w);
+        w->th = std::thread(MultiDev::loop, w, (int)devs[i]);
+    }
+    *out = ctx;
+    return GJKEPA_OK;
+}
+
+int32_t gjkepa_device_count(const gjkepa_ctx *ctx)
+{
+    if (!ctx) return 0;
+    return ctx->multi ? (int32_t)ctx->multi->kids.size() : 1;
+}
+
+// pin a caller's array once so that the copies of every later batch run at full PCIe speed and overlap the kernels
+// (arrays a Fortran host ALLOCATEs are pageable: the driver then stages every copy through its own small pinned buffer)
+int gjkepa_host_register(void *p, int64_t bytes)
+{
+    if (!p || bytes <= 0) return GJKEPA_ERR_ARG;
+    return cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable) == cudaSuccess ? GJKEPA_OK : GJKEPA_ERR_CUDA;
+}
+int gjkepa_host_unregister(void *p)
+{
+    if (!p) return GJKEPA_ERR_ARG;
+    return cudaHostUnregister(p) == cudaSuccess ? GJKEPA_OK : GJKEPA_ERR_CUDA;
 }
 
 // ---- candidate pairs on the device ----
@@ -981,9 +1029,14 @@ int gjkepa_broadphase_f64(gjkepa_ctx *ctx, int64_t n_hulls, const double *verts,
                           int64_t cap, int32_t *pair_a, int32_t *pair_b, int64_t *n_pairs)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
+    if (ctx->multi) {               // the broad phase of one scene runs on the context's first device
+        const int rc = gjkepa_broadphase_f64(first_kid(ctx), n_hulls, verts, hull_off, cap, pair_a, pair_b, n_pairs);
+        if (rc) ctx->err = first_kid(ctx)->err;
+        return rc;
+    }
     if (n_hulls <= 0 || !verts || !hull_off || cap < 0 || !n_pairs || (cap > 0 && (!pair_a || !pair_b)) || n_hulls > 0x7fffffff)
         return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or null input");
-    CU(cudaSetDevice(ctx->device));
+    ON_DEVICE(ctx);
     cudaStream_t st = ctx->stream;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const int64_t n_vert = hull_off[n_hulls];
@@ -999,10 +1052,16 @@ int gjkepa_broadphase_posed_f64(gjkepa_ctx *ctx, int64_t n_bodies, const int32_t
                                 int64_t cap, int32_t *pair_a, int32_t *pair_b, int64_t *n_pairs)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
+    if (ctx->multi) {
+        const int rc = gjkepa_broadphase_posed_f64(first_kid(ctx), n_bodies, body_shape, pose, cap, pair_a, pair_b, n_pairs);
+        if (rc) ctx->err = first_kid(ctx)->err;
+        return rc;
+    }
     if (ctx->n_shapes <= 0) return fail(ctx, GJKEPA_ERR_ARG, "no shapes uploaded (gjkepa_shapes_upload)");
     if (n_bodies <= 0 || !body_shape || !pose || cap < 0 || !n_pairs || (cap > 0 && (!pair_a || !pair_b)) || n_bodies > 0x7fffffff)
         return fail(ctx, GJKEPA_ERR_ARG, "bad sizes or null input");
-    CU(cudaSetDevice(ctx->device));
+    if (int rcs = check_body_shapes(ctx, n_bodies, body_shape)) return rcs;
+    ON_DEVICE(ctx);
     cudaStream_t st = ctx->stream;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t o_pose = al((size_t)n_bodies * sizeof(int32_t)), total = o_pose + al((size_t)n_bodies * 12 * sizeof(double));
@@ -1024,11 +1083,18 @@ int gjkepa_scene_posed_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                            int64_t *n_candidates, int64_t *n_contacts)
 {
     if (!ctx) return GJKEPA_ERR_ARG;
+    if (ctx->multi) {               // one scene, one device: the step is a chain of dependent passes over all bodies
+        const int rc = gjkepa_scene_posed_f64(first_kid(ctx), version, tol_ff, n_bodies, body_shape, pose, mode, cap, body_a, body_b, depth, normal,
+                                              point, nearest, colli_type, n_candidates, n_contacts);
+        if (rc) ctx->err = first_kid(ctx)->err;
+        return rc;
+    }
     if (ctx->n_shapes <= 0) return fail(ctx, GJKEPA_ERR_ARG, "no shapes uploaded (gjkepa_shapes_upload)");
     if (n_bodies <= 0 || !body_shape || !pose || cap < 0 || !n_contacts || (cap > 0 && (!body_a || !body_b)) || n_bodies > 0x7fffffff
         || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL)
         return fail(ctx, GJKEPA_ERR_ARG, "bad sizes, mode or null input");
-    CU(cudaSetDevice(ctx->device));
+    if (int rcs = check_body_shapes(ctx, n_bodies, body_shape)) return rcs;
+    ON_DEVICE(ctx);
     cudaStream_t st = ctx->stream;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     // 1. poses to the device, world-space hull store (Kp)
@@ -1154,7 +1220,8 @@ int gjkepa_debug_fp64(gjkepa_ctx *ctx, int64_t n, const double *a, const double 
                       double *q_ref, double *s_fast, double *s_ref, uint8_t *in_range)
 {
     if (!ctx || n <= 0) return GJKEPA_ERR_ARG;
-    CU(cudaSetDevice(ctx->device));
+    if (ctx->multi) return gjkepa_debug_fp64(first_kid(ctx), n, a, b, q_fast, q_ref, s_fast, s_ref, in_range);
+    ON_DEVICE(ctx);
     double *d = nullptr; uint8_t *f = nullptr;
     CU(cudaMalloc((void **)&d, (size_t)n * 6 * sizeof(double)));
     CU(cudaMalloc((void **)&f, (size_t)n));

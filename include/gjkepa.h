@@ -36,6 +36,12 @@ typedef struct gjkepa_ctx gjkepa_ctx;
 #define GJKEPA_MODE_GJK      0   /* collision_ only                       (F:76-236)            */
 #define GJKEPA_MODE_EPA      1   /* + penetration_depth_, collision_normal_ (F:263-323, 863-1022) */
 #define GJKEPA_MODE_FULL     2   /* + nearest_points_, collision_point_, colliType_ (F:326-343)  */
+/* OR-ed into the mode of a HOST-buffer batch call: the real-valued results, colli_type and status come back as one row
+ * per CONTACT instead of one per pair -- row k belongs to pair contact_index[k] (ascending), *n_contacts rows in all
+ * (both arguments are then required; every array needs room for n_pairs rows at worst).  collision stays one byte per
+ * pair.  The rows are compacted on the device, so only contacts cross PCIe (45-75 % of the pairs of a broad-phase
+ * batch are misses whose rows would be the zeros of F:65-71). */
+#define GJKEPA_MODE_COMPACT  16
 
 /* per-pair status word: bits 0-7 GJK exit path, 8-15 GJK walk iterations (F:182-236),
  * 16-23 EPA iterations (F:296-323), 24-31 flags */
@@ -63,13 +69,30 @@ typedef struct gjkepa_ctx gjkepa_ctx;
 #define GJKEPA_ST_BAD_HINT     (1u << 31)  /* the pair has a hull larger than the bound given to gjkepa_set_max_hull_vertices:
                                               NOT processed (flag 0, outputs zero); fix the bound or set it to 0 */
 
-/* ---- context: one per GPU (one process per GPU; pairs shard by index across contexts) ----
- * Threading: a context owns its stream and its workspace and is used by ONE host thread at a time (several contexts on
+/* ---- context: one GPU (gjkepa_create) or several GPUs of one box (gjkepa_create_multi) ----
+ * Threading: a context owns its streams and its workspace and is used by ONE host thread at a time (several contexts on
  * one device may run from several threads).  gjkepa_pair_f64 is safe to call from any number of threads, OpenMP
- * threads included -- the reference is callable from an !$OMP PARALLEL DO (THREADPRIVATE scratch, F:55-60) -- but its
- * callers take turns on one process-wide context: a host loop over pairs belongs in gjkepa_batch_f64. */
+ * threads included -- the reference is callable from an !$OMP PARALLEL DO (THREADPRIVATE scratch, F:55-60): concurrent
+ * callers are coalesced into one small batch per round trip (see below).
+ * Every entry point leaves the calling thread's current CUDA device as it found it. */
 int  gjkepa_create(gjkepa_ctx **ctx, int32_t device);
+/* One context over n_devices GPUs (devices == NULL or n_devices == 0: every visible GPU).  The reference's model is
+ * "the caller runs the loop over pairs on all its cores" (F:55-60); here the HOST-buffer batch calls (gjkepa_batch_f64,
+ * _f32, _posed_f64, _resident_f64) split the pair list into one contiguous range per device, one host thread and one
+ * set of streams per device, and EVERY device copies its results straight into the caller's arrays at the pair's global
+ * index (compact rows: at the row offset the earlier ranges determine) -- N PCIe links in parallel, no collective, no
+ * gather through one GPU.  Results are bit-identical to a single-device context.  gjkepa_shapes_upload and
+ * gjkepa_store_upload replicate to every device.  Calls that are one chain of passes over a whole scene
+ * (gjkepa_broadphase_*, gjkepa_scene_posed_f64) run on the first device; gjkepa_batch_device_f64 and gjkepa_set_stream
+ * need a single-device context (GJKEPA_ERR_ARG). */
+int  gjkepa_create_multi(gjkepa_ctx **ctx, const int32_t *devices, int32_t n_devices);
+int32_t gjkepa_device_count(const gjkepa_ctx *ctx);
 int  gjkepa_destroy(gjkepa_ctx *ctx);
+/* Optional: page-lock an array the caller passes to the batch calls again and again (cudaHostRegister, portable).  The
+ * arrays a Fortran host ALLOCATEs are pageable; copies from pageable memory go through the driver's staging buffer at a
+ * fraction of PCIe speed and cannot overlap the kernels. */
+int  gjkepa_host_register(void *p, int64_t bytes);
+int  gjkepa_host_unregister(void *p);
 /* A new context launches on its own non-blocking stream.  gjkepa_set_stream switches to the
  * caller's stream (cudaStream_t cast to void*, taken literally: NULL is CUDA's legacy default
  * stream); gjkepa_use_own_stream switches back. */
@@ -106,6 +129,9 @@ int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
  * sphere test (F:76-77) is dropped as well under this knob -- a sphere miss implies separation, which the walk detects --
  * so GJKEPA_EXIT_SPHERE is not reported either. */
 #define GJKEPA_TUNE_EARLY_OUT      5
+/* HOST_CHUNKS: a host-buffer batch runs as this many chunks per device through a copy-in / compute / copy-out pipeline
+ * (0 = automatic: up to 8 chunks of at least 64k pairs; 1 = copy everything, compute, copy everything back). */
+#define GJKEPA_TUNE_HOST_CHUNKS    6
 #define GJKEPA_EXIT_EARLY_OUT      13
 int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);
 
@@ -121,13 +147,29 @@ int gjkepa_pair_f64(const int32_t *version, const double *tol_ff,
  * HOST buffers; H2D / D2H copies are part of the call.  Output pointers may be NULL (not wanted).
  * Outputs are written at the pair's index and are zero for non-colliding pairs, as F:65-71.
  * contact_index (optional, n_pairs entries) receives the indices of colliding pairs in ascending
- * order, *n_contacts their count. */
+ * order, *n_contacts their count (both built on the device from the flags).  Large batches run in chunks: the copy-in
+ * of a chunk overlaps the kernels of the one before and the copy-out of the one before that; when the pairs name
+ * hulls in roughly ascending order (pair-private stores) a chunk brings along only the hull range it needs. */
 int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                      int64_t n_hulls, const double *verts, const int64_t *hull_off,
                      int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
                      uint8_t *collision, int32_t *colli_type, double *nearest /*6*np*/,
                      double *normal /*3*np*/, double *point /*3*np*/, double *depth,
                      uint32_t *status, int64_t *n_contacts, int32_t *contact_index);
+
+/* ---- hull store resident on the device(s): only pair lists go in, only results come out ----
+ * A Fortran host cannot hold device pointers, so the store is named by the context.  gjkepa_store_upload copies a
+ * world-space hull store (layout as above, HOST buffers) to every device of the context -- for a multi-device context in
+ * parallel over their PCIe links -- and computes the envelope spheres of F:1175-1182 once; it replaces any earlier store.
+ * gjkepa_batch_resident_f64 is gjkepa_batch_f64 against that store: per pair 8 B go in and 1 B (flags), 33 B
+ * (+depth, normal) or 109 B (everything) come out, or only the contacts' rows with GJKEPA_MODE_COMPACT.  Results are
+ * bit-identical to gjkepa_batch_f64 on the same store. */
+int gjkepa_store_upload(gjkepa_ctx *ctx, int64_t n_hulls, const double *verts, const int64_t *hull_off);
+int gjkepa_batch_resident_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
+                              int64_t n_pairs, const int32_t *pair_a, const int32_t *pair_b, int32_t mode,
+                              uint8_t *collision, int32_t *colli_type, double *nearest /*6*np*/,
+                              double *normal /*3*np*/, double *point /*3*np*/, double *depth,
+                              uint32_t *status, int64_t *n_contacts, int32_t *contact_index);
 
 /* ---- fp32 mode: binary32 at the boundary (north_star: "1e-5 if an fp32 mode is offered") ----
  * Same call with the hull store, the tolerance and the real-valued results as float: half the bytes over PCIe, which

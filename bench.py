@@ -139,33 +139,129 @@ def cpu_rate(batch, mode, sample_pairs, threads=0, repeats=1):
     return n / best, used, n, hits, best
 
 
-def run_reference(args, rank):
+def static_config(desc, n, mode, world, bytes_per_pair, store_mb):
+    """The part of `config` both arms share (the reference arm runs the same pairs on the host cores)."""
+    return {"workload": desc, "pairs_per_gpu_per_step": n, "mode": mode, "sharding": f"pairs by index x{world}",
+            "l2": "inputs larger than L2 (hull store %.0f MB per GPU)" % store_mb,
+            "algorithmic_bytes_per_pair": bytes_per_pair}
+
+
+def run_reference(args, rank, world):
+    """The CPU path on the box's host cores: the C restatement of GCLIB_GJKEPA.f90 (oracle/), OpenMP over pairs, every
+    core, the SAME batch as the GPU arm's rank 0 (same seed, same number of pairs per step)."""
     if rank != 0:
         return
     batch, mode, desc = make_workload(args.workload, args.pairs, seed=12345)
-    sample = min(batch.n_pairs, 250_000)
+    out_bytes = {"gjk": 1, "epa": 33, "full": 109}[mode]
+    n = batch.n_pairs
     for _ in range(args.warmup):
-        cpu_rate(batch, mode, min(sample, 20_000))
+        cpu_rate(batch, mode, min(n, 50_000))
     t0 = time.perf_counter()
     n_done = 0
     for _ in range(args.steps):
-        rate, used, n, hits, dt = cpu_rate(batch, mode, sample)
-        n_done += n
+        rate, used, ns, hits, dt = cpu_rate(batch, mode, n)
+        n_done += ns
     total = time.perf_counter() - t0
     value = n_done / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "pairs_per_step": sample, "mode": mode},
+        "config": static_config(desc, n, mode, world, batch.algorithmic_bytes_per_pair(out_bytes), batch.verts.nbytes / 1e6),
+        "colliding_fraction": hits / n,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
-                         "sample": f"first {sample} pairs of the workload per step; C restatement of "
+                         "sample": f"all {n} pairs of rank 0's batch per step; C restatement of "
                                    "GCLIB_GJKEPA.f90 (not gfortran: no Fortran compiler in the image), "
                                    "OpenMP parallel-for over pairs"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def run_one_process(args, world, batch, h_in, mode, pinned_empty, W, dev):
+    """Rank 0 alone drives all N GPUs of the box through ONE multi-device context (gjkepa_create_multi), the other ranks
+    idle: the call a single Fortran host process makes.  Pairs shard by contiguous index range inside the library, every
+    GPU copies its own results into the caller's arrays, no collective.  Two workloads: the cfg2 step with everything
+    crossing PCIe (N x the per-GPU batch, so the per-GPU work is the same as in the one-rank-per-GPU run above), and
+    BASELINE configs[4] scaled to N GPUs: 12.5M pairs per GPU over a shared store of 16-vertex hulls resident on every
+    GPU (N = 8: 100M pairs over 10M bodies), GJK + EPA, the contact list (pair index, depth, normal) gathered to the host."""
+    import ctypes as C
+    import torch
+    from collision_detect_gjk_epa_b200 import Engine
+    ndev = min(world, torch.cuda.device_count())
+    eng = Engine(devices=list(range(ndev)))
+    res = {"devices": ndev, "api": "gjkepa_create_multi + host-buffer batch calls (C ABI), one host process"}
+
+    def timed(fn, steps):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        return (time.perf_counter() - t0) / steps
+
+    def phases():
+        ms = (C.c_double * 2)()
+        eng._L.gjkepa_host_phase_ms(eng._h, ms)
+        return {"shards_ms": ms[0], "contact_rows_to_host_ms": ms[1]}
+
+    # (a) cfg2, copy everything: the per-GPU batch tiled N times
+    n1 = batch.n_pairs
+    nh1 = int(batch.hull_off.shape[0] - 1)
+    nv1 = int(batch.hull_off[-1])
+    verts = pinned_empty((ndev * batch.verts.shape[0],), torch.float64)
+    off = pinned_empty((ndev * nh1 + 1,), torch.int64)
+    pa = pinned_empty((ndev * n1,), torch.int32)
+    pb = pinned_empty((ndev * n1,), torch.int32)
+    for r in range(ndev):
+        verts[r * batch.verts.shape[0]:(r + 1) * batch.verts.shape[0]] = batch.verts
+        off[r * nh1:(r + 1) * nh1 + 1] = batch.hull_off + r * nv1
+        pa[r * n1:(r + 1) * n1] = batch.pair_a + r * nh1
+        pb[r * n1:(r + 1) * n1] = batch.pair_b + r * nh1
+    flags = pinned_empty((ndev * n1,), torch.uint8)
+    eng.set_max_hull_vertices(int(np.diff(batch.hull_off).max()))
+    steps = max(3, min(args.steps, 10))
+    dt = timed(lambda: eng.batch_host(verts, off, pa, pb, mode=mode, out={"collision": flags}), steps)
+    assert np.array_equal(flags[:n1], flags[(ndev - 1) * n1:]), "shards of a tiled batch must agree"
+    res["cfg2_copy_all"] = {"pairs_per_step": ndev * n1, "ms_per_step": dt * 1e3, "value": ndev * n1 / dt, "unit": UNIT,
+                            "h2d_bytes_per_step": int(verts.nbytes + off.nbytes + pa.nbytes + pb.nbytes), "d2h_bytes_per_step": int(flags.nbytes),
+                            "h2d_gbs_total": (verts.nbytes + off.nbytes + pa.nbytes + pb.nbytes) / dt / 1e9}
+    eng.upload_store(verts, off)
+    dt = timed(lambda: eng.batch_resident(pa, pb, mode=mode, out={"collision": flags}), steps)
+    res["cfg2_resident_store"] = {"pairs_per_step": ndev * n1, "ms_per_step": dt * 1e3, "value": ndev * n1 / dt, "unit": UNIT,
+                                  "h2d_bytes_per_step": int(pa.nbytes + pb.nbytes), "d2h_bytes_per_step": int(flags.nbytes)}
+    del verts, off, pa, pb, flags
+
+    # (b) BASELINE configs[4]: shared store of 16-vertex hulls, 10 pairs per body, contact list to the host
+    per_gpu = int(os.environ.get("GJKEPA_BENCH_CFG5_PAIRS_PER_GPU", 12_500_000))
+    n5, nb5 = per_gpu * ndev, max(1000, per_gpu * ndev // 10)
+    t0 = time.perf_counter()
+    v5, o5, a5, b5 = W.make_shared_store_gpu(dev, nb5, n5, n_vert=16, seed=4242)
+    v5, o5, a5, b5 = v5.numpy(), o5.numpy(), a5.numpy(), b5.numpy()
+    gen_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng.upload_store(v5, o5)
+    up_s = time.perf_counter() - t0
+    out5 = {"collision": pinned_empty((n5,), torch.uint8), "contact_index": pinned_empty((n5,), torch.int32),
+            "depth": pinned_empty((n5,), torch.float64), "normal": pinned_empty((n5, 3), torch.float64)}
+    dt = timed(lambda: eng.batch_resident(a5, b5, mode="epa", out=out5, compact=True), 3)
+    nc = int(out5["n_contacts"])
+    ph = phases()
+    idx = out5["contact_index"][:nc]
+    ok = bool(nc > 0 and np.all(np.diff(idx.astype(np.int64)) > 0) and np.all(out5["collision"][idx] == 1)
+              and int(out5["collision"].sum(dtype=np.int64)) == nc and np.all(out5["depth"][:nc] >= 0.0)
+              and np.allclose(np.linalg.norm(out5["normal"][:min(nc, 1_000_000)], axis=1), 1.0, atol=1e-9))
+    res["cfg5"] = {"workload": f"BASELINE configs[4] at {ndev} GPU(s): {n5} pairs over a shared store of {nb5} 16-vertex hulls "
+                               f"({v5.nbytes / 1e9:.2f} GB, resident on every GPU), GJK+EPA, contact list (pair index, depth, normal) to the host",
+                   "pairs_per_step": n5, "contacts": nc, "ms_per_step": dt * 1e3, "pairs_per_s": n5 / dt, "contacts_per_s": nc / dt,
+                   "h2d_bytes_per_step": int(8 * n5), "d2h_bytes_per_step": int(n5 + 36 * nc), "phases": ph,
+                   "store_upload_s": up_s, "workload_generation_s": gen_s,
+                   "contact_list_checks_ok": ok,
+                   "algorithmic_gbs": (24 * 32 + 8 + 33) * n5 / dt / 1e9}
+    dtf = timed(lambda: eng.batch_resident(a5, b5, mode="gjk", out={"collision": out5["collision"]}), 3)
+    res["cfg5"]["gjk_only"] = {"ms_per_step": dtf * 1e3, "pairs_per_s": n5 / dtf}
+    eng.close()
+    return res
 
 
 def emit(line: dict):
@@ -187,12 +283,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
 
     import torch
     import torch.distributed as dist
     from collision_detect_gjk_epa_b200 import Engine
+    from collision_detect_gjk_epa_b200 import workloads as W
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the GJK/EPA path has no CPU fallback")
@@ -200,23 +297,55 @@ def main():
     dev = torch.device("cuda", local_rank)
     from collision_detect_gjk_epa_b200 import shard as _shard
     numa = _shard.bind_to_gpu_numa(local_rank)       # pinned buffers on the GPU's own NUMA node (undone before the CPU baseline)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")      # ranks that sit out a leg wait on the CPU, not in an NCCL kernel
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(xs):
+        t = torch.tensor(list(xs), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    keep = []
+
+    def pin(a):
+        tt = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        keep.append(tt)
+        return tt.numpy()
+
+    def pinned_empty(shape, dtype):
+        tt = torch.empty(shape, dtype=dtype, pin_memory=True)
+        keep.append(tt)
+        return tt.numpy()
+
     batch, mode, desc = make_workload(args.workload, args.pairs, seed=12345 + rank)
     eng = Engine(local_rank, lanes=args.lanes)
-    eng.set_max_hull_vertices(int(np.diff(batch.hull_off).max()))      # the caller knows its hull sizes
+    max_verts = int(np.diff(batch.hull_off).max())
+    eng.set_max_hull_vertices(max_verts)      # the caller knows its hull sizes
     n = batch.n_pairs
     out_bytes = {"gjk": 1, "epa": 33, "full": 109}[mode]
     bytes_per_pair = batch.algorithmic_bytes_per_pair(out_bytes)
 
-    # ---- device-resident inputs ----
+    # ---- device-resident inputs: `value` ----
     d_in = [torch.from_numpy(x).to(dev) for x in (batch.verts, batch.hull_off, batch.pair_a, batch.pair_b)]
     out = None
 
@@ -224,7 +353,8 @@ def main():
         nonlocal out
         out = eng.batch_device(*d_in, mode=mode, out=out, want_status=False)
 
-    for _ in range(max(3, args.warmup)):
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         step_device()
     barrier()
     eng.launch_count(reset=True)
@@ -239,107 +369,209 @@ def main():
     e1.record()
     barrier()
     sampler.live.clear()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = reduce_max(e0.elapsed_time(e1))
     launches = eng.launch_count()
-    # per-kernel durations: one more (untimed) profiled step gives a per-launch sample of each kernel
+    # per-kernel durations: a few more (untimed) profiled steps give a per-launch sample of each kernel
     ksamples = []
     eng.set_profiling(True)
     for _ in range(5):
         step_device()
         ksamples.append(eng.kernel_ms())
     for k in kern:
-        kern[k] = float(np.median([s[k] for s in ksamples]))
+        kern[k] = float(np.median([s_[k] for s_ in ksamples]))
     eng.set_profiling(False)
     hits = int(out["collision"].sum().item())
-
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(n), float(hits)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_total = float(t.item())
-    pairs_all, hits_all = float(tot[0].item()), float(tot[1].item())
+    pairs_all, hits_all = reduce_sum([float(n), float(hits)])
     value = pairs_all * args.steps / (ms_total * 1e-3)
 
-    # ---- end to end through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region) ----
-    def pin(a):
-        tt = torch.from_numpy(a).pin_memory()
-        return tt, tt.numpy()
-    keep = []
-    h_in = []
-    for x in (batch.verts, batch.hull_off, batch.pair_a, batch.pair_b):
-        tt, npv = pin(x)
-        keep.append(tt); h_in.append(npv)
-    h_out = {}
+    # ---- end to end through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region): `e2e` ----
+    h_in = [pin(x) for x in (batch.verts, batch.hull_off, batch.pair_a, batch.pair_b)]
     okeys = {"gjk": ["collision"], "epa": ["collision", "depth", "normal"],
              "full": ["collision", "depth", "normal", "colli_type", "nearest", "point"]}[mode]
-    shapes = {"collision": ((n,), np.uint8), "depth": ((n,), np.float64), "normal": ((n, 3), np.float64),
-              "colli_type": ((n,), np.int32), "nearest": ((n, 6), np.float64), "point": ((n, 3), np.float64)}
-    for k in okeys:
-        tt = torch.empty(shapes[k][0], dtype=getattr(torch, np.dtype(shapes[k][1]).name), pin_memory=True)
-        keep.append(tt); h_out[k] = tt.numpy()
+    shapes = {"collision": ((n,), torch.uint8), "depth": ((n,), torch.float64), "normal": ((n, 3), torch.float64),
+              "colli_type": ((n,), torch.int32), "nearest": ((n, 6), torch.float64), "point": ((n, 3), torch.float64)}
+    h_out = {k: pinned_empty(*shapes[k]) for k in okeys}
     h2d = int(sum(x.nbytes for x in h_in))
     d2h = int(sum(v.nbytes for v in h_out.values()))
     eng._L.gjkepa_use_own_stream(eng._h)
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
-        eng.batch_host(*h_in, mode=mode, out=h_out)
-    barrier()
+
+    def timed_host(fn, steps, everyone=True):
+        """steps calls of fn between two barriers; wall clock, max over the ranks taking part"""
+        for _ in range(2):
+            fn()
+        if everyone:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return reduce_max(dt) if everyone else dt
+
     sampler.live.set()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.batch_host(*h_in, mode=mode, out=h_out)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()      # sampled through both timed regions (device-resident steps, then end-to-end steps)
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    dt_copy = timed_host(lambda: eng.batch_host(*h_in, mode=mode, out=h_out), e2e_steps)
+    e2e_value = pairs_all * e2e_steps / dt_copy
+    # the same call with the hull store resident on the device (gjkepa_store_upload once, as a simulation uploads its
+    # geometry; per step only the pair list goes in and the results come out)
+    eng.upload_store(h_in[0], h_in[1])
+    dt_res = timed_host(lambda: eng.batch_resident(h_in[2], h_in[3], mode=mode, out=h_out), e2e_steps)
+    clocks = sampler.stop()      # sampled through the timed regions above (device-resident steps, then end-to-end steps)
+    e2e_res = {"value": pairs_all * e2e_steps / dt_res, "unit": UNIT, "ms_per_step": dt_res / e2e_steps * 1e3,
+               "h2d_bytes_per_step": int(h_in[2].nbytes + h_in[3].nbytes), "d2h_bytes_per_step": d2h,
+               "api": "gjkepa_store_upload once + gjkepa_batch_resident_f64 per step (C ABI, pinned host buffers)"}
+    e2e_solo = None
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = pairs_all * e2e_steps / float(te.item())
+        # the same copy-everything step with rank 0 alone on the box: what one GPU reaches when the other N-1 do not
+        # share the host's memory system with it (the per-GPU rate of the concurrent run, over this, is the e2e efficiency)
+        if rank == 0:
+            dts = timed_host(lambda: eng.batch_host(*h_in, mode=mode, out=h_out), e2e_steps, everyone=False)
+            e2e_solo = n * e2e_steps / dts
+        host_barrier()
+
+    # ---- plain pinned copies, all ranks at once: attributes the end-to-end number to the host/PCIe side ----
+    def copy_rate(h2d_dir: bool):
+        nb = 256 << 20
+        hb = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        db = torch.empty(nb, dtype=torch.uint8, device=dev)
+        src, dst = (hb, db) if h2d_dir else (db, hb)
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(8):
+            dst.copy_(src, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        gbs = 8 * nb / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = gbs
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [round(float(v), 2) for v in t.tolist()]
+    pcie = {"h2d_gbs_per_gpu_all_ranks_at_once": copy_rate(True), "d2h_gbs_per_gpu_all_ranks_at_once": copy_rate(False),
+            "what": "8 x 256 MiB cudaMemcpyAsync from/to pinned host memory per rank, all ranks started together (CUDA events)"}
+
+    # ---- GJK + EPA: contacts/s on cfg3 (1M pairs of 32-vertex hulls per GPU), device-resident and end to end ----
+    gjk_epa = None
+    if not args.no_extra and args.workload == "cfg2":
+        b3, m3, d3 = make_workload("cfg3", args.pairs, seed=777 + rank)
+        t3 = [torch.from_numpy(x).to(dev) for x in (b3.verts, b3.hull_off, b3.pair_a, b3.pair_b)]
+        o3 = None
+        eng.set_max_hull_vertices(32)
+        for _ in range(3):
+            o3 = eng.batch_device(*t3, mode=m3, out=o3, want_status=False)
+        barrier()
+        k3 = max(3, min(args.steps, 20))
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(k3):
+            o3 = eng.batch_device(*t3, mode=m3, out=o3, want_status=False)
+        f1.record()
+        barrier()
+        ms3 = reduce_max(f0.elapsed_time(f1)) / k3
+        eng.set_profiling(True)
+        ks3 = []
+        for _ in range(3):
+            o3 = eng.batch_device(*t3, mode=m3, out=o3, want_status=False)
+            ks3.append(eng.kernel_ms())
+        eng.set_profiling(False)
+        h3 = int(o3["collision"].sum().item())
+        p3_all, h3_all = reduce_sum([float(b3.n_pairs), float(h3)])
+        # end to end: store resident, pair list in, compact contact rows (index, depth, normal) out
+        eng._L.gjkepa_use_own_stream(eng._h)
+        eng.upload_store(b3.verts, b3.hull_off)
+        pa3, pb3 = pin(b3.pair_a), pin(b3.pair_b)
+        n3 = b3.n_pairs
+        c_out = {"collision": pinned_empty((n3,), torch.uint8), "contact_index": pinned_empty((n3,), torch.int32),
+                 "depth": pinned_empty((n3,), torch.float64), "normal": pinned_empty((n3, 3), torch.float64)}
+        dt3 = timed_host(lambda: eng.batch_resident(pa3, pb3, mode="epa", out=c_out, compact=True), k3)
+        assert c_out["n_contacts"] == h3, (c_out["n_contacts"], h3)
+        gjk_epa = {"workload": d3, "pairs_per_gpu_per_step": n3, "ms_per_step": ms3,
+                   "pairs_per_s": p3_all / ms3 * 1e3, "contacts_per_s": h3_all / ms3 * 1e3, "contacts_per_step_all_gpus": h3_all,
+                   "kernel_ms": {k: float(np.median([q[k] for q in ks3])) for k in ("hull_prep", "gjk", "epa")},
+                   "algorithmic_gbs": b3.algorithmic_bytes_per_pair(33) * p3_all / (ms3 * 1e-3) / 1e9,
+                   "timing": "device-resident inputs, CUDA events, max over ranks",
+                   "e2e": {"contacts_per_s": h3_all * k3 / dt3, "pairs_per_s": p3_all * k3 / dt3, "ms_per_step": dt3 / k3 * 1e3,
+                           "h2d_bytes_per_step": int(8 * n3), "d2h_bytes_per_step": int(n3 + 36 * h3),
+                           "api": "gjkepa_batch_resident_f64 | GJKEPA_MODE_COMPACT (C ABI, pinned host buffers): pair list in, "
+                                  "flags + one row (pair index, depth, normal) per contact out"}}
+        del t3, o3
+        eng.set_max_hull_vertices(max_verts)
+
+    # ---- one HOST process over all N GPUs (gjkepa_create_multi): what a Fortran host calling the C ABI gets ----
+    one_process = None
+    if not args.no_extra and args.workload == "cfg2":
+        host_barrier()
+        if rank == 0:
+            one_process = run_one_process(args, world, batch, h_in, mode, pinned_empty, W, dev)
+        host_barrier()
 
     if rank != 0:
+        eng.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
-    traffic = None
+    traffic, traffic_src = None, None
     tfile = ROOT / "profiles" / "ncu_traffic.json"          # dram bytes per launch from the committed ncu --set full captures
-    if tfile.exists():
-        try:
-            traffic = json.loads(tfile.read_text()).get(args.workload, {})
-        except Exception:
-            traffic = None
     peaks, peak_src = None, "fallback"
     pk = ROOT / "MEASURED_PEAKS.json"
     if pk.exists():
         peaks = json.loads(pk.read_text()); peak_src = "measured"
     peak_gbs = float(peaks["hbm_gbs"]) if peaks else 6650.0
     dom = "epa" if (mode != "gjk" and kern["epa"] > kern["gjk"]) else "gjk"
+    if tfile.exists():
+        try:
+            ent = json.loads(tfile.read_text()).get(args.workload, {})
+            traffic = ent.get({"gjk": "gjk_kernel", "epa": "epa_kernel"}[dom])
+            traffic_src = {"profile": ent.get("profile"), "commit": ent.get("commit"), "note": ent.get("source")}
+        except Exception:
+            traffic = None
     dom_units = hits if dom == "epa" else n                       # units one launch of that kernel processes (rank 0)
     dom_bytes = bytes_per_pair * dom_units
     achieved = dom_bytes / (kern[dom] * 1e-3) / 1e9 if kern[dom] > 0 else None
     step_ms = ms_total / args.steps
+    cfg = static_config(desc, n, mode, world, bytes_per_pair, batch.verts.nbytes / 1e6)
+    cfg["lanes_per_pair"] = args.lanes or "auto (hulls <= 16 vertices: 1 thread/pair, init kernel + compacting walk kernel; larger: 4 lanes/pair, 8 pairs per warp in lockstep)"
+    cfg["host_numa_node"] = numa[0] if numa else None      # process + pinned buffers bound to the GPU's NUMA node
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "pairs_per_gpu_per_step": n, "mode": mode, "sharding": f"pairs by index x{world}",
-                   "l2": "inputs larger than L2 (hull store %.0f MB per GPU)" % (batch.verts.nbytes / 1e6),
-                   "algorithmic_bytes_per_pair": bytes_per_pair,
-                   "colliding_fraction": hits_all / pairs_all, "lanes_per_pair": args.lanes or "auto (hulls <= 16 vertices: 1 thread/pair, init kernel + compacting walk kernel; larger: 4 lanes/pair, 8 pairs per warp in lockstep)"},
-        "contacts_per_s": hits_all * args.steps / (ms_total * 1e-3),
+        "config": cfg,
+        "colliding_fraction": hits_all / pairs_all,
+        "colliding_flags_per_s": hits_all * args.steps / (ms_total * 1e-3),
         "roofline": {"bound": "hbm", "kernel": {"gjk": "gjk stage (gjk_init_kernel + gjk_walk_kernel)", "epa": "epa stage (epa3_kernel + epa_kernel)"}[dom],
                      "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": (achieved / peak_gbs) if achieved else None, "peak_source": peak_src,
-                     "traffic": (traffic or {}).get({"gjk": "gjk_kernel", "epa": "epa_kernel"}[dom]),
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": dom_bytes,
                      "kernel_ms": kern, "kernel_share_of_step": kern[dom] / step_ms if step_ms else None},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "gjkepa_batch_f64 (C ABI, pinned host buffers)"},
+                "ms_per_step": dt_copy / e2e_steps * 1e3, "steps": e2e_steps,
+                "api": "gjkepa_batch_f64 (C ABI, pinned host buffers; everything the reference call takes crosses PCIe every step, "
+                       "in chunks that overlap the kernels)",
+                "h2d_gbs_per_gpu": h2d / (dt_copy / e2e_steps) / 1e9,
+                "limiter": "PCIe: %.0f MB of world-space vertices per GPU per step; the kernels are %.0f %% of the step" % (
+                    h2d / 1e6, 100.0 * step_ms / (dt_copy / e2e_steps * 1e3)),
+                "resident_store": e2e_res},
+        "pcie": pcie,
         "gpu_launches": launches,
         "clocks": clocks,
     }
-    line["config"]["host_numa_node"] = numa[0] if numa else None      # process + pinned buffers bound to the GPU's NUMA node
+    if e2e_solo:
+        line["e2e"]["rank0_alone_value"] = e2e_solo
+        line["e2e"]["efficiency_vs_rank0_alone"] = (e2e_value / world) / e2e_solo
+        line["e2e"]["efficiency_note"] = ("per-GPU rate with all ranks copying at once over the rate of rank 0 alone on the same box: "
+                                          "what the shared host memory / PCIe root costs (see pcie.*_all_ranks_at_once)")
+    if gjk_epa:
+        line["gjk_epa"] = gjk_epa
+        line["contacts_per_s"] = gjk_epa["contacts_per_s"]      # GJK+EPA contacts (depth and normal produced) per second, all GPUs
+    if one_process:
+        line["one_process"] = one_process
     if not args.no_cpu:
         sample = min(n, 1_000_000)
         if numa:
@@ -351,37 +583,12 @@ def main():
         if numa:
             _shard.bind_to_gpu_numa(local_rank)
     if not args.no_extra and args.workload == "cfg2" and world == 1:
-        # secondary headline: GJK+EPA contacts/s on cfg3 (1M pairs of 32-vertex hulls)
-        b3, m3, d3 = make_workload("cfg3", args.pairs, seed=12345)
-        t3 = [torch.from_numpy(x).to(dev) for x in (b3.verts, b3.hull_off, b3.pair_a, b3.pair_b)]
-        o3 = None
-        eng.set_max_hull_vertices(32)
-        for _ in range(3):
-            o3 = eng.batch_device(*t3, mode=m3, out=o3, want_status=False)
-        torch.cuda.synchronize()
-        k3 = max(3, min(args.steps, 20))
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(k3):
-            o3 = eng.batch_device(*t3, mode=m3, out=o3, want_status=False)
-        f1.record()
-        torch.cuda.synchronize()
-        ms3 = f0.elapsed_time(f1) / k3
-        h3 = int(o3["collision"].sum().item())
-        line["extra"] = {"workload": d3, "ms_per_step": ms3, "pairs_per_s": b3.n_pairs / ms3 * 1e3,
-                         "contacts_per_s": h3 / ms3 * 1e3, "contacts": h3,
-                         "algorithmic_gbs": b3.algorithmic_bytes_per_pair(33) * b3.n_pairs / (ms3 * 1e-3) / 1e9}
-    if not args.no_extra and args.workload == "cfg2" and world == 1:
         # the same kind of step with the shapes resident on the device and only poses crossing PCIe
         # (gjkepa_shapes_upload once, gjkepa_batch_posed_f64 per step): 2 bodies per pair, every body its own box
-        from collision_detect_gjk_epa_b200 import workloads as W
         pb = W.make_posed(n_shapes=2 * args.pairs, n_bodies=2 * args.pairs, n_pairs=args.pairs, sigma=1.0, kind="box", seed=777)
         eng.upload_shapes(pb.shape_verts, pb.shape_off)
-        hp = []
-        for x in (pb.body_shape, pb.pose, pb.pair_a, pb.pair_b):
-            tt, npv = pin(x); keep.append(tt); hp.append(npv)
-        tt = torch.empty((pb.n_pairs,), dtype=torch.uint8, pin_memory=True); keep.append(tt)
-        po = {"collision": tt.numpy()}
+        hp = [pin(x) for x in (pb.body_shape, pb.pose, pb.pair_a, pb.pair_b)]
+        po = {"collision": pinned_empty((pb.n_pairs,), torch.uint8)}
         for _ in range(2):
             eng.batch_posed(*hp, mode="gjk", out=po)
         torch.cuda.synchronize()
@@ -421,10 +628,9 @@ def main():
             "note": "opt-in GJKEPA_TUNE_EARLY_OUT: the walk of a separated pair ends when a support value proves separation"}
     if not args.no_extra and args.workload == "cfg2" and world == 1:
         # fp32 mode: the same cfg2 step through gjkepa_batch_f32 (float hull store over PCIe, binary64 kernels on the device)
-        t32, v32 = pin(batch.verts.astype(np.float32)); keep.append(t32)
+        v32 = pin(batch.verts.astype(np.float32))
         f_in = [v32, h_in[1], h_in[2], h_in[3]]
-        t32o = torch.empty((batch.n_pairs,), dtype=torch.uint8, pin_memory=True); keep.append(t32o)
-        f_out = {"collision": t32o.numpy()}
+        f_out = {"collision": pinned_empty((batch.n_pairs,), torch.uint8)}
         flags64 = h_out["collision"].copy()              # what gjkepa_batch_f64 returned for the same pairs (e2e leg above)
         eng.set_max_hull_vertices(int(np.diff(batch.hull_off).max()))
         for _ in range(2):
@@ -457,9 +663,7 @@ def main():
         t = (site + rng.uniform(-0.3, 0.3, size=(nb, 3))) * 1.6
         pose = np.concatenate([W._quat_rot(rng, nb).reshape(nb, 9), t], axis=1)
         shp = rng.integers(0, 1000, size=nb).astype(np.int32)
-        hb = []
-        for x in (shp, pose):
-            tt, npv = pin(x); keep.append(tt); hb.append(npv)
+        hb = [pin(x) for x in (shp, pose)]
         cap = 24 * nb
         ta = torch.empty((cap,), dtype=torch.int32, pin_memory=True); tb_ = torch.empty((cap,), dtype=torch.int32, pin_memory=True)
         keep += [ta, tb_]

@@ -85,6 +85,9 @@ struct gjkepa_ctx {
     double *d_store_verts = nullptr; int64_t *d_store_off = nullptr; gjk::Sphere *d_store_sphere = nullptr;
     int64_t n_store_hulls = 0; int store_max_verts = 0;
     int host_chunks = 0;           // chunks per host batch (0 = automatic)
+    double phase_ms[2] = {0.0, 0.0};        // wall clock of the last host batch: shards (copies + kernels), contact rows to the host
+    double host_ms[3] = {0.0, 0.0, 0.0};    // profiling: K0/K1/K3 durations summed over the chunks of the last host batch
+    bool host_ms_valid = false;
     HostPipe *pipe = nullptr;      // created on first use
     MultiDev *multi = nullptr;     // gjkepa_create_multi: this context only fans out to its children
 };
@@ -314,6 +317,7 @@ int gjkepa_kernel_ms(gjkepa_ctx *ctx, double *ms)
         }
         return GJKEPA_OK;
     }
+    if (ctx->host_ms_valid) { for (int k = 0; k < 3; ++k) ms[k] = ctx->host_ms[k]; return GJKEPA_OK; }
     ON_DEVICE(ctx);
     for (int k = 0; k < 3; ++k) {
         ms[k] = 0.0;
@@ -345,6 +349,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
 {
     if (!ctx) return GJKEPA_ERR_ARG;
     if (ctx->multi) return fail(ctx, GJKEPA_ERR_ARG, "device buffers belong to one GPU: use a single-device context");
+    ctx->host_ms_valid = false;
     const bool no_clear = (mode & GJKEPA_MODE_NO_CLEAR_) != 0;
     mode &= ~GJKEPA_MODE_NO_CLEAR_;
     if (n_pairs < 0 || n_hulls < 0 || mode < GJKEPA_MODE_GJK || mode > GJKEPA_MODE_FULL)
@@ -979,6 +984,13 @@ int gjkepa_create_multi(gjkepa_ctx **out, const int32_t *devices, int32_t n_devi
         w->th = std::thread(MultiDev::loop, w, (int)devs[i]);
     }
     *out = ctx;
+    return GJKEPA_OK;
+}
+
+int gjkepa_host_phase_ms(const gjkepa_ctx *ctx, double *ms)
+{
+    if (!ctx || !ms) return GJKEPA_ERR_ARG;
+    ms[0] = ctx->phase_ms[0]; ms[1] = ctx->phase_ms[1];
     return GJKEPA_OK;
 }
 

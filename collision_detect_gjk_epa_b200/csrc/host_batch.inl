@@ -338,6 +338,7 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
     }
 
     // ---- the pipeline ----
+    double acc_ms[3] = {0.0, 0.0, 0.0};
     for (int k = 0; k < nchunk; ++k) {
         const int s = k & 1;
         const int64_t a = ch[k].a, n = ch[k].b - ch[k].a;
@@ -380,6 +381,11 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
             w_near ? r64 + r_near * cp : nullptr, w_nrm ? r64 + r_nrm * cp : nullptr, w_pt ? r64 + r_pt * cp : nullptr, w_dep ? r64 + r_dep * cp : nullptr,
             w_st ? (uint32_t *)(out + o_st) : nullptr, nullptr, nullptr);
         if (rc) return rc;
+        if (ctx->profiling) {    // a profiled run gives up the overlap: per-kernel durations summed over the chunks
+            double t[3];
+            if (int rq = gjkepa_kernel_ms(ctx, t)) return rq;
+            for (int q = 0; q < 3; ++q) acc_ms[q] += t[q];
+        }
         if (want_cnt) {          // colliding pairs of the chunk, ascending, and their number -- on the device, from the flags
             size_t tb = p.cap_sel_tmp;
             CU(cub::DeviceSelect::Flagged(p.d_sel_tmp, tb, thrust::counting_iterator<int32_t>((int32_t)(P0 + a)), (const uint8_t *)(out + o_col),
@@ -435,6 +441,7 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         *count = c;
     }
     p.acc_valid = want_idx;
+    if (ctx->profiling) { for (int q = 0; q < 3; ++q) ctx->host_ms[q] = acc_ms[q]; ctx->host_ms_valid = true; }
     return GJKEPA_OK;
 }
 
@@ -548,10 +555,17 @@ int run_request(gjkepa_ctx *ctx, const Req &r)
     if (r.compact && !r.n_contacts) return fail(ctx, GJKEPA_ERR_ARG, "GJKEPA_MODE_COMPACT needs n_contacts");
     if (r.compact && r.f32) return fail(ctx, GJKEPA_ERR_ARG, "GJKEPA_MODE_COMPACT is not offered by the fp32 entry");
     if (r.n_pairs == 0) { if (r.n_contacts) *r.n_contacts = 0; return GJKEPA_OK; }
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+    const clk::time_point t_start = clk::now();
+    ctx->phase_ms[0] = ctx->phase_ms[1] = 0.0;
     if (!ctx->multi) {
         int64_t cnt = 0;
         if (int rc = run_shard(ctx, r, 0, r.n_pairs, &cnt)) return rc;
+        ctx->phase_ms[0] = ms_since(t_start);
+        const clk::time_point t1 = clk::now();
         if (want_idx) { if (int rc = finish_shard(ctx, r, 0, cnt)) return rc; }
+        ctx->phase_ms[1] = ms_since(t1);
         if (r.n_contacts) *r.n_contacts = cnt;
         return GJKEPA_OK;
     }
@@ -570,6 +584,8 @@ int run_request(gjkepa_ctx *ctx, const Req &r)
     int rc = GJKEPA_OK;
     for (int s = 0; s < n; ++s) { const int q = m.wait(s); if (q && !rc) { rc = q; ctx->err = m.kids[(size_t)s]->err; } }
     if (rc) return rc;
+    ctx->phase_ms[0] = ms_since(t_start);
+    const clk::time_point t_fin = clk::now();
     int64_t total = 0;
     if (want_idx) {
         for (int s = 0; s < n; ++s) {
@@ -583,6 +599,7 @@ int run_request(gjkepa_ctx *ctx, const Req &r)
     } else {
         for (int s = 0; s < n; ++s) total += cnt[(size_t)s];
     }
+    ctx->phase_ms[1] = ms_since(t_fin);
     if (r.n_contacts) *r.n_contacts = total;
     return rc;
 }

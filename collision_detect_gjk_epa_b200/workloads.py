@@ -156,6 +156,50 @@ def make_shared_store(n_bodies: int, n_pairs: int, n_vert: int = 16, seed: int =
     return PairBatch(verts, hull_off, a.astype(np.int32), b.astype(np.int32), name=f"store{n_bodies}x{n_vert}")
 
 
+def make_shared_store_gpu(device, n_bodies: int, n_pairs: int, n_vert: int = 16, seed: int = 12345,
+                          spacing: float = 1.0, chunk: int = 1 << 20):
+    """make_shared_store's recipe generated with torch on `device` (numpy takes minutes for cfg5's 10M bodies / 100M
+    pairs) and delivered in PINNED host tensors (verts float64, hull_off int64, pair_a / pair_b int32), as a host that
+    keeps its geometry in page-locked memory would hold them.  Same distribution, different random stream."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    g = int(np.ceil(n_bodies ** (1.0 / 3.0)))
+    verts = torch.empty(3 * n_vert * n_bodies, dtype=torch.float64, pin_memory=True)
+    vview = verts.view(n_bodies, 3, n_vert)
+    f64 = dict(dtype=torch.float64, device=device, generator=gen)
+    for lo in range(0, n_bodies, chunk):
+        hi = min(n_bodies, lo + chunk)
+        m = hi - lo
+        d = torch.randn((m, n_vert, 3), **f64)
+        d /= d.norm(dim=2, keepdim=True)
+        loc = d * (0.5 + 0.5 * torch.rand((m, 1, 3), **f64))
+        q = torch.randn((m, 4), **f64)
+        q /= q.norm(dim=1, keepdim=True)
+        w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        rot = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                           2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                           2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=1).view(m, 3, 3)
+        pts = torch.einsum("mij,mvj->mvi", rot, loc)
+        idx = torch.arange(lo, hi, device=device)
+        site = torch.stack([idx % g, (idx // g) % g, idx // (g * g)], dim=1).to(torch.float64)
+        pts += ((site + (torch.rand((m, 3), **f64) * 0.6 - 0.3)) * spacing)[:, None, :]
+        vview[lo:hi].copy_(pts.transpose(1, 2))
+    hull_off = (torch.arange(n_bodies + 1, dtype=torch.int64) * n_vert).pin_memory()
+    fwd = [(dx, dy, dz) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dz, dy, dx) > (0, 0, 0)]
+    stride = torch.tensor([dx + g * dy + g * g * dz for dx, dy, dz in fwd], dtype=torch.int64, device=device)
+    pair_a = torch.empty(n_pairs, dtype=torch.int32, pin_memory=True)
+    pair_b = torch.empty(n_pairs, dtype=torch.int32, pin_memory=True)
+    for lo in range(0, n_pairs, 16 * chunk):
+        hi = min(n_pairs, lo + 16 * chunk)
+        a = torch.randint(0, n_bodies, (hi - lo,), device=device, generator=gen, dtype=torch.int64)
+        b = (a + stride[torch.randint(0, 13, (hi - lo,), device=device, generator=gen)]) % n_bodies
+        pair_a[lo:hi].copy_(a.to(torch.int32))
+        pair_b[lo:hi].copy_(b.to(torch.int32))
+    torch.cuda.synchronize(device)
+    return verts, hull_off, pair_a, pair_b
+
+
 def unit_cubes(offset=(0.5, 0.0, 0.0)) -> PairBatch:
     """cfg1: A = [-.5,.5]^3, B = A + offset."""
     sx = np.array([-1, 1, -1, 1, -1, 1, -1, 1.0])

@@ -87,6 +87,9 @@ int  gjkepa_create(gjkepa_ctx **ctx, int32_t device);
  * need a single-device context (GJKEPA_ERR_ARG). */
 int  gjkepa_create_multi(gjkepa_ctx **ctx, const int32_t *devices, int32_t n_devices);
 int32_t gjkepa_device_count(const gjkepa_ctx *ctx);
+/* wall clock (ms) of the last HOST-buffer batch call: ms[0] = the shards (copy-in, kernels, per-pair results copied out;
+ * devices side by side), ms[1] = the contact rows / contact_index copied to the caller's arrays at their row offsets */
+int  gjkepa_host_phase_ms(const gjkepa_ctx *ctx, double *ms /*[2]*/);
 int  gjkepa_destroy(gjkepa_ctx *ctx);
 /* Optional: page-lock an array the caller passes to the batch calls again and again (cudaHostRegister, portable).  The
  * arrays a Fortran host ALLOCATEs are pageable; copies from pageable memory go through the driver's staging buffer at a

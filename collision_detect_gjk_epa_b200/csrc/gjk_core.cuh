@@ -354,21 +354,28 @@ GJK_HD void scan_minmax(const HV &h, Vec3 d, int lane0, int step, double &hi, in
 
 // support_mapping, F:1030-1062: p1(first argmax d.p1) - p2(first argmax (-d).p2)
 template <class G, class HV>
-GJK_HD Vec3 support(const G &g, const HV &A, const HV &B, Vec3 d)
+GJK_HD Vec3 support_i(const G &g, const HV &A, const HV &B, Vec3 d, int &iA, int &iB)
 {
     constexpr int L = G::LANES;
-    double bA, bB; int iA, iB;
+    double bA, bB;
     scan_argmax(A, d, g.lane, L, bA, iA);
     scan_argmax(B, neg(d), g.lane, L, bB, iB);
     g.argmax_first(bA, iA);
     g.argmax_first(bB, iB);
     return A.get(iA) - B.get(iB);
 }
+template <class G, class HV>
+GJK_HD Vec3 support(const G &g, const HV &A, const HV &B, Vec3 d)
+{
+    int iA, iB;
+    return support_i(g, A, B, d, iA, iB);
+}
 
 // supports along +d and -d from one pass (F:97 and F:103): dot(-d,v) == -dot(d,v) bit for bit, so
 // the first arg-max of dot(-d,.) is the first arg-min of dot(d,.).
+// ia / ib: vertex numbers of the two rows in their hulls (row 0 in bits 0-7, row 1 in bits 8-15)
 template <class G, class HV>
-GJK_HD void support_both(const G &g, const HV &A, const HV &B, Vec3 d, Vec3 &sp, Vec3 &sm)
+GJK_HD void support_both(const G &g, const HV &A, const HV &B, Vec3 d, Vec3 &sp, Vec3 &sm, unsigned &ia, unsigned &ib)
 {
     constexpr int L = G::LANES;
     double hiA, loA, hiB, loB; int ihA, ilA, ihB, ilB;
@@ -378,6 +385,8 @@ GJK_HD void support_both(const G &g, const HV &A, const HV &B, Vec3 d, Vec3 &sp,
     g.argmax_first(hiB, ihB); g.argmin_first(loB, ilB);
     sp = A.get(ihA) - B.get(ilB);      // direction +d
     sm = A.get(ilA) - B.get(ihB);      // direction -d
+    ia = (unsigned)ihA | ((unsigned)ilA << 8);
+    ib = (unsigned)ilB | ((unsigned)ihB << 8);
 }
 
 #if defined(__CUDACC__)
@@ -503,6 +512,8 @@ struct Walk {
     int iters;          // reference `iter`
     int n_support;
     unsigned fl;
+    unsigned ia, ib;    // after gjk_init: the vertex numbers behind the four rows, S[r] = A[(ia >> 8r) & 255] - B[(ib >> 8r) & 255]
+                        // (hulls of at most 256 vertices; what the seed queue carries instead of the rows)
 #if defined(GJK_SHADOW_HISTORY) && !defined(__CUDA_ARCH__)
     Vec3 sh1[4], sh2[4];    // test builds: simplex_last_1 / _2 kept explicitly, as the reference does (F:193-194)
 #endif
@@ -569,6 +580,7 @@ GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, cons
     const Vec3 O = v3(0.0, 0.0, 0.0);
     w.S[0] = w.S[1] = w.S[2] = w.S[3] = O;
     w.qk = O; w.mk = 0.0; w.D1 = O; w.k1 = 2; w.iters = 0; w.n_support = 0; w.fl = WF_FIRST | (early ? WF_EARLY : 0u);
+    w.ia = w.ib = 0u;
 
     // F:76-77.  With shortcut E1 the test is skipped (and the spheres need not be computed): the spheres enclose the hulls, so a
     // miss means the hulls are more than 1.0 apart, which the walk finds out on its own -- same flag, different exit path
@@ -577,7 +589,7 @@ GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, cons
     for (;;) {
         ++it;
         if (it > 99) return EXIT_INIT_CAP;                                    // F:86
-        support_both(g, A, B, dir_table(it - 1), w.S[0], w.S[1]);            // F:94-103
+        support_both(g, A, B, dir_table(it - 1), w.S[0], w.S[1], w.ia, w.ib);  // F:94-103
         w.n_support += 2;
         if (early && (early_separated(w.S[0], dir_table(it - 1)) || early_separated(w.S[1], neg(dir_table(it - 1))))) return EXIT_EARLY_OUT;
         if (!close3(w.S[0], w.S[1])) break;                                  // F:106
@@ -589,7 +601,8 @@ GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, cons
         dir = vec_pl_tail<MathFast>(w.S[0], ab, dab);
         if (dir.x != dir.x) { dir = vec_pl_tail<MathCold>(w.S[0], ab, dab); w.fl |= WF_COLD; }   // NaN marks "redo exactly"
     }
-    w.S[2] = support(g, A, B, dir); ++w.n_support;                           // F:119
+    { int iA, iB; w.S[2] = support_i(g, A, B, dir, iA, iB); w.ia |= (unsigned)iA << 16; w.ib |= (unsigned)iB << 16; }   // F:119
+    ++w.n_support;
     if (early && early_separated(w.S[2], dir)) return EXIT_EARLY_OUT;
     if (close3(w.S[2], w.S[0]) || close3(w.S[2], w.S[1])) return EXIT_DUP3;  // F:123
 
@@ -612,7 +625,8 @@ GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, cons
         if (fabs(dt) < 1.0e-8 && inside_pf3(w.S[0], w.S[1], w.S[2], O)) return EXIT_TRI_ORIGIN;   // F:140
         if (dt < 0.0) dir = neg(dir);                                        // F:151
     }
-    w.S[3] = support(g, A, B, dir); ++w.n_support;                           // F:154
+    { int iA, iB; w.S[3] = support_i(g, A, B, dir, iA, iB); w.ia |= (unsigned)iA << 24; w.ib |= (unsigned)iB << 24; }   // F:154
+    ++w.n_support;
     if (early && early_separated(w.S[3], dir)) return EXIT_EARLY_OUT;
     {   // DIST_PF_SIGN(S3, (S0,S1,S2)), F:157, with UNINML's own zero rule (F:1392)
         bool nz = fabs(c3.x) > 1.0e-12 || fabs(c3.y) > 1.0e-12 || fabs(c3.z) > 1.0e-12;

@@ -153,10 +153,15 @@ __device__ __forceinline__ Sphere hull_sphere_t2(const HullViewT2 &hv)
 }
 
 // ---- seed queue: what K1i hands to K1w (structure of arrays, `cap` entries each) ----
-constexpr int SEED_F64 = 16;             // S0..S3 xyz, unit normal of face (1,2,3) xyz, its |cross|
+// The four rows of the tetrahedron are A[i] - B[j] for vertex numbers K1i knows, and K1w stages the hulls anyway:
+// the queue carries the eight vertex numbers (8 bytes) and K1w rebuilds the rows bit for bit from its staged copy,
+// instead of 96 bytes of coordinates written and read back through HBM.  The unit normal of face (1,2,3) travels
+// as computed (its straight-line / cold-redo history is not worth repeating): 64 bytes per seed, was 152.
+constexpr int SEED_F64 = 4;              // unit normal of face (1,2,3) xyz, its |cross|
 constexpr unsigned SEED_COLD = 1u;       // fln = flags (4 bits) | nA << 4 | nB << 18
 struct SeedQueue {
     double   *f64;                       // SEED_F64 arrays of cap doubles
+    uint2    *idx;                       // vertex numbers of the rows in hull A (.x) and hull B (.y), one byte per row
     int32_t  *pair;
     uint32_t *fln;
     int64_t  *oa, *ob;                   // hull offsets (vertex units), so K1w needs no dependent index loads
@@ -307,10 +312,8 @@ gjk_init_kernel(TwoStageArgs ta)
                 const unsigned long long s = base + __popc(go & ((1u << lane) - 1u));
                 double *f = ta.q.f64 + s;
                 const int64_t cap = ta.q.cap;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) { f[(3 * r) * cap] = w.S[r].x; f[(3 * r + 1) * cap] = w.S[r].y; f[(3 * r + 2) * cap] = w.S[r].z; }
-                f[12 * cap] = w.qk.x; f[13 * cap] = w.qk.y; f[14 * cap] = w.qk.z;
-                f[15 * cap] = w.mk;
+                f[0] = w.qk.x; f[cap] = w.qk.y; f[2 * cap] = w.qk.z; f[3 * cap] = w.mk;
+                ta.q.idx[s] = make_uint2(w.ia, w.ib);
                 ta.q.pair[s] = (int32_t)p;
                 ta.q.fln[s] = ((w.fl & WF_COLD) ? SEED_COLD : 0u) | ((unsigned)nA << 4) | ((unsigned)nB << 18);
                 ta.q.oa[s] = m.oa; ta.q.ob[s] = m.ob;
@@ -358,8 +361,9 @@ gjk_walk_kernel(TwoStageArgs ta)
             prefetch_l2_range(a.verts + 3 * bt.oa, 24 * (int)((bt.fln >> 4) & 0x3fffu));
             prefetch_l2_range(a.verts + 3 * bt.ob, 24 * (int)(bt.fln >> 18));
         }
-        if (bt.n > 0)                                               // seed records: 16 fields x 256 bytes, one line per lane
+        if (bt.n > 0 && lane < 2 * SEED_F64)                        // seed records: 4 fields x 256 bytes, one line per lane
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ta.q.f64 + (size_t)(lane >> 1) * cap + bt.base + (lane & 1) * 16));
+        if (bt.n > 0 && (lane == 8 || lane == 9)) asm volatile("prefetch.global.L2 [%0];" ::"l"(ta.q.idx + bt.base + (lane & 1) * 16));
     };
     Batch cur, nxt;
     fetch(cur); prefetch(cur);
@@ -385,14 +389,14 @@ gjk_walk_kernel(TwoStageArgs ta)
                 const int nA = take ? (int)((sfln >> 4) & 0x3fffu) : 0, nB = take ? (int)(sfln >> 18) : 0;
                 const int hA = (nA + 1) >> 1, hB = (nB + 1) >> 1;
                 const int tmaxA = __reduce_max_sync(FULL, 3 * hA), tmaxB = __reduce_max_sync(FULL, 3 * hB);
+                uint2 t2 = make_uint2(0u, 0u);
                 stage_own_hull(col, a.verts + 3 * soa, nA, hA, take, tmaxA);
                 stage_own_hull(col + 3 * hA * T2_PITCH, a.verts + 3 * sob, nB, hB, take, tmaxB);
                 if (take) {
                     const double *f = ta.q.f64 + (cur.base + (unsigned long long)(bcur + rank));
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) w.S[r] = v3(f[(3 * r) * cap], f[(3 * r + 1) * cap], f[(3 * r + 2) * cap]);
-                    w.qk = v3(f[12 * cap], f[13 * cap], f[14 * cap]);
-                    w.mk = f[15 * cap];
+                    w.qk = v3(f[0], f[cap], f[2 * cap]);
+                    w.mk = f[3 * cap];
+                    t2 = ta.q.idx[cur.base + (unsigned long long)(bcur + rank)];
                     w.D1 = v3(0.0, 0.0, 0.0); w.k1 = 2; w.iters = 0; w.n_support = 4;
                     w.fl = WF_FIRST | ((sfln & SEED_COLD) ? WF_COLD : 0u) | (a.early_out ? WF_EARLY : 0u);
                     p = sp_;
@@ -402,6 +406,10 @@ gjk_walk_kernel(TwoStageArgs ta)
                 }
                 bcur += n_take;
                 cp_async_wait_all();
+                if (take) {                                         // the tetrahedron K1i ended with, from the staged hulls
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) w.S[r] = A.get((int)((t2.x >> (8 * r)) & 0xffu)) - B.get((int)((t2.y >> (8 * r)) & 0xffu));
+                }
             }
         }
         if (!__any_sync(FULL, active)) {

@@ -127,10 +127,8 @@ gjk_init_group_kernel(TwoStageArgs ta, int slot_doubles)
                 const unsigned long long s = base + __popc(go & ((1u << lane) - 1u));
                 double *f = ta.q.f64 + s;
                 const int64_t cap = ta.q.cap;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) { f[(3 * r) * cap] = w.S[r].x; f[(3 * r + 1) * cap] = w.S[r].y; f[(3 * r + 2) * cap] = w.S[r].z; }
-                f[12 * cap] = w.qk.x; f[13 * cap] = w.qk.y; f[14 * cap] = w.qk.z;
-                f[15 * cap] = w.mk;
+                f[0] = w.qk.x; f[cap] = w.qk.y; f[2 * cap] = w.qk.z; f[3 * cap] = w.mk;
+                ta.q.idx[s] = make_uint2(w.ia, w.ib);
                 ta.q.pair[s] = (int32_t)p;
                 ta.q.fln[s] = ((w.fl & WF_COLD) ? SEED_COLD : 0u) | ((unsigned)GA.n << 4) | ((unsigned)GB.n << 18);
                 ta.q.oa[s] = (int64_t)((GA.x - a.verts) / 3); ta.q.ob[s] = (int64_t)((GB.x - a.verts) / 3);
@@ -178,9 +176,10 @@ gjk_walk_group_kernel(TwoStageArgs ta, int slot_doubles)
     // L2 prefetch, a few pairs ahead only: with 1.5 KB per pair a whole batch per warp (x 2400 resident warps)
     // outgrows L2 and the lines are gone again before they are used (ncu: DRAM reads 2x the hull bytes)
     constexpr int AHEAD = 8;
-    auto prefetch_records = [&](const Batch &bt) {                // seed records: 16 fields x 256 bytes, one line per lane
-        if (bt.n > 0)
+    auto prefetch_records = [&](const Batch &bt) {                // seed records: 4 fields x 256 bytes, one line per lane
+        if (bt.n > 0 && lane < 2 * SEED_F64)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ta.q.f64 + (size_t)(lane >> 1) * cap + bt.base + (lane & 1) * 16));
+        if (bt.n > 0 && (lane == 8 || lane == 9)) asm volatile("prefetch.global.L2 [%0];" ::"l"(ta.q.idx + bt.base + (lane & 1) * 16));
     };
     auto prefetch_hulls = [&](const Batch &bt, int from) {         // the hull blocks of entries [from, from + AHEAD)
         if (lane >= from && lane < from + AHEAD && lane < bt.n) {
@@ -230,16 +229,16 @@ gjk_walk_group_kernel(TwoStageArgs ta, int slot_doubles)
                                             it_, count, cur.base, bcur, rank, n_take, cur.n, src, sp_, soa, sob, nA_, nB_);
                 }
 #endif
+                uint2 t2 = make_uint2(0u, 0u);
                 if (take) {
                     const int nA = (int)((sfln >> 4) & 0x3fffu), nB = (int)(sfln >> 18);
                     const double *srcA = a.verts + 3 * soa, *srcB = a.verts + 3 * sob;
                     for (int e = gl; e < 3 * nA; e += L) cp_async8(slot + e, srcA + e);
                     for (int e = gl; e < 3 * nB; e += L) cp_async8(slot + 3 * nA + e, srcB + e);
                     const double *f = ta.q.f64 + (cur.base + (unsigned long long)(bcur + rank));
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) w.S[r] = v3(f[(3 * r) * cap], f[(3 * r + 1) * cap], f[(3 * r + 2) * cap]);
-                    w.qk = v3(f[12 * cap], f[13 * cap], f[14 * cap]);
-                    w.mk = f[15 * cap];
+                    w.qk = v3(f[0], f[cap], f[2 * cap]);
+                    w.mk = f[3 * cap];
+                    t2 = ta.q.idx[cur.base + (unsigned long long)(bcur + rank)];
                     w.D1 = v3(0.0, 0.0, 0.0); w.k1 = 2; w.iters = 0; w.n_support = 4;
                     w.fl = WF_FIRST | ((sfln & SEED_COLD) ? WF_COLD : 0u) | (a.early_out ? WF_EARLY : 0u);
                     p = sp_;
@@ -250,6 +249,10 @@ gjk_walk_group_kernel(TwoStageArgs ta, int slot_doubles)
                 bcur += n_take;
                 cp_async_wait_all();
                 __syncwarp();                                   // the group's lanes read each other's copies
+                if (take) {                                     // the tetrahedron K1ig ended with, from the staged hulls
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) w.S[r] = A.get((int)((t2.x >> (8 * r)) & 0xffu)) - B.get((int)((t2.y >> (8 * r)) & 0xffu));
+                }
             }
         }
         if (!__any_sync(FULL, active)) {

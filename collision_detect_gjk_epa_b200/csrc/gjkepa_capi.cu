@@ -55,6 +55,7 @@ struct gjkepa_ctx {
     int early_out = 0;             // shortcut E1 (opt-in): see gjk_core.cuh
     int tile_max_vertices = 16;    // largest hull the thread-per-pair kernels stage (larger ones: 4-lane kernels)
     double *d_seed_f64 = nullptr; int32_t *d_seed_pair = nullptr; uint32_t *d_seed_fl = nullptr; int64_t *d_seed_off = nullptr; int64_t cap_seed = 0;
+    uint2 *d_seed_idx = nullptr;
     int32_t *d_ovf = nullptr; int64_t cap_ovf = 0;
     int32_t *d_ovf2 = nullptr; int64_t cap_ovf2 = 0;
     // workspace (device)
@@ -209,6 +210,7 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
     if (ctx->d_seed_pair) cudaFree(ctx->d_seed_pair);
     if (ctx->d_seed_fl) cudaFree(ctx->d_seed_fl);
     if (ctx->d_seed_off) cudaFree(ctx->d_seed_off);
+    if (ctx->d_seed_idx) cudaFree(ctx->d_seed_idx);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->d_shape_verts) cudaFree(ctx->d_shape_verts);
     if (ctx->d_shape_off) cudaFree(ctx->d_shape_off);
@@ -437,16 +439,18 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
             if (ctx->d_seed_pair) cudaFree(ctx->d_seed_pair);
             if (ctx->d_seed_fl) cudaFree(ctx->d_seed_fl);
             if (ctx->d_seed_off) cudaFree(ctx->d_seed_off);
-            ctx->d_seed_f64 = nullptr; ctx->d_seed_pair = nullptr; ctx->d_seed_fl = nullptr; ctx->d_seed_off = nullptr; ctx->cap_seed = 0;
+            if (ctx->d_seed_idx) cudaFree(ctx->d_seed_idx);
+            ctx->d_seed_f64 = nullptr; ctx->d_seed_pair = nullptr; ctx->d_seed_fl = nullptr; ctx->d_seed_off = nullptr; ctx->d_seed_idx = nullptr; ctx->cap_seed = 0;
             const int64_t ncap = ((n_pairs + n_pairs / 8 + 1024) + 31) & ~(int64_t)31;
             cudaError_t e = cudaMalloc((void **)&ctx->d_seed_f64, (size_t)ncap * gjk::SEED_F64 * sizeof(double));
             if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_pair, (size_t)ncap * sizeof(int32_t));
             if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_fl, (size_t)ncap * sizeof(uint32_t));
             if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_off, (size_t)ncap * 2 * sizeof(int64_t));
+            if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_idx, (size_t)ncap * sizeof(uint2));
             if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc seed queue", e);
             ctx->cap_seed = ncap;
         }
-        ta.q.f64 = ctx->d_seed_f64; ta.q.pair = ctx->d_seed_pair; ta.q.fln = ctx->d_seed_fl;
+        ta.q.f64 = ctx->d_seed_f64; ta.q.pair = ctx->d_seed_pair; ta.q.fln = ctx->d_seed_fl; ta.q.idx = ctx->d_seed_idx;
         ta.q.oa = ctx->d_seed_off; ta.q.ob = ctx->d_seed_off + ctx->cap_seed;
         ta.q.count = ctx->d_counters + 6; ta.q.head = ctx->d_counters + 7; ta.q.cap = ctx->cap_seed;
         const size_t smem = (size_t)ta.col_units * gjk::T2_PITCH * (gjk::TILE / 32);
@@ -526,7 +530,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                 // buffers of the thread-per-pair stage are free again by now (same stream), only the counters differ
                 gjk::TwoStageArgs tg;
                 tg.b = b; tg.col_units = 0; tg.refill = ctx->walk_refill;
-                tg.q.f64 = ctx->d_seed_f64; tg.q.pair = ctx->d_seed_pair; tg.q.fln = ctx->d_seed_fl;
+                tg.q.f64 = ctx->d_seed_f64; tg.q.pair = ctx->d_seed_pair; tg.q.fln = ctx->d_seed_fl; tg.q.idx = ctx->d_seed_idx;
                 tg.q.oa = ctx->d_seed_off; tg.q.ob = ctx->d_seed_off + ctx->cap_seed;
                 tg.q.count = ctx->d_counters + 10; tg.q.head = ctx->d_counters + 11; tg.q.cap = ctx->cap_seed;
                 if (fuse) {

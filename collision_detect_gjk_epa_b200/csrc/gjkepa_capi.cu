@@ -1256,8 +1256,78 @@ int gjkepa_debug_fp64(gjkepa_ctx *ctx, int64_t n, const double *a, const double 
 }
 
 // ---- drop-in single pair: same dummy-argument list as GJKEPA (F:39-52), everything by reference ----
-static std::mutex g_default_mu;
-static gjkepa_ctx *g_default_ctx = nullptr;
+// The reference is called from inside an !$OMP PARALLEL DO over pairs (THREADPRIVATE scratch, F:55-60): many host threads,
+// one pair each, all at once.  A GPU round trip costs tens of microseconds whatever it carries, so concurrent callers are
+// COMBINED: a caller that finds no batch in flight becomes the leader, takes every request queued so far (its own included),
+// runs them as ONE small batch on the process-wide context and hands each caller its results; callers that arrive while
+// that batch is on the GPU queue up for the next one, which the next leader (the first of them to notice) runs.
+// Throughput is then (calling threads) / (one round trip) instead of 1 / (one round trip).
+} // extern "C"
+namespace {
+struct PairJob {
+    int32_t version; double tol; const double *p1; int32_t n1; const double *p2; int32_t n2;
+    uint8_t *collision; int32_t *colli_type; double *nearest, *normal, *point, *depth;
+    int rc = GJKEPA_OK;
+    std::atomic<int> done{0};
+};
+std::mutex g_pair_mu;                          // guards the queue and the leader flag
+std::vector<PairJob *> g_pair_q;
+bool g_pair_leader = false;
+gjkepa_ctx *g_default_ctx = nullptr;           // created by the first leader, used by one leader at a time
+
+// one batch: jobs that share version_ and TOL_FF_ go through one gjkepa_batch_f64 call (tiny-batch path: one block in, one block out)
+void run_pair_jobs(std::vector<PairJob *> &jobs)
+{
+    static std::vector<double> verts, nr, nm, pt, dp;      // leader-only scratch
+    static std::vector<int64_t> off;
+    static std::vector<int32_t> pa, pb, ty;
+    static std::vector<uint8_t> col;
+    static std::vector<PairJob *> grp;
+    if (!g_default_ctx) {
+        const int rc = gjkepa_create(&g_default_ctx, 0);
+        if (rc) { for (PairJob *j : jobs) { j->rc = rc; j->done.store(1, std::memory_order_release); } return; }
+    }
+    size_t next = 0;
+    std::vector<char> taken(jobs.size(), 0);
+    while (next < jobs.size()) {
+        while (next < jobs.size() && taken[next]) ++next;
+        if (next >= jobs.size()) break;
+        const int32_t ver = jobs[next]->version; const double tol = jobs[next]->tol;
+        grp.clear(); verts.clear(); off.assign(1, 0); pa.clear(); pb.clear();
+        size_t bytes = 0;
+        for (size_t i = next; i < jobs.size(); ++i) {
+            PairJob *j = jobs[i];
+            if (taken[i] || j->version != ver || !(j->tol == tol)) continue;
+            const size_t add = (size_t)24 * (j->n1 + j->n2) + 160;
+            if (!grp.empty() && (bytes + add > 80 * 1024 || grp.size() >= 256)) break;      // stays on the tiny-batch path
+            bytes += add; taken[i] = 1; grp.push_back(j);
+            verts.insert(verts.end(), j->p1, j->p1 + 3 * (size_t)j->n1);
+            off.push_back(off.back() + j->n1);
+            verts.insert(verts.end(), j->p2, j->p2 + 3 * (size_t)j->n2);
+            off.push_back(off.back() + j->n2);
+            pa.push_back((int32_t)(2 * (grp.size() - 1))); pb.push_back((int32_t)(2 * (grp.size() - 1) + 1));
+        }
+        const size_t m = grp.size();
+        col.assign(m, 0); ty.assign(m, 0); nr.assign(6 * m, 0.0); nm.assign(3 * m, 0.0); pt.assign(3 * m, 0.0); dp.assign(m, 0.0);
+        const int rc = gjkepa_batch_f64(g_default_ctx, ver, tol, (int64_t)(2 * m), verts.data(), off.data(), (int64_t)m, pa.data(), pb.data(),
+                                        GJKEPA_MODE_FULL, col.data(), ty.data(), nr.data(), nm.data(), pt.data(), dp.data(), nullptr, nullptr, nullptr);
+        for (size_t k = 0; k < m; ++k) {
+            PairJob *j = grp[k];
+            j->rc = rc;
+            if (!rc) {
+                if (j->collision) *j->collision = col[k];          /* LOGICAL*1: write 1, read "!= 0" */
+                if (j->colli_type) *j->colli_type = ty[k];
+                if (j->nearest) std::memcpy(j->nearest, &nr[6 * k], 48);
+                if (j->normal) std::memcpy(j->normal, &nm[3 * k], 24);
+                if (j->point) std::memcpy(j->point, &pt[3 * k], 24);
+                if (j->depth) *j->depth = dp[k];
+            }
+            j->done.store(1, std::memory_order_release);           // j may leave its caller's stack frame from here on
+        }
+    }
+}
+}  // namespace
+extern "C" {
 
 int gjkepa_pair_f64(const int32_t *version, const double *tol_ff,
                     const double *p1, const int32_t *n1, const double *p2, const int32_t *n2,
@@ -1265,27 +1335,43 @@ int gjkepa_pair_f64(const int32_t *version, const double *tol_ff,
                     double *nearest, double *normal, double *point, double *depth)
 {
     if (!version || !tol_ff || !p1 || !n1 || !p2 || !n2 || *n1 <= 0 || *n2 <= 0) return GJKEPA_ERR_ARG;
-    std::lock_guard<std::mutex> lk(g_default_mu);
-    if (!g_default_ctx) {
-        int rc = gjkepa_create(&g_default_ctx, 0);
-        if (rc) return rc;
+    PairJob job;
+    job.version = *version; job.tol = *tol_ff; job.p1 = p1; job.n1 = *n1; job.p2 = p2; job.n2 = *n2;
+    job.collision = collision; job.colli_type = colli_type; job.nearest = nearest; job.normal = normal; job.point = point; job.depth = depth;
+    bool lead = false;
+    {
+        std::lock_guard<std::mutex> lk(g_pair_mu);
+        g_pair_q.push_back(&job);
+        if (!g_pair_leader) { g_pair_leader = true; lead = true; }
     }
-    std::vector<double> verts((size_t)3 * (*n1 + *n2));
-    std::memcpy(verts.data(), p1, (size_t)3 * *n1 * sizeof(double));
-    std::memcpy(verts.data() + 3 * *n1, p2, (size_t)3 * *n2 * sizeof(double));
-    int64_t off[3] = { 0, *n1, (int64_t)*n1 + *n2 };
-    int32_t pa = 0, pb = 1;
-    uint8_t col = 0; int32_t type = 0; double nr[6] = {0}, nm[3] = {0}, pt[3] = {0}, dp = 0.0;
-    int rc = gjkepa_batch_f64(g_default_ctx, *version, *tol_ff, 2, verts.data(), off, 1, &pa, &pb,
-                              GJKEPA_MODE_FULL, &col, &type, nr, nm, pt, &dp, nullptr, nullptr, nullptr);
-    if (rc) return rc;
-    if (collision) *collision = col;          /* LOGICAL*1: write 1, read "!= 0" */
-    if (colli_type) *colli_type = type;
-    if (nearest) std::memcpy(nearest, nr, sizeof nr);
-    if (normal) std::memcpy(normal, nm, sizeof nm);
-    if (point) std::memcpy(point, pt, sizeof pt);
-    if (depth) *depth = dp;
-    return GJKEPA_OK;
+    std::vector<PairJob *> mine;
+    unsigned spins = 0;
+    for (;;) {
+        if (lead) {
+            // run batches until this caller's own request is served, then pass the lead on
+            {
+                std::lock_guard<std::mutex> lk(g_pair_mu);
+                mine.swap(g_pair_q);
+            }
+            if (!mine.empty()) run_pair_jobs(mine);
+            mine.clear();
+            if (job.done.load(std::memory_order_acquire)) {
+                std::lock_guard<std::mutex> lk(g_pair_mu);
+                g_pair_leader = false;              // a waiting caller picks the lead up (below)
+                return job.rc;
+            }
+            continue;
+        }
+        if (job.done.load(std::memory_order_acquire)) return job.rc;
+        if ((++spins & 63u) == 0u) {
+            std::lock_guard<std::mutex> lk(g_pair_mu);
+            if (!g_pair_leader && !job.done.load(std::memory_order_acquire)) { g_pair_leader = true; lead = true; }
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if (spins > 4000u) std::this_thread::yield();
+    }
 }
 
 }  // extern "C"

@@ -202,7 +202,21 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
     const int32_t *pa = r.pair_a + P0, *pb = r.pair_b + P0;
 
     // ---- chunk plan ----
-    int nchunk = ctx->host_chunks > 0 ? ctx->host_chunks : (int)(np / 65536 < 1 ? 1 : (np / 65536 > 8 ? 8 : np / 65536));
+    // Chunks pay when the copies are a large part of the step: about one per 32 MB that crosses PCIe per pair-proportional
+    // array (hull bytes of a pair-private store, pair lists, per-pair results), at most 8, at least 64k pairs each.  A
+    // resident store with compact results stays in one piece (every chunk costs the kernels' ramp-up and tail once more).
+    int nchunk = ctx->host_chunks;
+    if (nchunk <= 0) {
+        const bool epa_ = r.mode >= GJKEPA_MODE_EPA, full_ = r.mode == GJKEPA_MODE_FULL;
+        double per_pair = 8.0 + (r.collision ? 1.0 : 0.0) + (r.status && !r.compact ? 4.0 : 0.0);
+        if (!r.compact) per_pair += (r.f32 ? 0.5 : 1.0) * ((r.depth && epa_ ? 8 : 0) + (r.normal && epa_ ? 24 : 0) + (r.point && full_ ? 24 : 0) + (r.nearest && full_ ? 48 : 0))
+                                    + (r.colli_type && full_ ? 4 : 0);
+        if ((r.src == SRC_HOST || r.src == SRC_HOST_F32) && r.n_hulls >= r.n_pairs / 2)
+            per_pair += (r.f32 ? 12.0 : 24.0) * (double)(r.hull_off[r.n_hulls] - r.hull_off[0]) / (double)r.n_pairs;
+        const double mb = per_pair * (double)np / (32.0 * 1024 * 1024);
+        nchunk = mb < 1.0 ? 1 : (mb > 8.0 ? 8 : (int)mb);
+        if ((int64_t)nchunk > np / 65536) nchunk = (int)(np / 65536 < 1 ? 1 : np / 65536);
+    }
     if (nchunk > hostb::MAX_CHUNKS) nchunk = hostb::MAX_CHUNKS;
     int64_t cp = (np + nchunk - 1) / nchunk;
     cp = (cp + 1023) & ~(int64_t)1023;

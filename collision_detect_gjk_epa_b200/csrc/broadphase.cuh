@@ -35,6 +35,17 @@ __host__ __device__ __forceinline__ double dkey_inv(unsigned long long k)
 #endif
 }
 
+// A body whose envelope sphere is not finite (a NaN or Inf vertex) takes no part: it neither moves the grid's bounds --
+// one NaN would put every body into cell 0 (an all-pairs scan) or drop whole rows of cells -- nor gets a cell, and it
+// is emitted in no pair.  The narrow phase answers FALSE for every pair that has such a body (NaN: every comparison of
+// F:1185 fails; Inf: the walk ends on the reference's STOP path, tests/test_gpu_nonfinite.py), so the CONTACT set is
+// what an all-pairs host loop gets; only candidates that could never collide are left out.
+__device__ __forceinline__ bool finite_sphere(const Sphere &v)
+{
+    return fabs(v.cx) <= DBL_MAX && fabs(v.cy) <= DBL_MAX && fabs(v.cz) <= DBL_MAX && fabs(v.r) <= DBL_MAX;
+}
+constexpr unsigned long long KEY_NONE = 0x7fffffffffffffffull;      // sorts after every cell of an exact grid
+
 // slack: the absolute term of the sphere test, 1.0 in the reference (F:1185)
 __global__ void bounds_init_kernel(Bounds *b, double slack)
 {
@@ -49,6 +60,7 @@ bounds_kernel(const Sphere *__restrict__ s, int64_t n, Bounds *b)
     unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, kr = 0ull, m0 = 0ull, m1 = 0ull, m2 = 0ull;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const Sphere v = s[i];
+        if (!finite_sphere(v)) continue;
         const unsigned long long a0 = dkey(v.cx), a1 = dkey(v.cy), a2 = dkey(v.cz), ar = dkey(v.r);
         k0 = a0 < k0 ? a0 : k0; k1 = a1 < k1 ? a1 : k1; k2 = a2 < k2 ? a2 : k2; kr = ar > kr ? ar : kr;
         m0 = a0 > m0 ? a0 : m0; m1 = a1 > m1 ? a1 : m1; m2 = a2 > m2 ? a2 : m2;
@@ -100,8 +112,9 @@ keys_kernel(const Sphere *__restrict__ s, int64_t n, const Bounds *__restrict__ 
     const Grid g = grid_of(b);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         long long ix, iy, iz;
-        cell_of(g, s[i], ix, iy, iz);
-        keys[i] = cell_key(ix, iy, iz);
+        const Sphere v = s[i];
+        cell_of(g, v, ix, iy, iz);
+        keys[i] = finite_sphere(v) ? cell_key(ix, iy, iz) : KEY_NONE;
         ids[i] = (int32_t)i;
     }
 }
@@ -136,6 +149,7 @@ pairs_kernel(const Sphere *__restrict__ s, int64_t n, const Bounds *__restrict__
         cell_of(g, si, ix, iy, iz);
         int64_t cnt = 0;
         const int64_t out0 = FILL ? offsets[t] : 0;
+        if (!finite_sphere(si)) { if (!FILL) counts[t] = 0; continue; }
         if (g.exact) {
             // every body's cell index lies in [0, n*] (floor is monotone), so rows outside are empty and the three cells
             // of a row along x are one run of consecutive keys
@@ -164,7 +178,8 @@ pairs_kernel(const Sphere *__restrict__ s, int64_t n, const Bounds *__restrict__
             for (int64_t u = lower_bound(skeys, n, key); u < n && skeys[u] == key; ++u) {
                 const int32_t j = sids[u];
                 if (j <= i) continue;
-                if (sphere_pass(si, s[j], g.slack)) {                 // F:1185, the reference's own test
+                const Sphere sj = s[j];
+                if (finite_sphere(sj) && sphere_pass(si, sj, g.slack)) {   // F:1185, the reference's own test
                     if (FILL) { const int64_t o = out0 + cnt; if (o < cap) { pair_a[o] = i; pair_b[o] = j; } }
                     ++cnt;
                 }

@@ -362,7 +362,7 @@ gjk_group_staged_kernel(BatchArgs a, int slot_doubles)
         cp_async_wait_all();
         {
             unsigned spins = 0;
-            while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 24)) __trap(); }
+            while (!mbar_try_wait(bar, parity)) { if (++spins > 64u) __nanosleep(32); }     // no poll limit (see gjk_two_stage_group.cuh)
             parity ^= 1u;
         }
         __syncwarp();

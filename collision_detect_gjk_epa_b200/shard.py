@@ -2,9 +2,13 @@
 
 Pairs are independent, so the batch splits by contiguous pair-index range with NO collective on
 the data path: every rank (one process per GPU) holds the whole hull store (replicated; 3.84 GB at
-cfg5) and its slice of the pair list, and writes results at the pair's global index.  The only
+cfg5) and its slice of the pair list.  ShardedEngine.run returns SHARD-LOCAL arrays (row k = pair
+pair_range[0] + k); only the gathered contact list carries global pair numbers.  The only
 exchange is optional and follows the kernels: an all-gather of the compacted contact list
 (counts first, then padded blocks) so that every rank sees every contact.
+
+One HOST process over several GPUs needs none of this: a context made by gjkepa_create_multi
+(Engine(devices=[...])) shards inside the library and writes at the global pair index.
 """
 from __future__ import annotations
 

@@ -143,3 +143,32 @@ def test_scene_step_without_contacts(W, engine):
     engine.upload_shapes(pb.shape_verts, pb.shape_off)
     sc = engine.scene_posed(pb.body_shape, pb.pose, mode="epa")
     assert sc["n_candidates"] == 0 and sc["n_contacts"] == 0 and len(sc["body_a"]) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("poison", [np.nan, np.inf, -np.inf])
+def test_non_finite_bodies_do_not_poison_the_grid(W, orc, engine, poison):
+    """One NaN / Inf vertex used to reach the grid's global bounds (every body in cell 0: an all-pairs scan, or whole rows
+    of cells dropped).  Such a body now takes no part; every other pair is found as before, and the contacts of a scene
+    step are those of the scene without it (the narrow phase answers FALSE for any pair with a non-finite hull)."""
+    verts, off = _scene(W, 4000, 16, 1.6, seed=77)
+    bad = (17, 2500)
+    v = verts.copy()
+    for h in bad:
+        v[3 * off[h] + 5] = poison
+    ra, rb = orc.sphere_pairs(verts, off)                       # the clean scene
+    want = {(a, b) for a, b in zip(ra.tolist(), rb.tolist()) if a not in bad and b not in bad}
+    ga, gb = engine.broadphase(v, off)
+    assert _as_set(ga, gb) == want
+    # scene step: shapes = the hulls themselves, identity poses
+    n = len(off) - 1
+    pose = np.zeros((n, 12)); pose[:, 0] = pose[:, 4] = pose[:, 8] = 1.0
+    shp = np.arange(n, dtype=np.int32)
+    engine.upload_shapes(v, off)
+    got = engine.scene_posed(shp, pose, mode="epa")
+    engine.upload_shapes(verts, off)
+    clean = engine.scene_posed(shp, pose, mode="epa")
+    keep = ~(np.isin(clean["body_a"], bad) | np.isin(clean["body_b"], bad))
+    assert got["n_contacts"] == int(keep.sum())
+    assert np.array_equal(got["body_a"], clean["body_a"][keep]) and np.array_equal(got["body_b"], clean["body_b"][keep])
+    assert np.array_equal(got["depth"], clean["depth"][keep])

@@ -233,7 +233,7 @@ constexpr int WARPS = 4;
 #define EPA3_MIN_CTAS 5
 #endif
 template <int LP, int VC, int FC, int HC>
-__global__ void __launch_bounds__(WARPS * 32, EPA3_MIN_CTAS)
+__global__ void __launch_bounds__(WARPS * 32, (HC > 64 ? 4 : EPA3_MIN_CTAS))      // shared memory holds 4 CTAs of the 128-vertex form
 epa3_kernel(EpaArgs a)
 {
     static_assert(FC <= 255 && VC <= 255, "ids are bytes");
@@ -407,30 +407,95 @@ inline int launch_one(const EpaArgs &a, int sm_count, cudaStream_t st)
     return 0;
 }
 
-// Up to three passes over shrinking lists.  The linked-mesh kernel (16 lanes and a 36-vertex mesh per pair,
-// two pairs per warp) runs first when the caller bounds its hulls by 32 vertices; with larger or mixed hulls it
-// does not pay (the two pairs of a warp hold each other up and a full-warp version of it matches the general
-// kernel to within 5 %, measured on cfg4), so those batches go straight to the general kernel: (64,128)
-// polytopes, then (128,256) = the reference's hard bound (4 + 99 iterations) for what is left.
-// counters: [1] pass-1 head, [4] pass-1 declined count, [3] pass-2 head, [8] pass-2 declined count, [9] pass-3 head
-inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32_t *ovf2, unsigned long long *counters,
-                  bool small_first, int *launches)
+// ---- per-pair routing by hull size (counters below are indices into the context's counter block) ----
+// The colliding pairs reach the EPA stage in the order the GJK warps finished them.  route_count / route_fill bin the
+// work list by nA + nB: "small" (<= 64 vertices: the linked-mesh kernel with a 64-vertex staging buffer), "big"
+// (<= 128: the same kernel with a 128-vertex buffer, 4 CTAs per SM instead of 5) and "huge" (the general kernel, which
+// reads such hulls from global memory); inside small and big the items are grouped in four sub-bins of 16 vertices, so
+// that the two pairs sharing a warp in lockstep are of similar size (their loops run to the larger trip count).
+// Which kernel family solves a pair therefore depends on the PAIR, not on the batch it came in or on a caller's hint.
+constexpr int R_BINS = 8;                      // 0-3 small (<=16, <=32, <=48, <=64), 4-7 big (<=80, .., <=128)
+constexpr int C_BIN = 16, C_CUR = 24, C_NSMALL = 32, C_NBIG = 33, C_HEAD_SMALL = 34, C_HEAD_BIG = 35;   // counter slots
+
+__device__ __forceinline__ int route_bin(const EpaArgs &a, long long item)
 {
-    int rc = 0, nl = 0;
-    EpaArgs b = a;
-    b.item_list = nullptr; b.item_count = nullptr;
-    if (small_first) {
-        a.item_list = nullptr; a.item_count = nullptr;
-        a.queue_head = counters + 1;
-        a.ovf_items = ovf1; a.ovf_count = counters + 4;
+    const int p = a.wl_pair[item];
+    const int ha = a.pair_a[p], hb = a.pair_b[p];
+    const int s = (int)(a.hull_off[ha + 1] - a.hull_off[ha]) + (int)(a.hull_off[hb + 1] - a.hull_off[hb]);
+    return s > 128 ? R_BINS : (s <= 0 ? 0 : (s - 1) >> 4);
+}
+
+__global__ void __launch_bounds__(256)
+route_count_kernel(EpaArgs a, unsigned long long *counters)
+{
+    const unsigned long long n = *a.wl_count;
+    const int lane = threadIdx.x & 31;
+    for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < n; i0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i = i0 + lane;
+        const int bin = i < n ? route_bin(a, (long long)i) : -1;
+        const unsigned peers = __match_any_sync(FULL, bin);
+        if (bin >= 0 && bin < R_BINS && lane == __ffs(peers) - 1) atomicAdd(counters + C_BIN + bin, (unsigned long long)__popc(peers));
+    }
+}
+
+// item numbers into small_list / big_list (grouped by sub-bin) and, for the huge class, straight into the general kernel's list
+__global__ void __launch_bounds__(256)
+route_fill_kernel(EpaArgs a, unsigned long long *counters, int32_t *small_list, int32_t *big_list, int32_t *huge_list, unsigned long long *huge_count)
+{
+    const unsigned long long n = *a.wl_count;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base[R_BINS];
+    {
+        unsigned long long s = 0;
+#pragma unroll
+        for (int b = 0; b < R_BINS; ++b) { if (b == 4) s = 0; base[b] = s; s += counters[C_BIN + b]; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        counters[C_NSMALL] = counters[C_BIN] + counters[C_BIN + 1] + counters[C_BIN + 2] + counters[C_BIN + 3];
+        counters[C_NBIG] = counters[C_BIN + 4] + counters[C_BIN + 5] + counters[C_BIN + 6] + counters[C_BIN + 7];
+    }
+    for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < n; i0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i = i0 + lane;
+        const int bin = i < n ? route_bin(a, (long long)i) : -1;
+        const unsigned peers = __match_any_sync(FULL, bin);
+        if (bin < 0) continue;
+        const int leader = __ffs(peers) - 1;
+        unsigned long long at = 0;
+        if (lane == leader) at = atomicAdd(bin < R_BINS ? counters + C_CUR + bin : huge_count, (unsigned long long)__popc(peers));
+        at = __shfl_sync(peers, at, leader) + __popc(peers & ((1u << lane) - 1u));
+        if (bin >= R_BINS) huge_list[at] = (int32_t)i;
+        else if (bin < 4) small_list[base[bin] + at] = (int32_t)i;
+        else big_list[base[bin] + at] = (int32_t)i;
+    }
+}
+
+// EPA stage.  route -> linked-mesh kernel over the small list -> linked-mesh kernel (128-vertex staging) over the big list
+// -> general kernel (64,128) over what they declined (capacity, a visible region that is not a disk) plus the huge class
+// -> general kernel (128,256) = the reference's hard bound (4 + 99 iterations) for what is left.
+// lists: route (2 x n_pairs: small | big), ovf1 (declined + huge), ovf2 (declined by the (64,128) pass).
+// counters: [4] ovf1 count, [3] (64,128) head, [8] ovf2 count, [9] (128,256) head, [16..35] routing (above)
+inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32_t *ovf2, int32_t *route, int64_t route_stride,
+                  unsigned long long *counters, int *launches)
+{
+    int rc = 0;
+    a.item_list = nullptr; a.item_count = nullptr;
+    const int rb = sm_count * 8;
+    route_count_kernel<<<rb, 256, 0, st>>>(a, counters);
+    route_fill_kernel<<<rb, 256, 0, st>>>(a, counters, route, route + route_stride, ovf1, counters + 4);
+    EpaArgs s = a;
+    s.item_list = route; s.item_count = counters + C_NSMALL; s.queue_head = counters + C_HEAD_SMALL;
+    s.ovf_items = ovf1; s.ovf_count = counters + 4;
 #ifndef EPA3_LP
 #define EPA3_LP 16
 #endif
-        rc = launch_one<EPA3_LP, 36, 68, 64>(a, sm_count, st);
-        if (rc) return rc;
-        ++nl;
-        b.item_list = ovf1; b.item_count = counters + 4;
-    }
+    rc = launch_one<EPA3_LP, 36, 68, 64>(s, sm_count, st);
+    if (rc) return rc;
+    EpaArgs g = s;
+    g.item_list = route + route_stride; g.item_count = counters + C_NBIG; g.queue_head = counters + C_HEAD_BIG;
+    rc = launch_one<EPA3_LP, 36, 68, 128>(g, sm_count, st);
+    if (rc) return rc;
+    EpaArgs b = a;
+    b.item_list = ovf1; b.item_count = counters + 4;
     b.queue_head = counters + 3;
     b.ovf_items = ovf2; b.ovf_count = counters + 8;
     rc = epa::launch_one<64, 128>(b, sm_count, st);
@@ -440,7 +505,7 @@ inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32
     c.queue_head = counters + 9;
     c.ovf_items = nullptr; c.ovf_count = nullptr;
     rc = epa::launch_one<128, 256>(c, sm_count, st);
-    if (launches) *launches = nl + 2;
+    if (launches) *launches = 6;
     return rc;
 }
 

@@ -36,6 +36,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 constexpr int hostb_max_chunks = 64;
+constexpr int N_COUNTERS = 64;           // device counter block of a context (work lists, queue heads, EPA routing)
 struct HostPipe;       // host_batch.inl: chunked copy/compute pipeline of the host-buffer entries
 struct MultiDev;       // host_batch.inl: one child context + worker thread per device
 
@@ -58,6 +59,7 @@ struct gjkepa_ctx {
     uint2 *d_seed_idx = nullptr;
     int32_t *d_ovf = nullptr; int64_t cap_ovf = 0;
     int32_t *d_ovf2 = nullptr; int64_t cap_ovf2 = 0;
+    int32_t *d_route = nullptr; int64_t cap_route = 0;        // EPA routing lists (small | big), 2 x n_pairs
     // workspace (device)
     gjk::Sphere *d_sphere = nullptr; int64_t cap_sphere = 0;
     int32_t *d_wl_pair = nullptr; double *d_wl_simplex = nullptr; int64_t cap_wl = 0;
@@ -165,9 +167,10 @@ int gjkepa_create(gjkepa_ctx **out, int32_t device)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return GJKEPA_ERR_CUDA;
     gjkepa_ctx *ctx = new gjkepa_ctx();
     ctx->device = device;
+    DeviceKeep keep_device_;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_counters, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_counters, N_COUNTERS * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&ctx->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
@@ -206,6 +209,7 @@ int gjkepa_destroy(gjkepa_ctx *ctx)
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_ovf) cudaFree(ctx->d_ovf);
     if (ctx->d_ovf2) cudaFree(ctx->d_ovf2);
+    if (ctx->d_route) cudaFree(ctx->d_route);
     if (ctx->d_seed_f64) cudaFree(ctx->d_seed_f64);
     if (ctx->d_seed_pair) cudaFree(ctx->d_seed_pair);
     if (ctx->d_seed_fl) cudaFree(ctx->d_seed_fl);
@@ -370,7 +374,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         if (point)      CU(cudaMemsetAsync(point, 0, (size_t)n_pairs * 3 * sizeof(double), st));
         if (depth)      CU(cudaMemsetAsync(depth, 0, (size_t)n_pairs * sizeof(double), st));
     }
-    CU(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, N_COUNTERS * sizeof(unsigned long long), st));
     if (n_pairs == 0) {
         if (n_contacts) CU(cudaMemsetAsync(n_contacts, 0, sizeof(int64_t), st));
         return GJKEPA_OK;
@@ -401,6 +405,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     const bool use_tile = ctx->lanes == 0 && !tiny;
     if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf, ctx->cap_ovf, n_pairs); if (rc) return rc; }
     if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf2, ctx->cap_ovf2, n_pairs); if (rc) return rc; }
+    if (mode >= GJKEPA_MODE_EPA && !tiny && !ctx->epa_general) { rc = ensure(ctx, ctx->d_route, ctx->cap_route, 2 * n_pairs); if (rc) return rc; }
 
     ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = false;
     const bool prof = ctx->profiling;
@@ -594,8 +599,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         int nl = 0;
         if (prof) CU(cudaEventRecord(ctx->ev[4], st));
         if (ctx->epa_general || tiny) rc = epa::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_counters, &nl);
-        else                  rc = epa3::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_ovf2, ctx->d_counters,
-                                                ctx->max_hull_hint > 0 && ctx->max_hull_hint <= 32, &nl);
+        else                  rc = epa3::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_ovf2, ctx->d_route, n_pairs, ctx->d_counters, &nl);
         if (rc) return fail(ctx, GJKEPA_ERR_CUDA, "epa launch", (cudaError_t)rc);
         DBG_SYNC("epa kernels");
         if (k4) { contact::launch(e, ctx->sm_count, st); ++nl; }

@@ -426,13 +426,14 @@ __device__ __forceinline__ int route_bin(const EpaArgs &a, long long item)
 }
 
 __global__ void __launch_bounds__(256)
-route_count_kernel(EpaArgs a, unsigned long long *counters)
+route_count_kernel(EpaArgs a, unsigned long long *counters, uint8_t *bins)
 {
     const unsigned long long n = *a.wl_count;
     const int lane = threadIdx.x & 31;
     for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < n; i0 += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long i = i0 + lane;
         const int bin = i < n ? route_bin(a, (long long)i) : -1;
+        if (bin >= 0) bins[i] = (uint8_t)bin;               // the filling pass reads this instead of chasing the indices again
         const unsigned peers = __match_any_sync(FULL, bin);
         if (bin >= 0 && bin < R_BINS && lane == __ffs(peers) - 1) atomicAdd(counters + C_BIN + bin, (unsigned long long)__popc(peers));
     }
@@ -440,7 +441,8 @@ route_count_kernel(EpaArgs a, unsigned long long *counters)
 
 // item numbers into small_list / big_list (grouped by sub-bin) and, for the huge class, straight into the general kernel's list
 __global__ void __launch_bounds__(256)
-route_fill_kernel(EpaArgs a, unsigned long long *counters, int32_t *small_list, int32_t *big_list, int32_t *huge_list, unsigned long long *huge_count)
+route_fill_kernel(EpaArgs a, unsigned long long *counters, const uint8_t *bins, int32_t *small_list, int32_t *big_list, int32_t *huge_list,
+                  unsigned long long *huge_count)
 {
     const unsigned long long n = *a.wl_count;
     const int lane = threadIdx.x & 31;
@@ -456,7 +458,7 @@ route_fill_kernel(EpaArgs a, unsigned long long *counters, int32_t *small_list, 
     }
     for (unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; i0 < n; i0 += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long i = i0 + lane;
-        const int bin = i < n ? route_bin(a, (long long)i) : -1;
+        const int bin = i < n ? (int)bins[i] : -1;
         const unsigned peers = __match_any_sync(FULL, bin);
         if (bin < 0) continue;
         const int leader = __ffs(peers) - 1;
@@ -472,28 +474,39 @@ route_fill_kernel(EpaArgs a, unsigned long long *counters, int32_t *small_list, 
 // EPA stage.  route -> linked-mesh kernel over the small list -> linked-mesh kernel (128-vertex staging) over the big list
 // -> general kernel (64,128) over what they declined (capacity, a visible region that is not a disk) plus the huge class
 // -> general kernel (128,256) = the reference's hard bound (4 + 99 iterations) for what is left.
-// lists: route (2 x n_pairs: small | big), ovf1 (declined + huge), ovf2 (declined by the (64,128) pass).
+// lists: route (2 x route_stride ints: small | big, then route_stride bytes of bin numbers), ovf1 (declined + huge), ovf2
+// (declined by the (64,128) pass).  all_small: the store's hulls are known to have at most 32 vertices, so every pair is
+// "small" and of one sub-bin width -- the same kernel the routing would pick, without the two routing passes.
 // counters: [4] ovf1 count, [3] (64,128) head, [8] ovf2 count, [9] (128,256) head, [16..35] routing (above)
 inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32_t *ovf2, int32_t *route, int64_t route_stride,
-                  unsigned long long *counters, int *launches)
+                  unsigned long long *counters, bool all_small, int *launches)
 {
-    int rc = 0;
+    int rc = 0, nl = 0;
     a.item_list = nullptr; a.item_count = nullptr;
-    const int rb = sm_count * 8;
-    route_count_kernel<<<rb, 256, 0, st>>>(a, counters);
-    route_fill_kernel<<<rb, 256, 0, st>>>(a, counters, route, route + route_stride, ovf1, counters + 4);
     EpaArgs s = a;
-    s.item_list = route; s.item_count = counters + C_NSMALL; s.queue_head = counters + C_HEAD_SMALL;
+    s.queue_head = counters + C_HEAD_SMALL;
     s.ovf_items = ovf1; s.ovf_count = counters + 4;
 #ifndef EPA3_LP
 #define EPA3_LP 16
 #endif
-    rc = launch_one<EPA3_LP, 36, 68, 64>(s, sm_count, st);
-    if (rc) return rc;
-    EpaArgs g = s;
-    g.item_list = route + route_stride; g.item_count = counters + C_NBIG; g.queue_head = counters + C_HEAD_BIG;
-    rc = launch_one<EPA3_LP, 36, 68, 128>(g, sm_count, st);
-    if (rc) return rc;
+    if (all_small) {
+        rc = launch_one<EPA3_LP, 36, 68, 64>(s, sm_count, st);
+        if (rc) return rc;
+        nl += 1;
+    } else {
+        const int rb = sm_count * 8;
+        uint8_t *bins = reinterpret_cast<uint8_t *>(route + 2 * route_stride);
+        route_count_kernel<<<rb, 256, 0, st>>>(a, counters, bins);
+        route_fill_kernel<<<rb, 256, 0, st>>>(a, counters, bins, route, route + route_stride, ovf1, counters + 4);
+        s.item_list = route; s.item_count = counters + C_NSMALL;
+        rc = launch_one<EPA3_LP, 36, 68, 64>(s, sm_count, st);
+        if (rc) return rc;
+        EpaArgs g = s;
+        g.item_list = route + route_stride; g.item_count = counters + C_NBIG; g.queue_head = counters + C_HEAD_BIG;
+        rc = launch_one<EPA3_LP, 36, 68, 128>(g, sm_count, st);
+        if (rc) return rc;
+        nl += 4;
+    }
     EpaArgs b = a;
     b.item_list = ovf1; b.item_count = counters + 4;
     b.queue_head = counters + 3;
@@ -505,7 +518,7 @@ inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32
     c.queue_head = counters + 9;
     c.ovf_items = nullptr; c.ovf_count = nullptr;
     rc = epa::launch_one<128, 256>(c, sm_count, st);
-    if (launches) *launches = 6;
+    if (launches) *launches = nl + 2;
     return rc;
 }
 

@@ -405,7 +405,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     const bool use_tile = ctx->lanes == 0 && !tiny;
     if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf, ctx->cap_ovf, n_pairs); if (rc) return rc; }
     if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf2, ctx->cap_ovf2, n_pairs); if (rc) return rc; }
-    if (mode >= GJKEPA_MODE_EPA && !tiny && !ctx->epa_general) { rc = ensure(ctx, ctx->d_route, ctx->cap_route, 2 * n_pairs); if (rc) return rc; }
+    if (mode >= GJKEPA_MODE_EPA && !tiny && !ctx->epa_general) { rc = ensure(ctx, ctx->d_route, ctx->cap_route, 2 * n_pairs + n_pairs / 4 + 4); if (rc) return rc; }
 
     ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = false;
     const bool prof = ctx->profiling;
@@ -599,7 +599,8 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         int nl = 0;
         if (prof) CU(cudaEventRecord(ctx->ev[4], st));
         if (ctx->epa_general || tiny) rc = epa::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_counters, &nl);
-        else                  rc = epa3::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_ovf2, ctx->d_route, n_pairs, ctx->d_counters, &nl);
+        else                  rc = epa3::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_ovf2, ctx->d_route, n_pairs, ctx->d_counters,
+                                                ctx->max_hull_hint > 0 && ctx->max_hull_hint <= 32, &nl);
         if (rc) return fail(ctx, GJKEPA_ERR_CUDA, "epa launch", (cudaError_t)rc);
         DBG_SYNC("epa kernels");
         if (k4) { contact::launch(e, ctx->sm_count, st); ++nl; }
@@ -1352,8 +1353,23 @@ int gjkepa_pair_f64(const int32_t *version, const double *tol_ff,
     unsigned spins = 0;
     for (;;) {
         if (lead) {
-            // run batches until this caller's own request is served, then pass the lead on
+            // run batches until this caller's own request is served, then pass the lead on.  Callers released by the previous
+            // batch come back within a microsecond or two: a short gathering window (until the queue stops growing, a few
+            // microseconds at most, against a round trip of ~50) keeps them in THIS batch instead of the one after
             {
+                size_t seen = 0;
+                for (int w = 0; w < 6; ++w) {
+                    size_t now;
+                    { std::lock_guard<std::mutex> lk(g_pair_mu); now = g_pair_q.size(); }
+                    if (w > 0 && now == seen) break;
+                    seen = now;
+                    const auto t0 = std::chrono::steady_clock::now();
+                    while (std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() < 1.5) {
+#if defined(__x86_64__) || defined(__i386__)
+                        __builtin_ia32_pause();
+#endif
+                    }
+                }
                 std::lock_guard<std::mutex> lk(g_pair_mu);
                 mine.swap(g_pair_q);
             }

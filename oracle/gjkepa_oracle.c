@@ -740,6 +740,23 @@ static void epa_solve(int version, double tol_ff, const hull_t *a, const hull_t 
     out->colli_type = collision_type(a, b, out->normal, tol_ff);                  /* F:343 */
 }
 
+/* The contact epilogue alone (F:326-343) on a GIVEN normal: what the reference computes once EPA has produced
+ * collision_normal_.  For tests that check a result's nearest points / collision point / type against the reference's
+ * own rules evaluated on that result's normal (ties between faces of equal depth may legitimately pick another normal). */
+void orc_epilogue(int32_t version, double tol_ff, const double *p1, int32_t n1, const double *p2, int32_t n2,
+                  const double normal_in[3], double nearest[6], double point[3], double normal_out[3], int32_t *colli_type)
+{
+    hull_t a = mk_hull(p1, n1), b = mk_hull(p2, n2);
+    double nrm[3] = { normal_in[0], normal_in[1], normal_in[2] };
+    point[0] = point[1] = point[2] = 0.0;
+    nearest_points(&a, &b, nrm, nearest);
+    if (version == 1) collision_point_01(&a, &b, nrm, point);
+    else if (version == 2) collision_point_02(&a, &b, nrm, point);
+    else if (version == 3) { double nnew[3]; collision_point_03(&a, &b, nrm, point, nnew); memcpy(nrm, nnew, sizeof nnew); }
+    memcpy(normal_out, nrm, sizeof nrm);
+    *colli_type = collision_type(&a, &b, nrm, tol_ff);
+}
+
 /* ------------------------------------------------------------------ L3 GJKEPA, F:39-239 */
 static inline int all_close3(const double a[3], const double b[3])
 { return fabs(a[0] - b[0]) < 1.0e-8 && fabs(a[1] - b[1]) < 1.0e-8 && fabs(a[2] - b[2]) < 1.0e-8; }

@@ -78,6 +78,8 @@ int orc_gjkepa_batch(int32_t version, double tol_ff,
                      uint32_t *status, int32_t *n_support);
 
 /* exposed pieces, for unit tests */
+void orc_epilogue(int32_t version, double tol_ff, const double *p1, int32_t n1, const double *p2, int32_t n2,
+                  const double normal_in[3], double nearest[6], double point[3], double normal_out[3], int32_t *colli_type);
 void orc_support(const double *p1, int32_t n1, const double *p2, int32_t n2,
                  const double dir[3], double res[3], int32_t *i1, int32_t *i2);
 int  orc_is_inside_pf(const double *v /*nnode*3 row-major*/, int32_t nnode, const double p[3]);

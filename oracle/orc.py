@@ -68,6 +68,8 @@ def lib():
         L.orc_quickhull.restype = C.c_int
         L.orc_dir_table.argtypes = [C.c_int32, dp]
         L.orc_dir_table.restype = None
+        L.orc_epilogue.argtypes = [C.c_int32, C.c_double, dp, C.c_int32, dp, C.c_int32, dp, dp, dp, dp, ip]
+        L.orc_epilogue.restype = None
         L.orc_max_threads.restype = C.c_int
         L.orc_sphere_pairs.argtypes = [dp, C.POINTER(C.c_int64), C.c_int64, C.c_int64, ip, ip]
         L.orc_sphere_pairs.restype = C.c_int64
@@ -120,6 +122,17 @@ def batch(verts, hull_off, pair_a, pair_b, version=1, tol_ff=1.0, mode=MODE_FULL
         out["n_support"].ctypes.data_as(C.POINTER(C.c_int32)))
     out["threads"] = used
     return out
+
+
+def epilogue(p1, p2, normal, version=1, tol_ff=1.0) -> dict:
+    """The reference's contact epilogue (F:326-343: nearest points, collision point by `version`, collision type)
+    evaluated on a GIVEN collision normal.  p1, p2: (n,3) vertex arrays."""
+    (b1, n1), (b2, n2) = _fblock(p1), _fblock(p2)
+    nrm = np.ascontiguousarray(normal, dtype=np.float64)
+    near, pt, nout = np.zeros(6), np.zeros(3), np.zeros(3)
+    ct = C.c_int32(0)
+    lib().orc_epilogue(int(version), float(tol_ff), _dp(b1), n1, _dp(b2), n2, _dp(nrm), _dp(near), _dp(pt), _dp(nout), C.byref(ct))
+    return {"nearest": near, "point": pt, "normal": nout, "colli_type": int(ct.value)}
 
 
 def quickhull(pts) -> np.ndarray:

@@ -30,7 +30,7 @@ SYMBOLS = [
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile the CUDA library for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + list(CSRC.glob("*.inl")) + \
+    srcs = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.inc")) + list(CSRC.glob("*.inl")) + list(CSRC.glob("*.h")) + \
         [_PKG.parent / "include" / "gjkepa.h"]
     stale = (not SO_PATH.exists()) or any(s.stat().st_mtime > SO_PATH.stat().st_mtime for s in srcs)
     if force or stale:

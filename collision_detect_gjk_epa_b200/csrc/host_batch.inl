@@ -16,10 +16,11 @@
 //   * contact_index / n_contacts / GJKEPA_MODE_COMPACT rows are built ON THE DEVICE (cub::DeviceSelect over the
 //     flags, then a row gather into per-shard accumulators): no host loop over pairs, and only contacts cross PCIe.
 #pragma once
+#include "host_plan.h"
 
 namespace hostb {
 
-constexpr int MAX_CHUNKS = 64;
+constexpr int MAX_CHUNKS = hostplan::MAX_CHUNKS;
 
 // pair list and hull offsets of a chunk made relative to the first hull / first vertex of the range it brought along
 __global__ void __launch_bounds__(256)
@@ -152,19 +153,7 @@ void pipe_free(gjkepa_ctx *ctx)
     ctx->pipe = nullptr;
 }
 
-struct Chunk { int64_t a, b; int64_t hlo, hhi; };      // pairs [a,b) of the shard (shard-relative), hulls [hlo,hhi] they name
-
-// lowest and highest hull number named by pairs [a,b)
-void hull_range(const int32_t *pa, const int32_t *pb, int64_t a, int64_t b, int64_t &lo, int64_t &hi)
-{
-    int32_t mn = 0x7fffffff, mx = -1;
-    for (int64_t i = a; i < b; ++i) {
-        const int32_t x = pa[i], y = pb[i];
-        mn = x < mn ? x : mn; mn = y < mn ? y : mn;
-        mx = x > mx ? x : mx; mx = y > mx ? y : mx;
-    }
-    lo = mn; hi = mx;
-}
+using hostplan::Chunk;
 
 // K0 once for a store that several chunks share (skipped under shortcut E1, which drops the sphere test)
 int spheres_for(gjkepa_ctx *ctx, const double *d_verts, const int64_t *d_off, int64_t n_hulls, gjk::Sphere *out, cudaStream_t st)
@@ -201,47 +190,19 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
     const size_t RS = r.f32 ? 4 : 8;                    // bytes per real in the caller's arrays
     const int32_t *pa = r.pair_a + P0, *pb = r.pair_b + P0;
 
-    // ---- chunk plan ----
-    // Chunks pay when the copies are a large part of the step: about one per 32 MB that crosses PCIe per pair-proportional
-    // array (hull bytes of a pair-private store, pair lists, per-pair results), at most 8, at least 64k pairs each.  A
-    // resident store with compact results stays in one piece (every chunk costs the kernels' ramp-up and tail once more).
-    int nchunk = ctx->host_chunks;
-    if (nchunk <= 0) {
-        const bool epa_ = r.mode >= GJKEPA_MODE_EPA, full_ = r.mode == GJKEPA_MODE_FULL;
-        double per_pair = 8.0 + (r.collision ? 1.0 : 0.0) + (r.status && !r.compact ? 4.0 : 0.0);
-        if (!r.compact) per_pair += (r.f32 ? 0.5 : 1.0) * ((r.depth && epa_ ? 8 : 0) + (r.normal && epa_ ? 24 : 0) + (r.point && full_ ? 24 : 0) + (r.nearest && full_ ? 48 : 0))
-                                    + (r.colli_type && full_ ? 4 : 0);
-        if ((r.src == SRC_HOST || r.src == SRC_HOST_F32) && r.n_hulls >= r.n_pairs / 2)
-            per_pair += (r.f32 ? 12.0 : 24.0) * (double)(r.hull_off[r.n_hulls] - r.hull_off[0]) / (double)r.n_pairs;
-        const double mb = per_pair * (double)np / (32.0 * 1024 * 1024);
-        nchunk = mb < 1.0 ? 1 : (mb > 8.0 ? 8 : (int)mb);
-        if ((int64_t)nchunk > np / 65536) nchunk = (int)(np / 65536 < 1 ? 1 : np / 65536);
-    }
-    if (nchunk > hostb::MAX_CHUNKS) nchunk = hostb::MAX_CHUNKS;
-    int64_t cp = (np + nchunk - 1) / nchunk;
-    cp = (cp + 1023) & ~(int64_t)1023;
-    nchunk = (int)((np + cp - 1) / cp);
-    std::vector<Chunk> ch((size_t)nchunk);
-    for (int k = 0; k < nchunk; ++k) { ch[k].a = (int64_t)k * cp; ch[k].b = ch[k].a + cp < np ? ch[k].a + cp : np; ch[k].hlo = 0; ch[k].hhi = -1; }
+    // ---- chunk plan (host_plan.h) ----
     const bool host_store = r.src == SRC_HOST || r.src == SRC_HOST_F32;
-    bool ranged = false;
-    int64_t Hlo = 0, Hhi = r.n_hulls - 1;               // hull range uploaded whole when !ranged
-    if (host_store) {
-        // a store much smaller than the pair list is shared by the pairs (cfg5): it goes up whole.  Otherwise look at what
-        // the chunks name: pair-private stores (pair i uses hulls near 2i) let every chunk bring its own range.
-        if (r.n_hulls >= r.n_pairs / 2) {
-            int64_t sum_v = 0;
-            Hlo = r.n_hulls; Hhi = -1;
-            for (int k = 0; k < nchunk; ++k) {
-                hull_range(pa, pb, ch[k].a, ch[k].b, ch[k].hlo, ch[k].hhi);
-                if (ch[k].hlo < 0 || ch[k].hhi >= r.n_hulls) return fail(ctx, GJKEPA_ERR_ARG, "pair list names a hull outside the store");
-                sum_v += r.hull_off[ch[k].hhi + 1] - r.hull_off[ch[k].hlo];
-                Hlo = ch[k].hlo < Hlo ? ch[k].hlo : Hlo; Hhi = ch[k].hhi > Hhi ? ch[k].hhi : Hhi;
-            }
-            const int64_t whole_v = r.hull_off[Hhi + 1] - r.hull_off[Hlo];
-            ranged = sum_v <= whole_v + whole_v / 4;
-        }
-    }
+    const bool private_store = host_store && r.n_hulls >= r.n_pairs / 2;     // else shared by the pairs (cfg5): it goes up whole
+    double per_pair = 8.0 + (r.collision ? 1.0 : 0.0) + (r.status && !r.compact ? 4.0 : 0.0);
+    if (!r.compact) per_pair += (r.f32 ? 0.5 : 1.0) * ((w_dep ? 8 : 0) + (w_nrm ? 24 : 0) + (w_pt ? 24 : 0) + (w_near ? 48 : 0)) + (w_type ? 4 : 0);
+    if (private_store) per_pair += (r.f32 ? 12.0 : 24.0) * (double)(r.hull_off[r.n_hulls] - r.hull_off[0]) / (double)r.n_pairs;
+    const hostplan::Plan plan = hostplan::plan_shard(np, ctx->host_chunks, per_pair, private_store, r.n_hulls, r.hull_off, pa, pb);
+    if (plan.bad_index) return fail(ctx, GJKEPA_ERR_ARG, "pair list names a hull outside the store");
+    const int nchunk = plan.nchunk;
+    const int64_t cp = plan.cp;
+    const std::vector<Chunk> &ch = plan.ch;
+    const bool ranged = plan.ranged;
+    const int64_t Hlo = plan.Hlo, Hhi = plan.Hhi;               // hull range uploaded whole when !ranged
     const int64_t whole_nh = Hhi - Hlo + 1;
     const int64_t whole_v0 = host_store ? r.hull_off[Hlo] : 0, whole_nv = host_store ? r.hull_off[Hhi + 1] - whole_v0 : 0;
 
@@ -554,13 +515,7 @@ void multi_free(gjkepa_ctx *ctx)
     ctx->multi = nullptr;
 }
 
-// shard s of n_pairs over n devices: contiguous, sizes differ by at most one
-void shard_range(int64_t n_pairs, int s, int n, int64_t &lo, int64_t &hi)
-{
-    const int64_t base = n_pairs / n, rem = n_pairs % n;
-    lo = s * base + (s < rem ? s : rem);
-    hi = lo + base + (s < rem ? 1 : 0);
-}
+using hostplan::shard_range;
 
 // one host-buffer batch on whatever the context stands for: its own device, or every device of a multi context
 int run_request(gjkepa_ctx *ctx, const Req &r)
@@ -584,9 +539,7 @@ int run_request(gjkepa_ctx *ctx, const Req &r)
         return GJKEPA_OK;
     }
     MultiDev &m = *ctx->multi;
-    // few pairs: one device (a shard below ~4k pairs does not fill a GPU)
-    int n = (int)m.kids.size();
-    if (r.n_pairs < (int64_t)n * 4096) n = (int)(r.n_pairs / 4096 < 1 ? 1 : r.n_pairs / 4096);
+    const int n = hostplan::shards_for(r.n_pairs, (int)m.kids.size());      // few pairs: fewer devices
     std::vector<int64_t> cnt((size_t)n, 0);
     for (int s = 0; s < n; ++s) {
         gjkepa_ctx *k = m.kids[(size_t)s];

@@ -12,4 +12,29 @@ for piece in "$@"; do case $piece in
            for t in 1 4 16 32 64; do build/pair_threads $t 20000 8; done 2>&1 | tee $out/${tag}_pair_threads.txt
            build/pair_threads 32 20000 32 2>&1 | tee -a $out/${tag}_pair_threads.txt ;;
   ab)      bash tools/ab_kernels.sh $AB_LIBS 2>&1 | tee $out/${tag}_ab.txt ;;
+  resident) python tools/resident_kernel_ms.py 2>&1 | tee $out/${tag}_resident_kernel_ms.txt ;;
+  ncu)     # launch list of the bench command, then full captures of the hot kernels (each only after the same command ran
+           # clean); the reports are summarised HERE (raw metrics, opcode mix, top source lines) because gpurun brings back
+           # at most 64 MiB, and only the small ones travel
+           python bench.py --steps 2 --warmup 1 --no-cpu --no-extra > $out/${tag}_plain_bench.log 2>&1 &&
+           ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-extra > $out/${tag}_ncu_launch.log 2>&1
+           export CHECK=0 LANES=0
+           summarise() {   # <rep> <out.txt> <kernel regex> ...
+               rep=$1; txt=$2; shift 2
+               python tools/ncu_summary.py $rep > $txt 2>&1
+               for k in "$@"; do echo "=== opcode mix: $k" >> $txt; python tools/ncu_opmix.py $rep "$k" 25 >> $txt 2>&1
+                                 echo "=== top source lines by stall samples: $k" >> $txt; python tools/ncu_source_top.py $rep "$k" 30 --by-samples >> $txt 2>&1; done
+           }
+           WL=cfg2 MODE=gjk python tests/tools/quick_time.py > $out/${tag}_plain_cfg2.log 2>&1 &&
+           WL=cfg2 MODE=gjk ncu --set full --clock-control none --import-source on -k regex:gjk_ -s 8 -c 2 -f -o $out/${tag}_prof_gjk_cfg2 python tests/tools/quick_time.py > $out/${tag}_ncu_a.log 2>&1
+           summarise $out/${tag}_prof_gjk_cfg2.ncu-rep $out/${tag}_prof_gjk_cfg2.txt gjk_init_kernel gjk_walk_kernel
+           WL=cfg4 MODE=epa python tests/tools/quick_time.py > $out/${tag}_plain_cfg4.log 2>&1 &&
+           WL=cfg4 MODE=epa ncu --set full --clock-control none --import-source on -k "regex:epa|route|gjk_" -s 20 -c 10 -f -o $out/${tag}_prof_cfg4 python tests/tools/quick_time.py > $out/${tag}_ncu_b.log 2>&1
+           summarise $out/${tag}_prof_cfg4.ncu-rep $out/${tag}_prof_cfg4.txt "epa3_kernel.*64EE" "epa3_kernel.*128EE" "epa_kernel"
+           rm -f $out/${tag}_prof_cfg4.ncu-rep
+           WL=cfg5 MODE=epa python tests/tools/quick_time.py > $out/${tag}_plain_cfg5.log 2>&1 &&
+           WL=cfg5 MODE=epa ncu --set full --clock-control none --import-source on -k "regex:epa3|gjk_|hull_prep" -s 12 -c 4 -f -o $out/${tag}_prof_cfg5 python tests/tools/quick_time.py > $out/${tag}_ncu_c.log 2>&1
+           summarise $out/${tag}_prof_cfg5.ncu-rep $out/${tag}_prof_cfg5.txt gjk_init_kernel gjk_walk_kernel epa3_kernel
+           rm -f $out/${tag}_prof_cfg5.ncu-rep
+           ls -la $out/${tag}_prof_*.ncu-rep ;;
 esac; done

@@ -918,7 +918,7 @@ static int store_upload_one(gjkepa_ctx *ctx, int64_t n_hulls, const double *vert
     CU(cudaMemcpyAsync(ctx->d_store_verts, verts + 3 * v0, (size_t)nv * 24, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->d_store_off, hull_off, (size_t)(n_hulls + 1) * 8, cudaMemcpyHostToDevice, st));
     if (v0 != 0) {
-        hostb::rebase_kernel<<<(unsigned)((n_hulls + 256) / 256 < 4096 ? (n_hulls + 256) / 256 : 4096), 256, 0, st>>>(nullptr, nullptr, 0, 0, ctx->d_store_off, n_hulls + 1, v0);
+        hostb::rebase_kernel<<<(unsigned)((n_hulls + 256) / 256 < 4096 ? (n_hulls + 256) / 256 : 4096), 256, 0, st>>>(nullptr, nullptr, 0, 0, 0, ctx->d_store_off, n_hulls + 1, v0, nullptr);
         ++ctx->launches;
     }
     if (int rc = spheres_for(ctx, ctx->d_store_verts, ctx->d_store_off, n_hulls, ctx->d_store_sphere, st)) return rc;

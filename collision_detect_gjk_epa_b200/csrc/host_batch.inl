@@ -22,17 +22,26 @@ namespace hostb {
 
 constexpr int MAX_CHUNKS = hostplan::MAX_CHUNKS;
 
-// pair list and hull offsets of a chunk made relative to the first hull / first vertex of the range it brought along
+// Pair list and hull offsets of a chunk made relative to the first hull / first vertex of the range it brought along, and
+// every hull number checked against the store the kernels will index (n_hulls entries): a number outside it is replaced by 0
+// -- so that no kernel reads out of bounds -- and reported through *bad, which fails the call with GJKEPA_ERR_ARG.
 __global__ void __launch_bounds__(256)
-rebase_kernel(int32_t *__restrict__ pa, int32_t *__restrict__ pb, int64_t n_pairs, int32_t hull_lo,
-              int64_t *__restrict__ off, int64_t n_off, int64_t vert_lo)
+rebase_kernel(int32_t *__restrict__ pa, int32_t *__restrict__ pb, int64_t n_pairs, int32_t hull_lo, int64_t n_hulls,
+              int64_t *__restrict__ off, int64_t n_off, int64_t vert_lo, int64_t *__restrict__ bad)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n = n_pairs > n_off ? n_pairs : n_off;
+    bool wrong = false;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        if (i < n_pairs) { pa[i] -= hull_lo; pb[i] -= hull_lo; }
+        if (i < n_pairs) {
+            int32_t a = pa[i] - hull_lo, b = pb[i] - hull_lo;
+            if (a < 0 || a >= n_hulls) { a = 0; wrong = true; }
+            if (b < 0 || b >= n_hulls) { b = 0; wrong = true; }
+            pa[i] = a; pb[i] = b;
+        }
         if (i < n_off) off[i] -= vert_lo;
     }
+    if (bad && __any_sync(0xffffffffu, wrong) && (threadIdx.x & 31) == 0) atomicAdd((unsigned long long *)bad, 1ull);
 }
 
 struct CompactArgs {
@@ -84,7 +93,7 @@ struct HostPipe {
     void *d_whole = nullptr; size_t cap_whole = 0;      // a host batch's hull store uploaded whole (shared stores)
     void *d_acc = nullptr;   size_t cap_acc = 0;        // compact accumulators of the shard
     void *d_sel_tmp = nullptr; size_t cap_sel_tmp = 0;
-    int64_t *d_cnt = nullptr;                           // [0..MAX_CHUNKS) contacts per chunk, [MAX_CHUNKS] rows accumulated
+    int64_t *d_cnt = nullptr;                           // [0..MAX_CHUNKS) contacts per chunk, [MAX_CHUNKS] rows accumulated, [MAX_CHUNKS+1] bad hull numbers
     int64_t *h_cnt = nullptr;                           // pinned mirror
     // accumulator layout of the last shard (run_shard -> finish_shard)
     size_t a_idx = 0, a_dep = 0, a_nrm = 0, a_pt = 0, a_near = 0, a_type = 0, a_st = 0;
@@ -122,8 +131,8 @@ int pipe_get(gjkepa_ctx *ctx, HostPipe **out)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_store, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_cnt, (hostb::MAX_CHUNKS + 1) * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaHostAlloc((void **)&p->h_cnt, (hostb::MAX_CHUNKS + 1) * sizeof(int64_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_cnt, (hostb::MAX_CHUNKS + 2) * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&p->h_cnt, (hostb::MAX_CHUNKS + 2) * sizeof(int64_t), cudaHostAllocDefault);
     ctx->pipe = p;
     if (e != cudaSuccess) { pipe_free(ctx); return fail(ctx, GJKEPA_ERR_CUDA, "host pipeline streams/events", e); }
     *out = p;
@@ -253,7 +262,7 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         const size_t a_total = p.a_st + al256(r.compact && w_st ? (size_t)np * 4 : 0);
         if (int rc = grow_bytes(ctx, p.d_acc, p.cap_acc, a_total, "cudaMalloc contact accumulators")) return rc;
     }
-    CU(cudaMemsetAsync(p.d_cnt, 0, (hostb::MAX_CHUNKS + 1) * sizeof(int64_t), sc));
+    CU(cudaMemsetAsync(p.d_cnt, 0, (hostb::MAX_CHUNKS + 2) * sizeof(int64_t), sc));
 
     // ---- the store the chunks run against ----
     const double *d_verts = nullptr; const int64_t *d_off = nullptr; int64_t nh_dev = 0;
@@ -302,7 +311,7 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         d_verts = (const double *)(b + o_v64); d_off = (const int64_t *)(b + o_off); nh_dev = whole_nh;
         if (Hlo != 0 || whole_v0 != 0) {            // offsets relative to the first vertex brought along (pair lists: per chunk)
             hostb::rebase_kernel<<<(unsigned)((whole_nh + 1 + 255) / 256 < 2048 ? (whole_nh + 1 + 255) / 256 : 2048), 256, 0, sc>>>(
-                nullptr, nullptr, 0, 0, (int64_t *)(b + o_off), whole_nh + 1, whole_v0);
+                nullptr, nullptr, 0, 0, 0, (int64_t *)(b + o_off), whole_nh + 1, whole_v0, nullptr);
             ++ctx->launches;
         }
         if (nchunk > 1 && !e1_skips_spheres) {
@@ -341,10 +350,10 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
             f32io::widen_kernel<<<(unsigned)(gb < gm ? gb : gm), 256, 0, sc>>>((const float *)(in + L.v32), (double *)(in + L.v64), ne);
             ++ctx->launches;
         }
-        if ((ranged && (hlo != 0 || v0 != 0)) || (!ranged && host_store && Hlo != 0)) {
+        {   // always: it is also the bounds check of the pair list (a wrong hull number must not become a wild device read)
             const int64_t w = ranged ? (n > nh + 1 ? n : nh + 1) : n; const int64_t gb = (w + 255) / 256;
             hostb::rebase_kernel<<<(unsigned)(gb < gm ? gb : gm), 256, 0, sc>>>((int32_t *)(in + L.pa), (int32_t *)(in + L.pb), n, (int32_t)hlo,
-                                                                                ranged ? (int64_t *)(in + L.off) : nullptr, ranged ? nh + 1 : 0, v0);
+                ranged ? nh : nh_dev, ranged ? (int64_t *)(in + L.off) : nullptr, ranged ? nh + 1 : 0, v0, p.d_cnt + hostb::MAX_CHUNKS + 1);
             ++ctx->launches;
         }
         double *r64 = (double *)(out + o_r64);
@@ -406,10 +415,11 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         }
         CU(cudaEventRecord(p.ev_out[s], so));
     }
-    if (want_cnt) CU(cudaMemcpyAsync(p.h_cnt, p.d_cnt, (hostb::MAX_CHUNKS + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, sc));
+    CU(cudaMemcpyAsync(p.h_cnt, p.d_cnt, (hostb::MAX_CHUNKS + 2) * sizeof(int64_t), cudaMemcpyDeviceToHost, sc));
     CU(cudaStreamSynchronize(sc));
     CU(cudaStreamSynchronize(so));
     CU(cudaStreamSynchronize(si));
+    if (p.h_cnt[hostb::MAX_CHUNKS + 1] != 0) return fail(ctx, GJKEPA_ERR_ARG, "pair list names a hull outside the store (results of those pairs are meaningless)");
     if (want_cnt) {
         int64_t c = 0;
         for (int k = 0; k < nchunk; ++k) c += p.h_cnt[k];

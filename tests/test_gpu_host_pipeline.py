@@ -208,6 +208,29 @@ def test_bad_shape_index_and_missing_store_are_argument_errors(engine, W):
     fresh.close()
 
 
+def test_hull_numbers_outside_the_store_fail_the_call_not_the_gpu(engine, multi, W):
+    """A wrong hull number in a pair list must come back as an argument error -- on the host for pair-private stores, from the
+    device-side bounds check for shared / resident stores -- never as a wild device read, and the context stays usable."""
+    from collision_detect_gjk_epa_b200.api import GjkEpaError
+    b = W.make_shared_store(3000, 40_000, n_vert=16, seed=4)
+    good = engine.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="epa")
+    for eng in (engine, multi):
+        eng.upload_store(b.verts, b.hull_off)
+        for bad_value in (3000, -1, 2 ** 31 - 1):
+            pa = b.pair_a.copy(); pa[12345] = bad_value
+            with pytest.raises(GjkEpaError):
+                eng.batch_resident(pa, b.pair_b, mode="epa")
+            with pytest.raises(GjkEpaError):
+                eng.batch_host(b.verts, b.hull_off, b.pair_a, pa, mode="gjk")
+        again = eng.batch_resident(b.pair_a, b.pair_b, mode="epa")
+        for k in ("collision", "status", "depth", "normal"):
+            assert np.array_equal(again[k], good[k]), k
+    p8 = W.make_pairs("box8", 30_000, 1.0, seed=6)             # pair-private store: the host-side range scan catches it
+    pa = p8.pair_a.copy(); pa[77] = 2 * 30_000
+    with pytest.raises(GjkEpaError):
+        engine.batch_host(p8.verts, p8.hull_off, pa, p8.pair_b, mode="gjk")
+
+
 def test_calls_leave_the_current_device_alone(engine, multi, W, n_gpus):
     import torch
     b = W.make_pairs("box8", 5000, 1.0, seed=2)

@@ -16,6 +16,7 @@ def main():
     elif wl == "cfg3": b = W.make_pairs("hull", n, 0.85, n_vert=32)
     elif wl == "hull16": b = W.make_pairs("hull", n, 0.85, n_vert=16)
     elif wl == "cfg5": b = W.make_shared_store(n // 10, n, n_vert=16)
+    elif wl == "cfg5big": b = W.make_shared_store(n // 2, n, n_vert=16)         # store larger than L2 (n = 4M: 768 MB)
     elif wl == "cfg4": b = W.make_mixed(n, 0.25)
     elif wl == "cfg4deep": b = W.make_pairs("hull", n, 0.05, n_vert=64)
     dev = torch.device("cuda:0")

@@ -12,6 +12,14 @@ for piece in "$@"; do case $piece in
            for t in 1 4 16 32 64; do build/pair_threads $t 20000 8; done 2>&1 | tee $out/${tag}_pair_threads.txt
            build/pair_threads 32 20000 32 2>&1 | tee -a $out/${tag}_pair_threads.txt ;;
   ab)      bash tools/ab_kernels.sh $AB_LIBS 2>&1 | tee $out/${tag}_ab.txt ;;
+  cfg5big) export CHECK=0 LANES=0
+           WL=cfg5 N=4000000 MODE=epa python tests/tools/quick_time.py 2>&1 | grep quick | tee $out/${tag}_cfg5big.txt
+           WL=cfg5big N=4000000 MODE=epa python tests/tools/quick_time.py 2>&1 | grep quick | tee -a $out/${tag}_cfg5big.txt
+           WL=cfg5big N=4000000 MODE=epa python tests/tools/quick_time.py > $out/${tag}_plain_cfg5big.log 2>&1 &&
+           WL=cfg5big N=4000000 MODE=epa ncu --set full --clock-control none --import-source on -k "regex:epa3|gjk_" -s 9 -c 3 -f -o $out/${tag}_prof_cfg5big python tests/tools/quick_time.py > $out/${tag}_ncu_d.log 2>&1
+           python tools/ncu_summary.py $out/${tag}_prof_cfg5big.ncu-rep > $out/${tag}_prof_cfg5big.txt 2>&1
+           for k in gjk_init_kernel gjk_walk_kernel epa3_kernel; do echo "=== top source lines by stall samples: $k" >> $out/${tag}_prof_cfg5big.txt; python tools/ncu_source_top.py $out/${tag}_prof_cfg5big.ncu-rep $k 14 --by-samples >> $out/${tag}_prof_cfg5big.txt 2>&1; done
+           rm -f $out/${tag}_prof_cfg5big.ncu-rep ;;
   resident) python tools/resident_kernel_ms.py 2>&1 | tee $out/${tag}_resident_kernel_ms.txt ;;
   ncu)     # launch list of the bench command, then full captures of the hot kernels (each only after the same command ran
            # clean); the reports are summarised HERE (raw metrics, opcode mix, top source lines) because gpurun brings back

@@ -459,7 +459,7 @@ epa_kernel(EpaArgs a)
             double *r = a.result + 12 * item;
             r[0] = nrm.x; r[1] = nrm.y; r[2] = nrm.z; r[3] = ok ? depth : -1.0;
         }
-        if (lane == 0 && a.status) a.status[p] |= st;
+        if (lane == 0 && a.status) atomicOr(a.status + p, st);
     }
 }
 

@@ -262,7 +262,7 @@ epa3_kernel(EpaArgs a)
                     if (a.normal) { double *o = a.normal + 3 * (int64_t)p; o[0] = nrm.x; o[1] = nrm.y; o[2] = nrm.z; }
                 }
                 if (a.result) { double *r = a.result + 12 * item; r[0] = nrm.x; r[1] = nrm.y; r[2] = nrm.z; r[3] = good ? depth : -1.0; }
-                if (a.status) a.status[p] |= s2;
+                if (a.status) atomicOr(a.status + p, s2);          // fire and forget: no round trip for the GJK half of the word
             }
         }
         busy = false;

@@ -256,23 +256,59 @@ gjk_init_kernel(TwoStageArgs ta)
     TileMeta cur = load_tile_meta(a, load_tile_ids(a, tile, n_tiles, lane));
     TileMeta nx = load_tile_meta(a, load_tile_ids(a, tile + n_warps, n_tiles, lane));
     TileIds nid = load_tile_ids(a, tile + 2 * n_warps, n_tiles, lane);
+    // issue the staging copies of a tile into this warp's columns (the previous tile must be done reading them)
+    auto stage = [&](const TileMeta &t) {
+        const int nA = t.nA(), nB = t.nB();
+        const int hA = (nA + 1) >> 1, hB = (nB + 1) >> 1;
+        const bool fits = t.valid && 3 * (hA + hB) <= ta.col_units;
+        const int tmaxA = __reduce_max_sync(FULL, fits ? 3 * hA : 0), tmaxB = __reduce_max_sync(FULL, fits ? 3 * hB : 0);
+        stage_own_hull(col, a.verts + 3 * t.oa, nA, hA, fits, tmaxA);
+        stage_own_hull(col + 3 * hA * T2_PITCH, a.verts + 3 * t.ob, nB, hB, fits, tmaxB);
+    };
+    stage(cur);
+    // Software pipeline over the warp's tiles: the staging of tile t+1 is issued as soon as tile t has been computed (the
+    // column is free then) and BEFORE tile t's results are written out -- the round trips of the queue atomics and the
+    // seed stores run while the copies are in flight (ncu, round 2: 11.7 % of this kernel's stall samples sat on the
+    // staging wait, 3.4 % on the atomics' round trip, with nothing between issue and wait).
     for (; tile < n_tiles; tile += n_warps) {
         const TileMeta m = cur;
         const int64_t p = tile * 32 + lane;
         const int nA = m.nA(), nB = m.nB();
         const int hA = (nA + 1) >> 1, hB = (nB + 1) >> 1;
         const bool fits = m.valid && 3 * (hA + hB) <= ta.col_units;
-        const int tmaxA = __reduce_max_sync(FULL, fits ? 3 * hA : 0), tmaxB = __reduce_max_sync(FULL, fits ? 3 * hB : 0);
-        stage_own_hull(col, a.verts + 3 * m.oa, nA, hA, fits, tmaxA);
-        stage_own_hull(col + 3 * hA * T2_PITCH, a.verts + 3 * m.ob, nB, hB, fits, tmaxB);
-        if (nx.valid) {                                     // next tile: hull blocks on their way to L2 while this one is worked
+        // shared store: this tile's envelope spheres are gathered at random from the table K0 filled (32 B each; with a
+        // store of millions of bodies a DRAM round trip) -- issued here so that they travel while the staging copies do
+        Sphere sa, sb;
+        sa.cx = sa.cy = sa.cz = sa.r = 0.0; sb = sa;
+        if (!FUSE && !a.early_out && fits) { sa = a.sphere[m.ha]; sb = a.sphere[m.hb]; }
+        if (nx.valid) {                                     // next tile: hull blocks (and spheres) on their way to L2 while this one is worked
             prefetch_l2_range(a.verts + 3 * nx.oa, 24 * nx.nA());
             prefetch_l2_range(a.verts + 3 * nx.ob, 24 * nx.nB());
+            if (!FUSE && !a.early_out) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.sphere + nx.ha));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.sphere + nx.hb));
+            }
         }
-        cur = nx;
-        nx = load_tile_meta(a, nid);                        // the following tiles' index chain overlaps this tile's work
-        nid = load_tile_ids(a, tile + 3 * n_warps, n_tiles, lane);
         cp_async_wait_all();
+        Walk w;
+        int e = -1;                                         // -1: nothing to report for this lane
+        if (fits) {
+            HullViewT2 A, B;
+            A.col = col; A.n = nA; A.h = hA;
+            B.col = col + 3 * hA * T2_PITCH; B.n = nB; B.h = hB;
+            if (FUSE && !a.early_out) { sa = hull_sphere_t2(A); sb = hull_sphere_t2(B); }     // E1 skips the sphere test (gjk_init)
+            e = gjk_init(g, A, B, sa, sb, w, a.early_out != 0);
+        }
+        __syncwarp();                                       // every lane is done with its column
+        cur = nx;
+        nx = load_tile_meta(a, nid);                        // the following tiles' index chain overlaps the write-out below
+        nid = load_tile_ids(a, tile + 3 * n_warps, n_tiles, lane);
+        stage(cur);                                         // next tile's copies in flight from here on (no-op past the last tile)
+        // ---- write-out of tile t ----
+        if (e > 0) {
+            if (a.collision) a.collision[p] = exit_is_collision(e) ? 1 : 0;
+            if (a.status) a.status[p] = pack_status_walk(e, w);
+        }
         {   // hulls too large for a column: leave to the sub-warp kernels (one atomic per warp)
             const unsigned big = __ballot_sync(FULL, m.valid && !fits);
             if (big) {
@@ -283,25 +319,6 @@ gjk_init_kernel(TwoStageArgs ta)
                 if (m.valid && !fits && a.ovf_status) { if (a.status) a.status[p] = a.ovf_status; if (a.collision) a.collision[p] = 0; }
             }
         }
-        Walk w;
-        int e = -1;                                         // -1: nothing to report for this lane
-        if (fits) {
-            HullViewT2 A, B;
-            A.col = col; A.n = nA; A.h = hA;
-            B.col = col + 3 * hA * T2_PITCH; B.n = nB; B.h = hB;
-            Sphere sa, sb;
-            sa.cx = sa.cy = sa.cz = sa.r = 0.0; sb = sa;
-            if (!a.early_out) {                              // E1 skips the sphere test (gjk_init)
-                if (FUSE) { sa = hull_sphere_t2(A); sb = hull_sphere_t2(B); }
-                else      { sa = a.sphere[m.ha];    sb = a.sphere[m.hb]; }
-            }
-            e = gjk_init(g, A, B, sa, sb, w, a.early_out != 0);
-            if (e > 0) {
-                if (a.collision) a.collision[p] = exit_is_collision(e) ? 1 : 0;
-                if (a.status) a.status[p] = pack_status_walk(e, w);
-            }
-        }
-        __syncwarp();
         push_contacts(a, e > 0 && exit_is_collision(e), p, w.S, lane);      // F:140: the origin on the first triangle
         const unsigned go = __ballot_sync(FULL, e == 0);
         if (go) {

@@ -17,6 +17,9 @@ def main():
     elif wl == "hull16": b = W.make_pairs("hull", n, 0.85, n_vert=16)
     elif wl == "cfg5": b = W.make_shared_store(n // 10, n, n_vert=16)
     elif wl == "cfg5big": b = W.make_shared_store(n // 2, n, n_vert=16)         # store larger than L2 (n = 4M: 768 MB)
+    elif wl == "cfg5bigsorted":                                                   # the same pairs in broad-phase order (grouped by first body)
+        b = W.make_shared_store(n // 2, n, n_vert=16)
+        o = np.argsort(b.pair_a, kind="stable"); b.pair_a = np.ascontiguousarray(b.pair_a[o]); b.pair_b = np.ascontiguousarray(b.pair_b[o])
     elif wl == "cfg4": b = W.make_mixed(n, 0.25)
     elif wl == "cfg4deep": b = W.make_pairs("hull", n, 0.05, n_vert=64)
     dev = torch.device("cuda:0")

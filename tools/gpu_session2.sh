@@ -6,6 +6,18 @@ for piece in "$@"; do case $piece in
   tests)   python -m pytest tests -x -q -m gpu > $out/${tag}_pytest_gpu.txt 2>&1; tail -3 $out/${tag}_pytest_gpu.txt ;;
   bench)   python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_cfg2.json 2> $out/${tag}_bench_cfg2.err; tail -3 $out/${tag}_bench_cfg2.err; wc -c $out/${tag}_bench_cfg2.json
            python bench.py --impl reference --steps 5 --warmup 1 > $out/${tag}_bench_ref.json 2>/dev/null ;;
+  benchw)  for w in cfg3 cfg4 cfg5; do python bench.py --workload $w --steps 20 --warmup 3 --no-extra > $out/${tag}_bench_$w.json 2> $out/${tag}_bench_$w.err; tail -2 $out/${tag}_bench_$w.err; done
+           python - <<PY
+import json
+for w in ["cfg2","cfg3","cfg4","cfg5"]:
+    try:
+        d=json.load(open("$out/${tag}_bench_%s.json" % w))
+        print(w, "ms/step %.3f" % d["ms_per_step"], "value %.3e" % d["value"], d["roofline"]["kernel_ms"], "frac %.3f" % d["roofline"]["frac"], "e2e %.3e" % d["e2e"]["value"], "resident %.3e" % d["e2e"]["resident_store"]["value"], "cpu %.3e" % d.get("cpu_baseline",{}).get("value",0))
+    except Exception as e: print(w, "ERR", e)
+PY
+           ;;
+  bench4)  python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 4 --steps 20 --warmup 5 > $out/${tag}_bench_4gpu.json 2> $out/${tag}_bench_4gpu.err; tail -3 $out/${tag}_bench_4gpu.err; wc -c $out/${tag}_bench_4gpu.json ;;
+  bench8)  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 20 --warmup 5 > $out/${tag}_bench_8gpu.json 2> $out/${tag}_bench_8gpu.err; tail -3 $out/${tag}_bench_8gpu.err; wc -c $out/${tag}_bench_8gpu.json ;;
   bench2)  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > $out/${tag}_bench_2gpu.json 2> $out/${tag}_bench_2gpu.err; tail -5 $out/${tag}_bench_2gpu.err; wc -c $out/${tag}_bench_2gpu.json ;;
   chunks)  python tools/chunk_sweep.py 2>&1 | tee $out/${tag}_chunk_sweep.txt ;;
   pairs)   g++ -O2 -fopenmp tools/pair_threads.cpp -Iinclude -Lcollision_detect_gjk_epa_b200 -lgjkepa_b200 -Wl,-rpath,$PWD/collision_detect_gjk_epa_b200 -o build/pair_threads

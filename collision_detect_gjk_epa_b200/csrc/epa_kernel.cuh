@@ -55,6 +55,11 @@ struct EpaArgs {
     int32_t *colli_type; double *nearest, *normal, *point, *depth; uint32_t *status;
     double *result;                 // optional: normal xyz, depth (-1: no result) in the first 4 doubles of the entry's 12-double
                                     // work-list slot (dead once the pair is retired); input of the contact kernel
+    // un-routed passes of the linked-mesh kernel over the whole work list (small batches, where two routing launches would cost
+    // more than they save): a pass works the items of ITS size class only -- take_gt < nA + nB, and with skip_large nothing
+    // beyond its staging buffer -- and leaves the others to the pass that owns them, so a pair meets the same kernel as in a
+    // routed batch
+    int32_t take_gt = -1; bool skip_large = false;
 };
 
 template <int VC, int FC>

@@ -284,7 +284,9 @@ epa3_kernel(EpaArgs a)
                     const gjk::HullView GA = gjk::hull_view(a.verts, a.hull_off, a.pair_a[p]);
                     const gjk::HullView GB = gjk::hull_view(a.verts, a.hull_off, a.pair_b[p]);
                     iters = 0; st = 0; nv = 4; nf = 4;
-                    if (GA.n + GB.n > HC) retire(false, true, 0.0, v3(0, 0, 0));          // hulls beyond the staging buffer
+                    const int tot = GA.n + GB.n;
+                    if (tot <= a.take_gt || (a.skip_large && tot > HC)) { /* another pass owns this pair */ }
+                    else if (tot > HC) retire(false, true, 0.0, v3(0, 0, 0));             // hulls beyond the staging buffer
                     else {
                         start = true;
                         A.n = GA.n; B.x = P.hx + GA.n; B.y = P.hy + GA.n; B.z = P.hz + GA.n; B.n = GB.n;
@@ -479,7 +481,7 @@ route_fill_kernel(EpaArgs a, unsigned long long *counters, const uint8_t *bins, 
 // "small" and of one sub-bin width -- the same kernel the routing would pick, without the two routing passes.
 // counters: [4] ovf1 count, [3] (64,128) head, [8] ovf2 count, [9] (128,256) head, [16..35] routing (above)
 inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32_t *ovf2, int32_t *route, int64_t route_stride,
-                  unsigned long long *counters, bool all_small, int *launches)
+                  unsigned long long *counters, bool all_small, bool unrouted, int *launches)
 {
     int rc = 0, nl = 0;
     a.item_list = nullptr; a.item_count = nullptr;
@@ -493,6 +495,16 @@ inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32
         rc = launch_one<EPA3_LP, 36, 68, 64>(s, sm_count, st);
         if (rc) return rc;
         nl += 1;
+    } else if (unrouted) {
+        // small batch: both size classes scan the whole work list and take their own items (EpaArgs::take_gt / skip_large)
+        s.skip_large = true;
+        rc = launch_one<EPA3_LP, 36, 68, 64>(s, sm_count, st);
+        if (rc) return rc;
+        EpaArgs g = s;
+        g.skip_large = false; g.take_gt = 64; g.queue_head = counters + C_HEAD_BIG;
+        rc = launch_one<EPA3_LP, 36, 68, 128>(g, sm_count, st);
+        if (rc) return rc;
+        nl += 2;
     } else {
         const int rb = sm_count * 8;
         uint8_t *bins = reinterpret_cast<uint8_t *>(route + 2 * route_stride);

@@ -256,7 +256,6 @@ template <> struct Lanes<1> {
     GJK_HD int bcast_i(int v, int) const { return v; }
     GJK_HD bool all(bool p) const { return p; }
     GJK_HD bool any(bool p) const { return p; }
-    GJK_HD bool any_group_running_with_me(bool p) const { return p; }      // see LanesW
     GJK_HD void argmax_first(double &, int &) const {}
     GJK_HD void argmin_first(double &, int &) const {}
 };
@@ -276,8 +275,6 @@ template <int L> struct Lanes {
     __device__ __forceinline__ int bcast_i(int v, int src) const { return __shfl_sync(mask, v, src, L); }
     __device__ __forceinline__ bool all(bool p) const { return (__ballot_sync(mask, p) & mask) == mask; }
     __device__ __forceinline__ bool any(bool p) const { return (__ballot_sync(mask, p) & mask) != 0u; }
-    __device__ __forceinline__ bool any_group_running_with_me(bool p) const { return p; }      // groups run on their own
-    __device__ __forceinline__ unsigned smask() const { return mask; }
     // larger value wins; equal values -> lower index (== first occurrence of the maximum)
     __device__ __forceinline__ void argmax_first(double &v, int &i) const
     {
@@ -313,9 +310,6 @@ template <int L> struct LanesW {
     __device__ __forceinline__ unsigned bits(bool p) const { return (__ballot_sync(0xffffffffu, p) >> shift) & ((1u << L) - 1u); }
     __device__ __forceinline__ bool all(bool p) const { return bits(p) == ((1u << L) - 1u); }
     __device__ __forceinline__ bool any(bool p) const { return bits(p) != 0u; }
-    // a loop whose trip count differs between the groups of the warp runs until the last group is done
-    __device__ __forceinline__ bool any_group_running_with_me(bool p) const { return __any_sync(0xffffffffu, p); }
-    __device__ __forceinline__ unsigned smask() const { return 0xffffffffu; }
     __device__ __forceinline__ void argmax_first(double &v, int &i) const
     {
 #pragma unroll
@@ -641,83 +635,6 @@ GJK_HD int gjk_init(const G &g, const HV &A, const HV &B, const Sphere &sa, cons
         if (fabs(dot3(w.S[3] - w.S[0], n)) < 1.0e-8) return EXIT_COPLANAR4;
     }
     return 0;
-}
-
-// gjk_init without early returns, for groups that run in LOCKSTEP inside one warp (LanesW: every collective takes the full
-// mask and must be reached by the whole warp).  Every stage is executed by every group; a group that has reached an exit
-// (`done`) goes through the remaining supports on whatever its registers hold and ignores the results.  Statement for
-// statement the arithmetic of gjk_init -- tests/test_host_sim.py runs both on the CPU and compares exit path, flags, simplex,
-// vertex numbers and the kept normal bit for bit.  `live` = false: a slot with no pair (results ignored, returns -1).
-template <class G, class HV>
-GJK_HD int gjk_init_lockstep(const G &g, const HV &A, const HV &B, const Sphere &sa, const Sphere &sb, Walk &w, bool live, bool early = false)
-{
-    const Vec3 O = v3(0.0, 0.0, 0.0);
-    w.S[0] = w.S[1] = w.S[2] = w.S[3] = O;
-    w.qk = O; w.mk = 0.0; w.D1 = O; w.k1 = 2; w.iters = 0; w.n_support = 0; w.fl = WF_FIRST | (early ? WF_EARLY : 0u);
-    w.ia = w.ib = 0u;
-    int e = live ? 0 : -1;
-    bool done = !live;
-    if (!done && !early && !sphere_hit(sa, sb)) { e = EXIT_SPHERE; done = true; }          // F:76-77
-    int it = 0;
-    bool looking = !done;
-    while (g.any_group_running_with_me(looking)) {                                          // F:86-106
-        if (looking) { ++it; if (it > 99) { e = EXIT_INIT_CAP; done = true; looking = false; } }
-        const Vec3 d = dir_table(looking ? it - 1 : 0);
-        Vec3 s0, s1; unsigned ia, ib;
-        support_both(g, A, B, d, s0, s1, ia, ib);
-        if (looking) {
-            w.S[0] = s0; w.S[1] = s1; w.ia = ia; w.ib = ib; w.n_support += 2;
-            if (early && (early_separated(s0, d) || early_separated(s1, neg(d)))) { e = EXIT_EARLY_OUT; done = true; looking = false; }
-            else if (!close3(s0, s1)) looking = false;
-        }
-    }
-    Vec3 dir;
-    {   // VEC_PL(O, S0, S1), F:1431-1438
-        Vec3 ab = w.S[1] - w.S[0], ac = O - w.S[0];
-        double dab = dot3(ac, ab);
-        dir = vec_pl_tail<MathFast>(w.S[0], ab, dab);
-        if (dir.x != dir.x) { dir = vec_pl_tail<MathCold>(w.S[0], ab, dab); if (!done) w.fl |= WF_COLD; }
-    }
-    {
-        int iA, iB;
-        const Vec3 s2 = support_i(g, A, B, dir, iA, iB);                                    // F:119
-        if (!done) {
-            w.S[2] = s2; w.ia |= (unsigned)iA << 16; w.ib |= (unsigned)iB << 16; ++w.n_support;
-            if (early && early_separated(s2, dir)) { e = EXIT_EARLY_OUT; done = true; }
-            else if (close3(s2, w.S[0]) || close3(s2, w.S[1])) { e = EXIT_DUP3; done = true; }   // F:123
-        }
-    }
-    Vec3 c3 = cross3(w.S[1] - w.S[0], w.S[2] - w.S[1]);                                     // F:132-135
-    double md3; Vec3 q3;
-    {
-        bool ok = true;
-        md3 = MathFast::nrm(c3, ok);
-        q3 = MathFast::dv(c3, md3, ok);
-        if (!ok) { if (!done) w.fl |= WF_COLD; bool dummy = true; md3 = MathCold::nrm(c3, dummy); q3 = (md3 == 0.0) ? O : MathCold::dv(c3, md3, dummy); }
-    }
-    dir = (md3 < 1.0e-12) ? O : q3;                                                         // UTZVEC
-    if (!done) { w.qk = dir; w.mk = md3; }
-    {
-        Vec3 vo = O - w.S[2];
-        double dt = dot3(vo, dir);
-        if (!done && fabs(dt) < 1.0e-8 && inside_pf3(w.S[0], w.S[1], w.S[2], O)) { e = EXIT_TRI_ORIGIN; done = true; }   // F:140
-        if (dt < 0.0) dir = neg(dir);                                                       // F:151
-    }
-    {
-        int iA, iB;
-        const Vec3 s3 = support_i(g, A, B, dir, iA, iB);                                    // F:154
-        if (!done) {
-            w.S[3] = s3; w.ia |= (unsigned)iA << 24; w.ib |= (unsigned)iB << 24; ++w.n_support;
-            if (early && early_separated(s3, dir)) { e = EXIT_EARLY_OUT; done = true; }
-        }
-    }
-    if (!done) {   // DIST_PF_SIGN(S3, (S0,S1,S2)), F:157, with UNINML's own zero rule (F:1392)
-        bool nz = fabs(c3.x) > 1.0e-12 || fabs(c3.y) > 1.0e-12 || fabs(c3.z) > 1.0e-12;
-        Vec3 n = nz ? q3 : O;
-        if (fabs(n.x) < 1.0e-12 && fabs(n.y) < 1.0e-12 && fabs(n.z) < 1.0e-12) { w.fl |= WF_STOP; e = EXIT_STOP; }
-        else if (fabs(dot3(w.S[3] - w.S[0], n)) < 1.0e-8) e = EXIT_COPLANAR4;
-    }
-    return e;
 }
 
 // One turn of the tetrahedron loop in two halves (see the header of this section).

@@ -153,44 +153,6 @@ __device__ __forceinline__ Sphere group_sphere(const G &g, const HV &h)
     return s;
 }
 
-// Both envelope spheres of a pair by a sub-warp of 4 lanes.  The six centroid sums (three axes of each hull) are sequential by
-// the reference's definition (F:1175: the order of the additions matters), i.e. six dependent chains of n additions; lane l runs
-// chains l and l + 4 interleaved (A.x A.y A.z B.x | B.y B.z - -), so the pair costs max(nA, nB)-ish dependent additions instead of
-// nA + nB with one lane idle.  Same operands in the same order as group_sphere: same bits.
-template <class G, class HV>
-__device__ __forceinline__ void group_spheres4(const G &g, const HV &A, const HV &B, Sphere &sa, Sphere &sb)
-{
-    static_assert(G::LANES == 4, "four lanes per pair");
-    const unsigned FULL = 0xffffffffu;
-    // chain 0 of this lane: lanes 0..2 -> A axis l, lane 3 -> B axis 0; chain 1: lanes 0,1 -> B axis 1 + l
-    const HV &h0 = (g.lane < 3) ? A : B;
-    const int ax0 = (g.lane < 3) ? g.lane : 0, ax1 = 1 + g.lane;
-    const int n0 = h0.n, n1 = (g.lane < 2) ? B.n : 0;
-    double s0 = 0.0, s1 = 0.0;
-    const int nmax = n0 > n1 ? n0 : n1;
-    for (int i = 0; i < nmax; ++i) {
-        if (i < n0) s0 = add(s0, h0.comp(ax0, i));
-        if (i < n1) s1 = add(s1, B.comp(ax1, i));
-    }
-    const double c0 = s0 / (double)n0, c1 = (n1 > 0) ? s1 / (double)n1 : 0.0;
-    sa.cx = __shfl_sync(FULL, c0, 0, 4); sa.cy = __shfl_sync(FULL, c0, 1, 4); sa.cz = __shfl_sync(FULL, c0, 2, 4);
-    sb.cx = __shfl_sync(FULL, c0, 3, 4); sb.cy = __shfl_sync(FULL, c1, 0, 4); sb.cz = __shfl_sync(FULL, c1, 1, 4);
-    const Vec3 ca = v3(sa.cx, sa.cy, sa.cz), cb = v3(sb.cx, sb.cy, sb.cz);
-    double ra = -1.0, rb = -1.0;
-    const int nab = A.n > B.n ? A.n : B.n;
-    for (int i = g.lane; i < nab; i += 4) {
-        if (i < A.n) { const Vec3 d = A.get(i) - ca; const double t = add(add(mul(d.x, d.x), mul(d.y, d.y)), mul(d.z, d.z)); if (t > ra) ra = t; }
-        if (i < B.n) { const Vec3 d = B.get(i) - cb; const double t = add(add(mul(d.x, d.x), mul(d.y, d.y)), mul(d.z, d.z)); if (t > rb) rb = t; }
-    }
-#pragma unroll
-    for (int o = 2; o > 0; o >>= 1) {
-        double t = __shfl_xor_sync(FULL, ra, o, 4); if (t > ra) ra = t;
-        t = __shfl_xor_sync(FULL, rb, o, 4); if (t > rb) rb = t;
-    }
-    sa.r = (A.n > 0) ? sqrt(ra) : -DBL_MAX;
-    sb.r = (B.n > 0) ? sqrt(rb) : -DBL_MAX;
-}
-
 __device__ __forceinline__ uint32_t pack_status(const GjkOut &o)
 {
     return (uint32_t)o.exit_path | ((uint32_t)o.iters << 8) | (o.stop_flag ? (1u << 25) : 0u)

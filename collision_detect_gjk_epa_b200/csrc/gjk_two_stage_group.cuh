@@ -139,125 +139,6 @@ gjk_init_group_kernel(TwoStageArgs ta, int slot_doubles)
     }
 }
 
-// ------------------------------------------------------------------ K1ig, lockstep form
-// The same stage with the 8 groups of a warp in LOCKSTEP (LanesW: constant full mask on every shuffle / vote, one
-// instruction stream for the 8 pairs; gjk_init_lockstep has no early return) -- what the walk kernel below already does.
-// The free-running form above ran 16.7 of 32 lanes per instruction on mixed hulls and 23.6 on uniform ones (ncu): groups
-// whose control flow differed were executed one after the other.  Both envelope spheres of a pair come from one pass
-// (group_spheres4: six interleaved centroid chains over four lanes instead of two times three with a lane idle).
-template <int L, bool FUSE>
-__global__ void __launch_bounds__(128)
-gjk_init_group_ls_kernel(TwoStageArgs ta, int slot_doubles)
-{
-    static_assert(L == 4, "four lanes per pair");
-    extern __shared__ __align__(16) double sm[];
-    __shared__ __align__(8) unsigned long long s_bar[4];
-    const BatchArgs &a = ta.b;
-    constexpr int PPW = 32 / L;                          // pairs per warp
-    const LanesW<L> g;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / L;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned leaders = 0x11111111u, before = (1u << (grp * L)) - 1u;
-    double *slot = sm + ((size_t)warp * PPW + grp) * slot_doubles;
-    unsigned long long *bar = &s_bar[warp];
-    if (lane == 0) mbar_init(bar, 1);
-    fence_proxy_async();
-    __syncwarp();
-    unsigned parity = 0;
-
-    const int64_t n_items = a.pair_list ? (int64_t)(*a.pair_list_count) : a.n_pairs;
-    const int64_t n_tiles = (n_items + PPW - 1) / PPW;
-    const int64_t n_warps = (int64_t)gridDim.x * 4;
-    for (int64_t tile = (int64_t)blockIdx.x * 4 + warp; tile < n_tiles; tile += n_warps) {
-        const int64_t it = tile * PPW + grp;
-        const bool valid = it < n_items;
-        int64_t p = 0; int ha = 0, hb = 0;
-        HullView GA, GB; GA.n = GB.n = 0; GA.x = GB.x = a.verts;
-        if (valid) {
-            p = a.pair_list ? (int64_t)a.pair_list[it] : it;
-            ha = __ldg(a.pair_a + p); hb = __ldg(a.pair_b + p);
-            GA = hull_view(a.verts, a.hull_off, ha); GB = hull_view(a.verts, a.hull_off, hb);
-        }
-        const bool fits = valid && 3 * (GA.n + GB.n) + 4 <= slot_doubles;
-        const unsigned bytesA = fits ? 24u * (unsigned)GA.n : 0u, bytesB = fits ? 24u * (unsigned)GB.n : 0u;
-        const bool bulkA = bytesA && ((bytesA & 15u) == 0) && ((reinterpret_cast<uintptr_t>(GA.x) & 15u) == 0);
-        const bool bulkB = bytesB && ((bytesB & 15u) == 0) && ((bytesA & 15u) == 0) && ((reinterpret_cast<uintptr_t>(GB.x) & 15u) == 0);
-        __syncwarp();                                     // the previous tile's slots are no longer read
-        fence_proxy_async();                              // order those generic reads before the async writes
-        unsigned tx = (g.lane == 0) ? ((bulkA ? bytesA : 0u) + (bulkB ? bytesB : 0u)) : 0u;
-        tx = __reduce_add_sync(FULL, tx);
-        if (lane == 0) mbar_expect_tx(bar, tx);
-        __syncwarp();
-        if (g.lane == 0) {
-            if (bulkA) bulk_g2s(slot, GA.x, bytesA, bar);
-            if (bulkB) bulk_g2s(slot + 3 * GA.n, GB.x, bytesB, bar);
-        }
-        if (bytesA && !bulkA) for (int e = g.lane; e < 3 * GA.n; e += L) cp_async8(slot + e, GA.x + e);
-        if (bytesB && !bulkB) for (int e = g.lane; e < 3 * GB.n; e += L) cp_async8(slot + 3 * GA.n + e, GB.x + e);
-        Sphere sa, sb;
-        sa.cx = sa.cy = sa.cz = sa.r = 0.0; sb = sa;
-        if (!FUSE && !a.early_out && fits) { sa = a.sphere[ha]; sb = a.sphere[hb]; }      // travels while the copies do
-        cp_async_wait_all();
-        {
-            unsigned spins = 0;
-            while (!mbar_try_wait(bar, parity)) { if (++spins > 64u) __nanosleep(32); }     // no poll limit (see above)
-            parity ^= 1u;
-        }
-        __syncwarp();
-        if (valid && !fits && g.lane == 0) {             // larger than a slot: plain sub-warp kernel
-            unsigned long long s2 = atomicAdd(a.ovf_count, 1ull);
-            a.ovf_list[s2] = (int32_t)p;
-            if (a.ovf_status) { if (a.status) a.status[p] = a.ovf_status; if (a.collision) a.collision[p] = 0; }
-        }
-        HullViewShared A, B;
-        const int nA = fits ? GA.n : 0, nB = fits ? GB.n : 0;       // a slot without a pair scans nothing
-        A.x = slot; A.y = slot + nA; A.z = slot + 2 * nA; A.n = nA;
-        B.x = slot + 3 * nA; B.y = B.x + nB; B.z = B.y + nB; B.n = nB;
-        if (FUSE && !a.early_out) group_spheres4(g, A, B, sa, sb);
-        Walk w;
-        const int e = gjk_init_lockstep(g, A, B, sa, sb, w, fits, a.early_out != 0);
-        const bool coll = e > 0 && exit_is_collision(e);
-        if (e > 0 && g.lane == 0) {
-            if (a.collision) a.collision[p] = coll ? 1 : 0;
-            if (a.status) a.status[p] = pack_status_walk(e, w);
-        }
-        {   // F:140 (the origin on the first triangle): EPA work list, one atomic per warp
-            const unsigned mcol = __ballot_sync(FULL, coll) & leaders;
-            if (mcol && a.wl_pair) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.wl_count, (unsigned long long)__popc(mcol));
-                base = __shfl_sync(FULL, base, 0);
-                if (coll) {
-                    const unsigned long long s3 = base + __popc(mcol & before);
-                    if (g.lane == 0) a.wl_pair[s3] = (int32_t)p;
-                    double *dst = a.wl_simplex + 12 * s3;
-#pragma unroll
-                    for (int r = g.lane; r < 4; r += L) {
-                        Vec3 row = pick4(w.S, r);
-                        dst[3 * r + 0] = row.x; dst[3 * r + 1] = row.y; dst[3 * r + 2] = row.z;
-                    }
-                }
-            }
-        }
-        const unsigned go = __ballot_sync(FULL, e == 0 && g.lane == 0);
-        if (go) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(ta.q.count, (unsigned long long)__popc(go));
-            base = __shfl_sync(FULL, base, 0);
-            if (e == 0 && g.lane == 0) {
-                const unsigned long long s = base + __popc(go & ((1u << lane) - 1u));
-                double *f = ta.q.f64 + s;
-                const int64_t cap = ta.q.cap;
-                f[0] = w.qk.x; f[cap] = w.qk.y; f[2 * cap] = w.qk.z; f[3 * cap] = w.mk;
-                ta.q.idx[s] = make_uint2(w.ia, w.ib);
-                ta.q.pair[s] = (int32_t)p;
-                ta.q.fln[s] = ((w.fl & WF_COLD) ? SEED_COLD : 0u) | ((unsigned)GA.n << 4) | ((unsigned)GB.n << 18);
-                ta.q.oa[s] = (int64_t)((GA.x - a.verts) / 3); ta.q.ob[s] = (int64_t)((GB.x - a.verts) / 3);
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------ K1wg
 template <int L>
 __global__ void __launch_bounds__(128, GJK_WALKG_MIN_CTAS)

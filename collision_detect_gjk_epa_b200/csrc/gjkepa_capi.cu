@@ -54,7 +54,6 @@ struct gjkepa_ctx {
     bool single_kernel = false;    // monolithic tile kernel instead of K1i + K1w
     bool epa_general = false;      // general EPA kernel only (no linked-mesh fast path)
     int early_out = 0;             // shortcut E1 (opt-in): see gjk_core.cuh
-    bool group_init_free = false;  // A/B: the free-running 4-lane init kernel instead of the lockstep one
     int tile_max_vertices = 16;    // largest hull the thread-per-pair kernels stage (larger ones: 4-lane kernels)
     double *d_seed_f64 = nullptr; int32_t *d_seed_pair = nullptr; uint32_t *d_seed_fl = nullptr; int64_t *d_seed_off = nullptr; int64_t cap_seed = 0;
     uint2 *d_seed_idx = nullptr;
@@ -301,7 +300,6 @@ int gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value)
         return GJKEPA_OK;
     }
     if (key == GJKEPA_TUNE_EARLY_OUT) { ctx->early_out = value != 0; return GJKEPA_OK; }
-    if (key == GJKEPA_TUNE_GROUP_INIT_FREE) { ctx->group_init_free = value != 0; return GJKEPA_OK; }
     return GJKEPA_ERR_ARG;
 }
 
@@ -407,7 +405,8 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     const bool use_tile = ctx->lanes == 0 && !tiny;
     if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf, ctx->cap_ovf, n_pairs); if (rc) return rc; }
     if (use_tile || mode >= GJKEPA_MODE_EPA) { rc = ensure(ctx, ctx->d_ovf2, ctx->cap_ovf2, n_pairs); if (rc) return rc; }
-    if (mode >= GJKEPA_MODE_EPA && !tiny && !ctx->epa_general) { rc = ensure(ctx, ctx->d_route, ctx->cap_route, 2 * n_pairs + n_pairs / 4 + 4); if (rc) return rc; }
+    const bool epa_unrouted = n_pairs <= 8192;       // two routing launches cost more than they save; the size classes filter in-kernel
+    if (mode >= GJKEPA_MODE_EPA && !epa_unrouted && !ctx->epa_general) { rc = ensure(ctx, ctx->d_route, ctx->cap_route, 2 * n_pairs + n_pairs / 4 + 4); if (rc) return rc; }
 
     ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = false;
     const bool prof = ctx->profiling;
@@ -540,17 +539,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                 tg.q.f64 = ctx->d_seed_f64; tg.q.pair = ctx->d_seed_pair; tg.q.fln = ctx->d_seed_fl; tg.q.idx = ctx->d_seed_idx;
                 tg.q.oa = ctx->d_seed_off; tg.q.ob = ctx->d_seed_off + ctx->cap_seed;
                 tg.q.count = ctx->d_counters + 10; tg.q.head = ctx->d_counters + 11; tg.q.cap = ctx->cap_seed;
-                if (!ctx->group_init_free) {
-                    if (fuse) {
-                        CU(cudaFuncSetAttribute(gjk::gjk_init_group_ls_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-                        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_group_ls_kernel<4, true>, 128, smem_c));
-                        gjk::gjk_init_group_ls_kernel<4, true><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(tg, slot_doubles);
-                    } else {
-                        CU(cudaFuncSetAttribute(gjk::gjk_init_group_ls_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-                        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_group_ls_kernel<4, false>, 128, smem_c));
-                        gjk::gjk_init_group_ls_kernel<4, false><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(tg, slot_doubles);
-                    }
-                } else if (fuse) {
+                if (fuse) {
                     CU(cudaFuncSetAttribute(gjk::gjk_init_group_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
                     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk::gjk_init_group_kernel<4, true>, 128, smem_c));
                     gjk::gjk_init_group_kernel<4, true><<<ctx->sm_count * (per_sm > 0 ? per_sm : 1), 128, smem_c, st>>>(tg, slot_doubles);
@@ -610,9 +599,10 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         if (k4) { e.full = false; e.result = ctx->d_wl_simplex; }
         int nl = 0;
         if (prof) CU(cudaEventRecord(ctx->ev[4], st));
-        if (ctx->epa_general || tiny) rc = epa::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_counters, &nl);
+        // every pair meets the EPA kernel its own hull sizes choose, whatever the batch: tiny batches included
+        if (ctx->epa_general) rc = epa::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_counters, &nl);
         else                  rc = epa3::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_ovf2, ctx->d_route, n_pairs, ctx->d_counters,
-                                                ctx->max_hull_hint > 0 && ctx->max_hull_hint <= 32, &nl);
+                                                ctx->max_hull_hint > 0 && ctx->max_hull_hint <= 32, epa_unrouted, &nl);
         if (rc) return fail(ctx, GJKEPA_ERR_CUDA, "epa launch", (cudaError_t)rc);
         DBG_SYNC("epa kernels");
         if (k4) { contact::launch(e, ctx->sm_count, st); ++nl; }

@@ -135,8 +135,6 @@ int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
 /* HOST_CHUNKS: a host-buffer batch runs as this many chunks per device through a copy-in / compute / copy-out pipeline
  * (0 = automatic: up to 8 chunks of at least 64k pairs; 1 = copy everything, compute, copy everything back). */
 #define GJKEPA_TUNE_HOST_CHUNKS    6
-/* GROUP_INIT_FREE: 1 = the 4-lane init kernel with free-running groups (round 1), 0 = its lockstep form (default); A/B only */
-#define GJKEPA_TUNE_GROUP_INIT_FREE 7
 #define GJKEPA_EXIT_EARLY_OUT      13
 int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);
 

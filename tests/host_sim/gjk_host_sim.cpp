@@ -61,32 +61,3 @@ extern "C" void hostsim_shadow_counts(long long *checks, long long *mismatch)
 {
     *checks = gjk::g_shadow_checks; *mismatch = gjk::g_shadow_mismatch;
 }
-
-// gjk_init (early returns) against gjk_init_lockstep (no early return: the form the lockstep 4-lane init kernel runs), L = 1, on
-// the CPU: exit path, flags, every simplex row, the vertex numbers behind the rows and the kept normal must be the same bits.
-// Returns the number of pairs that differ.
-extern "C" int64_t hostsim_init_forms_differ(const double *verts, const int64_t *hull_off, int64_t n_pairs,
-                                             const int32_t *pa, const int32_t *pb, int32_t early)
-{
-    using namespace gjk;
-    int64_t bad = 0;
-#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : bad)
-    for (int64_t i = 0; i < n_pairs; ++i) {
-        HullView A, B;
-        int64_t oa = hull_off[pa[i]], ob = hull_off[pb[i]];
-        A.n = (int)(hull_off[pa[i] + 1] - oa); A.x = verts + 3 * oa; A.y = A.x + A.n; A.z = A.y + A.n;
-        B.n = (int)(hull_off[pb[i] + 1] - ob); B.x = verts + 3 * ob; B.y = B.x + B.n; B.z = B.y + B.n;
-        Sphere sa = hull_sphere(A), sb = hull_sphere(B);
-        Lanes<1> g;
-        Walk w1, w2;
-        const int e1 = gjk_init(g, A, B, sa, sb, w1, early != 0);
-        const int e2 = gjk_init_lockstep(g, A, B, sa, sb, w2, true, early != 0);
-        bool same = e1 == e2 && w1.fl == w2.fl && w1.iters == w2.iters;
-        if (same && e1 == 0)
-            same = std::memcmp(w1.S, w2.S, sizeof w1.S) == 0 && w1.ia == w2.ia && w1.ib == w2.ib
-                && std::memcmp(&w1.qk, &w2.qk, sizeof w1.qk) == 0 && std::memcmp(&w1.mk, &w2.mk, sizeof w1.mk) == 0;
-        if (same && e1 == EXIT_TRI_ORIGIN) same = std::memcmp(w1.S, w2.S, sizeof w1.S) == 0;      // the rows the EPA work list gets
-        bad += same ? 0 : 1;
-    }
-    return bad;
-}

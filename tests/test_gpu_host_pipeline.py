@@ -255,3 +255,47 @@ def test_registered_pageable_arrays(engine, W):
     finally:
         assert L.gjkepa_host_unregister(C.c_void_p(b.verts.ctypes.data)) == 0
     assert np.array_equal(got["collision"], want["collision"])
+
+
+def test_random_sequence_of_host_batches(engine, multi, W):
+    """Buffers are grown on demand and reused from call to call (input / output slots, accumulators, seed queue, work lists,
+    routing lists): a random sequence of batch sizes, modes, chunk counts, output sets and contexts must keep giving the bits of
+    the plain call on a fresh engine."""
+    from collision_detect_gjk_epa_b200 import Engine
+    rng = np.random.default_rng(2024)
+    pools = [W.make_pairs("box8", 120_000, 1.0, seed=51), W.make_mixed(60_000, 0.3, seed=52), W.make_shared_store(5000, 90_000, n_vert=16, seed=53)]
+    fresh = Engine(0)
+    fresh.set_tuning(fresh.TUNE_HOST_CHUNKS, 1)
+    want = [fresh.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="full") for b in pools]
+    fresh.close()
+    for it in range(36):
+        k = int(rng.integers(0, 3)); b = pools[k]
+        n = int(rng.choice([1, 7, 255, 257, 4095, 4097, 30_000, b.n_pairs]))
+        lo = int(rng.integers(0, b.n_pairs - n + 1))
+        mode = str(rng.choice(["gjk", "epa", "full"]))
+        compact = bool(rng.integers(0, 2)) and mode != "gjk"
+        eng = multi if rng.integers(0, 2) else engine
+        eng.set_tuning(eng.TUNE_HOST_CHUNKS, int(rng.choice([0, 1, 2, 3, 7])))
+        if rng.integers(0, 2):
+            got = eng.batch_host(b.verts, b.hull_off, b.pair_a[lo:lo + n], b.pair_b[lo:lo + n], mode=mode, compact=compact, want_contacts=True)
+        else:
+            eng.upload_store(b.verts, b.hull_off)
+            got = eng.batch_resident(b.pair_a[lo:lo + n], b.pair_b[lo:lo + n], mode=mode, compact=compact, want_contacts=True)
+        ref = {key: v[lo:lo + n] for key, v in want[k].items()}
+        tag = (it, k, n, lo, mode, compact, eng is multi)
+        assert np.array_equal(got["collision"], ref["collision"]), tag
+        hits = np.nonzero(ref["collision"])[0]
+        assert got["n_contacts"] == len(hits) and np.array_equal(got["contact_index"][:len(hits)], hits.astype(np.int32)), tag
+        keys = {"gjk": [], "epa": ["depth", "normal"], "full": ["depth", "normal", "colli_type", "nearest", "point"]}[mode]
+        for key in keys + ["status"]:
+            if compact:
+                ok = np.array_equal(got[key][:len(hits)], ref[key][hits] if key != "status" or mode == "full" else got[key][:len(hits)])
+            else:
+                ok = np.array_equal(got[key], ref[key]) if key != "status" or mode == "full" else True
+            assert ok, (tag, key)
+        if mode != "full":          # the GJK half of the status word does not depend on the mode
+            st = got["status"][:len(hits)] if compact else got["status"]
+            rs = ref["status"][hits] if compact else ref["status"]
+            assert np.array_equal(st & 0xffff, rs & 0xffff), tag
+    for e in (engine, multi):
+        e.set_tuning(e.TUNE_HOST_CHUNKS, 0)

@@ -14,18 +14,16 @@ NORMAL_TOL = 1e-9
 
 def configure(eng, variant):
     """Kernel variants that must all give the same bits: 0 = automatic (init kernel + compacting walk kernel,
-    re-pack threshold 8; lockstep 4-lane init kernel for larger hulls; linked-mesh EPA kernels first), "r1"/"r32" = other
-    re-pack thresholds, "mono" = one GJK kernel per tile, "gen" = the general EPA kernel for every contact, "gfree" = the
-    free-running form of the 4-lane init kernel, 1/2/4 = sub-warp GJK kernels with that many lanes per pair."""
+    re-pack threshold 8; free-running 4-lane init kernel for larger hulls; linked-mesh EPA kernels first), "r1"/"r32" = other
+    re-pack thresholds, "mono" = one GJK kernel per tile, "gen" = the general EPA kernel for every contact, 1/2/4 = sub-warp GJK kernels with that many lanes per pair."""
     eng.set_tuning(eng.TUNE_SINGLE_KERNEL, 1 if variant == "mono" else 0)
     eng.set_tuning(eng.TUNE_EPA_GENERAL, 1 if variant == "gen" else 0)
     eng.set_tuning(eng.TUNE_WALK_REFILL, int(variant[1:]) if isinstance(variant, str) and variant[0] == "r" else 8)
     eng.set_tuning(eng.TUNE_EARLY_OUT, 0)                  # the parity build; test_early_out_* switches it on
-    eng.set_tuning(eng.TUNE_GROUP_INIT_FREE, 1 if variant == "gfree" else 0)
     eng.set_lanes(variant if isinstance(variant, int) else 0)
 
 
-ALL_VARIANTS = (0, "r1", "r32", "mono", "gen", "gfree", 1, 2, 4)
+ALL_VARIANTS = (0, "r1", "r32", "mono", "gen", 1, 2, 4)
 
 
 def check_against_oracle(orc, eng, b, mode, lanes=ALL_VARIANTS, version=1, tol_ff=1.0):

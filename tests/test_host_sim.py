@@ -142,20 +142,3 @@ def test_core_follows_the_oracle_on_nonfinite_and_extreme_inputs(orc, W, host_si
     assert np.array_equal(st & 0xffff, o["status"] & 0xffff)
     assert np.array_equal(ns, o["n_support"])
 
-
-@pytest.mark.parametrize("early", [0, 1])
-def test_lockstep_form_of_the_initial_tetrahedron_equals_the_plain_form(W, host_sim, early):
-    """gjk_init_lockstep (no early return; run by the lockstep 4-lane init kernel) against gjk_init on the CPU: exit path,
-    flags, simplex rows, vertex numbers and kept normal bit for bit, on every workload shape incl. touching cubes and
-    non-finite vertices."""
-    import ctypes as C
-    host_sim.hostsim_init_forms_differ.restype = C.c_int64
-    batches = [W.make_pairs("box8", 60000, 1.0, seed=1), W.make_pairs("hull", 40000, 0.85, seed=2, n_vert=32),
-               W.make_mixed(40000, 0.25, seed=3), W.make_shared_store(3000, 40000, n_vert=16, seed=4, spacing=2.5),
-               W.make_touching_mix(20000, seed=5), W.make_nonfinite("nan", 5000), W.make_nonfinite("inf", 5000),
-               W.make_pairs("hull", 20000, 3.0, seed=6, n_vert=5)]
-    i64p, i32p, dp = C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_double)
-    for b in batches:
-        bad = host_sim.hostsim_init_forms_differ(b.verts.ctypes.data_as(dp), b.hull_off.ctypes.data_as(i64p), b.n_pairs,
-                                                 b.pair_a.ctypes.data_as(i32p), b.pair_b.ctypes.data_as(i32p), early)
-        assert bad == 0, (b.name, bad)

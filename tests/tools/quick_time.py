@@ -32,7 +32,6 @@ def main():
     eng.set_tuning(eng.TUNE_EPA_GENERAL, int(os.environ.get('EPAGEN', '0')))
     eng.set_tuning(eng.TUNE_TILE_MAX_VERTICES, int(os.environ.get('TILEMAX', '16')))
     eng.set_tuning(eng.TUNE_EARLY_OUT, int(os.environ.get('E1', '0')))
-    if os.environ.get('GROUPFREE'): eng.set_tuning(7, int(os.environ['GROUPFREE']))
     chk = int(os.environ.get("CHECK", "20000"))
     ref = orc.batch(b.verts, b.hull_off, b.pair_a[:chk], b.pair_b[:chk], mode=orc.MODE_GJK) if chk else None
     e1 = int(os.environ.get('E1', '0'))

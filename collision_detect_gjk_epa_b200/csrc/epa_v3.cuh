@@ -481,7 +481,7 @@ route_fill_kernel(EpaArgs a, unsigned long long *counters, const uint8_t *bins, 
 // "small" and of one sub-bin width -- the same kernel the routing would pick, without the two routing passes.
 // counters: [4] ovf1 count, [3] (64,128) head, [8] ovf2 count, [9] (128,256) head, [16..35] routing (above)
 inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32_t *ovf2, int32_t *route, int64_t route_stride,
-                  unsigned long long *counters, bool all_small, bool unrouted, int *launches)
+                  unsigned long long *counters, bool all_small, bool unrouted, int classes, int *launches)
 {
     int rc = 0, nl = 0;
     a.item_list = nullptr; a.item_count = nullptr;
@@ -496,15 +496,21 @@ inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32
         if (rc) return rc;
         nl += 1;
     } else if (unrouted) {
-        // small batch: both size classes scan the whole work list and take their own items (EpaArgs::take_gt / skip_large)
-        s.skip_large = true;
-        rc = launch_one<EPA3_LP, 36, 68, 64>(s, sm_count, st);
-        if (rc) return rc;
-        EpaArgs g = s;
-        g.skip_large = false; g.take_gt = 64; g.queue_head = counters + C_HEAD_BIG;
-        rc = launch_one<EPA3_LP, 36, 68, 128>(g, sm_count, st);
-        if (rc) return rc;
-        nl += 2;
+        // small batch: both size classes scan the whole work list and take their own items (EpaArgs::take_gt / skip_large);
+        // `classes` (bit 0 small, bit 1 big or huge) lets a caller that knows its hull sizes skip a pass that would find nothing
+        if (classes & 1) {
+            s.skip_large = true;
+            rc = launch_one<EPA3_LP, 36, 68, 64>(s, sm_count, st);
+            if (rc) return rc;
+            ++nl;
+        }
+        if (classes & 2) {
+            EpaArgs g = s;
+            g.skip_large = false; g.take_gt = 64; g.queue_head = counters + C_HEAD_BIG;
+            rc = launch_one<EPA3_LP, 36, 68, 128>(g, sm_count, st);
+            if (rc) return rc;
+            ++nl;
+        }
     } else {
         const int rb = sm_count * 8;
         uint8_t *bins = reinterpret_cast<uint8_t *>(route + 2 * route_stride);
@@ -518,6 +524,17 @@ inline int launch(EpaArgs a, int sm_count, cudaStream_t st, int32_t *ovf1, int32
         rc = launch_one<EPA3_LP, 36, 68, 128>(g, sm_count, st);
         if (rc) return rc;
         nl += 4;
+    }
+    if (unrouted) {
+        // small batch: what the linked-mesh passes declined goes straight to the general kernel with the reference's hard
+        // bound (same code as the (64,128) form, larger arrays: same arithmetic), one launch less on the single-pair path
+        EpaArgs c = a;
+        c.item_list = ovf1; c.item_count = counters + 4;
+        c.queue_head = counters + 9;
+        c.ovf_items = nullptr; c.ovf_count = nullptr;
+        rc = epa::launch_one<128, 256>(c, sm_count, st);
+        if (launches) *launches = nl + 1;
+        return rc;
     }
     EpaArgs b = a;
     b.item_list = ovf1; b.item_count = counters + 4;

@@ -88,6 +88,7 @@ struct gjkepa_ctx {
     double *d_store_verts = nullptr; int64_t *d_store_off = nullptr; gjk::Sphere *d_store_sphere = nullptr;
     int64_t n_store_hulls = 0; int store_max_verts = 0;
     int host_chunks = 0;           // chunks per host batch (0 = automatic)
+    int epa_classes = 3;           // size classes present in the next small batch (bit 0: nA+nB <= 64, bit 1: larger), when the host knows
     double phase_ms[2] = {0.0, 0.0};        // wall clock of the last host batch: shards (copies + kernels), contact rows to the host
     double host_ms[3] = {0.0, 0.0, 0.0};    // profiling: K0/K1/K3 durations summed over the chunks of the last host batch
     bool host_ms_valid = false;
@@ -602,7 +603,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         // every pair meets the EPA kernel its own hull sizes choose, whatever the batch: tiny batches included
         if (ctx->epa_general) rc = epa::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_counters, &nl);
         else                  rc = epa3::launch(e, ctx->sm_count, st, ctx->d_ovf, ctx->d_ovf2, ctx->d_route, n_pairs, ctx->d_counters,
-                                                ctx->max_hull_hint > 0 && ctx->max_hull_hint <= 32, epa_unrouted, &nl);
+                                                ctx->max_hull_hint > 0 && ctx->max_hull_hint <= 32, epa_unrouted, ctx->epa_classes, &nl);
         if (rc) return fail(ctx, GJKEPA_ERR_CUDA, "epa launch", (cudaError_t)rc);
         DBG_SYNC("epa kernels");
         if (k4) { contact::launch(e, ctx->sm_count, st); ++nl; }
@@ -816,6 +817,14 @@ int gjkepa_batch_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
                 std::memcpy(h + i_pb, pair_b, (size_t)n_pairs * 4);
                 CU(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
                 CU(cudaMemsetAsync(d + q_col, 0, all_bytes - q_col, st));           // F:65-71 for every output at once
+                int classes = 0;                                                    // the hull sizes are in host memory: skip EPA passes that would find nothing
+                for (int64_t i = 0; i < n_pairs; ++i) {
+                    const int32_t a_ = pair_a[i], b_ = pair_b[i];
+                    if (a_ < 0 || a_ >= n_hulls || b_ < 0 || b_ >= n_hulls) return fail(ctx, GJKEPA_ERR_ARG, "pair list names a hull outside the store");
+                    classes |= ((hull_off[a_ + 1] - hull_off[a_]) + (hull_off[b_ + 1] - hull_off[b_]) <= 64) ? 1 : 2;
+                }
+                struct ClassesBack { gjkepa_ctx *c; ~ClassesBack() { c->epa_classes = 3; } } classes_back{ctx};
+                ctx->epa_classes = classes;
                 int rc = gjkepa_batch_device_f64(ctx, version, tol_ff, n_hulls, (const double *)(d + i_verts), (const int64_t *)(d + i_off),
                     n_pairs, (const int32_t *)(d + i_pa), (const int32_t *)(d + i_pb), mode | GJKEPA_MODE_NO_CLEAR_,
                     (uint8_t *)(d + q_col), colli_type ? (int32_t *)(d + q_type) : nullptr, nearest ? (double *)(d + q_near) : nullptr,

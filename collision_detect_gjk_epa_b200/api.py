@@ -83,6 +83,7 @@ class Engine:
         self._check(self._L.gjkepa_set_max_hull_vertices(self._h, int(n)), "gjkepa_set_max_hull_vertices")
 
     TUNE_WALK_REFILL, TUNE_SINGLE_KERNEL, TUNE_EPA_GENERAL, TUNE_TILE_MAX_VERTICES, TUNE_EARLY_OUT, TUNE_HOST_CHUNKS = 1, 2, 3, 4, 5, 6
+    TUNE_LOCALITY_SORT = 7
 
     def set_tuning(self, key: int, value: int):
         """GJKEPA_TUNE_* knobs of include/gjkepa.h (walk re-pack threshold, single-kernel A/B switch, host chunks)."""

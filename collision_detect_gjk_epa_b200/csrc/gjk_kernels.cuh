@@ -43,6 +43,9 @@ struct BatchArgs {
     uint32_t ovf_status;        // 0: a later pass works the overflow list; else no pass follows (the caller's bound on hull
                                 // sizes promised there would be none): the pair gets this status word and flag 0
     int32_t col_doubles;        // capacity of one shared-memory column
+    // optional visiting order of the thread-per-pair init kernel: entry q names pair (int32)order[q] (the low word of a sorted
+    // 64-bit key).  Results are written at the pair's own index, so the order only decides which hulls are in L2 together.
+    const unsigned long long *order;
     // EPA work list (null when not wanted)
     int32_t *wl_pair;
     double  *wl_simplex;        // 12 doubles per entry, row-major rows 0..3

@@ -215,23 +215,27 @@ constexpr int INIT_THREADS = GJK_INIT_THREADS;
 // ------------------------------------------------------------------ K1i
 // Index chain of one tile, loaded in two steps so that neither waits inside the tile that issues it: the
 // pair's hull numbers two tiles ahead, the hull offsets (which need the numbers) one tile ahead.
-struct TileIds  { int ha, hb; bool valid; };
+struct TileIds  { int ha, hb; int64_t p; bool valid; };
 struct TileMeta {                        // raw loads only: the vertex counts are formed when the tile is worked,
-    int ha, hb; long long oa, ea, ob, eb; bool valid;           // so nothing waits for these loads in the tile that issues them
+    int ha, hb; int64_t p; long long oa, ea, ob, eb; bool valid;   // so nothing waits for these loads in the tile that issues them
     __device__ __forceinline__ int nA() const { return (int)(ea - oa); }
     __device__ __forceinline__ int nB() const { return (int)(eb - ob); }
 };
 __device__ __forceinline__ TileIds load_tile_ids(const BatchArgs &a, int64_t tile, int64_t n_tiles, int lane)
 {
     TileIds m; m.ha = m.hb = 0;
-    const int64_t p = tile * 32 + lane;
-    m.valid = tile < n_tiles && p < a.n_pairs;
-    if (m.valid) { m.ha = __ldg(a.pair_a + p); m.hb = __ldg(a.pair_b + p); }
+    const int64_t q = tile * 32 + lane;
+    m.valid = tile < n_tiles && q < a.n_pairs;
+    m.p = q;
+    if (m.valid) {
+        if (a.order) m.p = (int64_t)(uint32_t)__ldg(a.order + q);      // visiting order (locality): one more link in a chain fetched two tiles ahead
+        m.ha = __ldg(a.pair_a + m.p); m.hb = __ldg(a.pair_b + m.p);
+    }
     return m;
 }
 __device__ __forceinline__ TileMeta load_tile_meta(const BatchArgs &a, const TileIds &id)
 {
-    TileMeta m; m.ha = id.ha; m.hb = id.hb; m.oa = m.ea = m.ob = m.eb = 0; m.valid = id.valid;
+    TileMeta m; m.ha = id.ha; m.hb = id.hb; m.p = id.p; m.oa = m.ea = m.ob = m.eb = 0; m.valid = id.valid;
     if (id.valid) {
         m.oa = __ldg(a.hull_off + id.ha); m.ea = __ldg(a.hull_off + id.ha + 1);
         m.ob = __ldg(a.hull_off + id.hb); m.eb = __ldg(a.hull_off + id.hb + 1);
@@ -272,7 +276,7 @@ gjk_init_kernel(TwoStageArgs ta)
     // staging wait, 3.4 % on the atomics' round trip, with nothing between issue and wait).
     for (; tile < n_tiles; tile += n_warps) {
         const TileMeta m = cur;
-        const int64_t p = tile * 32 + lane;
+        const int64_t p = m.p;
         const int nA = m.nA(), nB = m.nB();
         const int hA = (nA + 1) >> 1, hB = (nB + 1) >> 1;
         const bool fits = m.valid && 3 * (hA + hB) <= ta.col_units;

@@ -84,6 +84,8 @@ struct gjkepa_ctx {
     bool ev_valid[3] = {false, false, false};      // K0, K1, K3 recorded by the last batch
     // envelope spheres computed ahead of the batch (resident store, or once per host batch that is run in chunks): K0 is skipped
     const gjk::Sphere *ext_sphere = nullptr;
+    const unsigned long long *ext_order = nullptr;      // visiting order of the next batch's pairs (host_batch.inl: locality sort), or null
+    int locality_sort = 2;                               // 0 off, 1 always, 2 automatic (GJKEPA_TUNE_LOCALITY_SORT)
     // resident world-space hull store (gjkepa_store_upload)
     double *d_store_verts = nullptr; int64_t *d_store_off = nullptr; gjk::Sphere *d_store_sphere = nullptr;
     int64_t n_store_hulls = 0; int store_max_verts = 0;
@@ -301,6 +303,11 @@ int gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value)
         return GJKEPA_OK;
     }
     if (key == GJKEPA_TUNE_EARLY_OUT) { ctx->early_out = value != 0; return GJKEPA_OK; }
+    if (key == GJKEPA_TUNE_LOCALITY_SORT) {
+        if (value < 0 || value > 2) return GJKEPA_ERR_ARG;
+        ctx->locality_sort = value;
+        return GJKEPA_OK;
+    }
     return GJKEPA_ERR_ARG;
 }
 
@@ -428,6 +435,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     a.pair_list = nullptr; a.pair_list_count = nullptr;
     a.ovf_list = ctx->d_ovf; a.ovf_count = ctx->d_counters + 2; a.col_doubles = 0;
     a.early_out = ctx->early_out;
+    a.order = (use_tile && !ctx->single_kernel) ? ctx->ext_order : nullptr;
     a.ovf_status = (ctx->max_hull_hint != 0 && ctx->max_hull_hint <= ctx->tile_max_vertices) ? GJKEPA_ST_BAD_HINT : 0u;
     a.wl_pair = want_list ? ctx->d_wl_pair : nullptr;
     a.wl_simplex = want_list ? ctx->d_wl_simplex : nullptr;

@@ -135,6 +135,11 @@ int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
 /* HOST_CHUNKS: a host-buffer batch runs as this many chunks per device through a copy-in / compute / copy-out pipeline
  * (0 = automatic: up to 8 chunks of at least 64k pairs; 1 = copy everything, compute, copy everything back). */
 #define GJKEPA_TUNE_HOST_CHUNKS    6
+/* LOCALITY_SORT (host-buffer batches against a shared or resident store): visit the pairs in the order of their first hull, so
+ * that pairs sharing a hull find it in L2 -- what a broad phase's output order gives for free.  0 = never, 1 = always, 2 =
+ * automatic (default): when the store is larger than L2 and a sample of the pair list is not already ordered.  Results are
+ * written at the pair's own index and do not depend on this. */
+#define GJKEPA_TUNE_LOCALITY_SORT  7
 #define GJKEPA_EXIT_EARLY_OUT      13
 int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);
 

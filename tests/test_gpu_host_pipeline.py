@@ -299,3 +299,27 @@ def test_random_sequence_of_host_batches(engine, multi, W):
             assert np.array_equal(st & 0xffff, rs & 0xffff), tag
     for e in (engine, multi):
         e.set_tuning(e.TUNE_HOST_CHUNKS, 0)
+
+
+def test_locality_order_changes_no_result(engine, multi, W):
+    """GJKEPA_TUNE_LOCALITY_SORT: the init kernel visits the pairs of a shared / resident store in the order of their first hull
+    (what a broad phase's output order gives for free); every result is written at the pair's own index, so nothing may change."""
+    b = W.make_shared_store(20_000, 300_000, n_vert=16, seed=61)
+    for eng in (engine, multi):
+        eng.set_max_hull_vertices(0)
+        eng.upload_store(b.verts, b.hull_off)
+        eng.set_tuning(eng.TUNE_LOCALITY_SORT, 0)
+        want = eng.batch_resident(b.pair_a, b.pair_b, mode="full", want_contacts=True)
+        for chunks in (1, 3):
+            eng.set_tuning(eng.TUNE_HOST_CHUNKS, chunks)
+            eng.set_tuning(eng.TUNE_LOCALITY_SORT, 1)
+            same(eng.batch_resident(b.pair_a, b.pair_b, mode="full", want_contacts=True), want)
+            same(eng.batch_host(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="full"), want)
+        pb = W.make_posed(n_shapes=40, n_bodies=20_000, n_pairs=120_000, sigma=0.85, seed=62)
+        eng.upload_shapes(pb.shape_verts, pb.shape_off)
+        eng.set_tuning(eng.TUNE_LOCALITY_SORT, 0)
+        wp = eng.batch_posed(pb.body_shape, pb.pose, pb.pair_a, pb.pair_b, mode="epa")
+        eng.set_tuning(eng.TUNE_LOCALITY_SORT, 1)
+        same(eng.batch_posed(pb.body_shape, pb.pose, pb.pair_a, pb.pair_b, mode="epa"), wp)
+        eng.set_tuning(eng.TUNE_LOCALITY_SORT, 2)
+        eng.set_tuning(eng.TUNE_HOST_CHUNKS, 0)

@@ -1296,7 +1296,7 @@ struct PairJob {
 };
 std::mutex g_pair_mu;                          // guards the queue and the leader flag
 std::vector<PairJob *> g_pair_q;
-bool g_pair_leader = false;
+std::atomic<bool> g_pair_leader{false};       // written under the mutex; waiting callers peek at it without
 gjkepa_ctx *g_default_ctx = nullptr;           // created by the first leader, used by one leader at a time
 
 // one batch: jobs that share version_ and TOL_FF_ go through one gjkepa_batch_f64 call (tiny-batch path: one block in, one block out)
@@ -1366,7 +1366,7 @@ int gjkepa_pair_f64(const int32_t *version, const double *tol_ff,
     {
         std::lock_guard<std::mutex> lk(g_pair_mu);
         g_pair_q.push_back(&job);
-        if (!g_pair_leader) { g_pair_leader = true; lead = true; }
+        if (!g_pair_leader.load(std::memory_order_relaxed)) { g_pair_leader.store(true, std::memory_order_relaxed); lead = true; }
     }
     std::vector<PairJob *> mine;
     unsigned spins = 0;
@@ -1396,15 +1396,17 @@ int gjkepa_pair_f64(const int32_t *version, const double *tol_ff,
             mine.clear();
             if (job.done.load(std::memory_order_acquire)) {
                 std::lock_guard<std::mutex> lk(g_pair_mu);
-                g_pair_leader = false;              // a waiting caller picks the lead up (below)
+                g_pair_leader.store(false, std::memory_order_release);       // a waiting caller picks the lead up (below)
                 return job.rc;
             }
             continue;
         }
         if (job.done.load(std::memory_order_acquire)) return job.rc;
-        if ((++spins & 63u) == 0u) {
+        if ((++spins & 15u) == 0u && !g_pair_leader.load(std::memory_order_acquire)) {       // no leader: take the lead (lock only then)
             std::lock_guard<std::mutex> lk(g_pair_mu);
-            if (!g_pair_leader && !job.done.load(std::memory_order_acquire)) { g_pair_leader = true; lead = true; }
+            if (!g_pair_leader.load(std::memory_order_relaxed) && !job.done.load(std::memory_order_acquire)) {
+                g_pair_leader.store(true, std::memory_order_relaxed); lead = true;
+            }
         }
 #if defined(__x86_64__) || defined(__i386__)
         __builtin_ia32_pause();

@@ -663,6 +663,27 @@ def main():
             "colliding_fraction": float(f_out["collision"].mean()),
             "flag_mismatch_rate_vs_f64": float(np.mean(f_out["collision"] != flags64)),
             "api": "gjkepa_batch_f32 (C ABI, pinned host buffers; device widens to binary64, same kernels)"}
+        # ... and with binary32 ARITHMETIC as a filter in front (GJKEPA_TUNE_F32_FILTER): a float kernel proves pairs apart along
+        # the axes and the line of centroids; only the rest runs the binary64 kernels.  Flags must be the same.
+        flags_nofilter = f_out["collision"].copy()
+        eng.set_tuning(eng.TUNE_F32_FILTER, 1)
+        for _ in range(2):
+            eng.batch_host_f32(*f_in, mode="gjk", out=f_out)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(kf):
+            eng.batch_host_f32(*f_in, mode="gjk", out=f_out)
+        torch.cuda.synchronize()
+        dtff = (time.perf_counter() - t0) / kf
+        tot_f, filt_f = eng.f32_filter_stats()
+        eng.set_tuning(eng.TUNE_F32_FILTER, 0)
+        line["extra"]["e2e_f32_mode"]["with_f32_filter"] = {
+            "value": batch.n_pairs / dtff, "unit": UNIT, "ms_per_step": dtff * 1e3,
+            "fraction_filtered": filt_f / max(tot_f, 1), "fraction_of_separated_pairs_filtered": filt_f / max(1, int((flags_nofilter == 0).sum())),
+            "flag_mismatch_rate_vs_unfiltered": float(np.mean(f_out["collision"] != flags_nofilter)),
+            "flag_mismatch_rate_vs_f64": float(np.mean(f_out["collision"] != flags64)),
+            "note": "opt-in: binary32 separation test (3 axes + line of centroids, margin 1e-5 (1 + max|coordinate|)) before the binary64 "
+                    "kernels; the exit path of a filtered pair reads EARLY_OUT"}
         eng.set_max_hull_vertices(0)
     if not args.no_extra and args.workload == "cfg2" and world == 1:
         # upstream of the path: candidate pairs built on the device (gjkepa_broadphase_posed_f64) for 1M posed bodies

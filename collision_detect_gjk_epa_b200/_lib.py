@@ -24,7 +24,7 @@ SYMBOLS = [
     "gjkepa_create", "gjkepa_destroy", "gjkepa_set_stream", "gjkepa_use_own_stream", "gjkepa_last_error",
     "gjkepa_launch_count", "gjkepa_set_lanes", "gjkepa_set_max_hull_vertices", "gjkepa_set_tuning", "gjkepa_set_profiling", "gjkepa_kernel_ms", "gjkepa_pair_f64", "gjkepa_batch_f64",
     "gjkepa_batch_device_f64", "gjkepa_sync", "gjkepa_debug_fp64", "gjkepa_shapes_upload", "gjkepa_batch_posed_f64", "gjkepa_broadphase_f64", "gjkepa_broadphase_posed_f64", "gjkepa_batch_f32", "gjkepa_scene_posed_f64",
-    "gjkepa_create_multi", "gjkepa_device_count", "gjkepa_host_register", "gjkepa_host_unregister", "gjkepa_store_upload", "gjkepa_batch_resident_f64", "gjkepa_host_phase_ms",
+    "gjkepa_create_multi", "gjkepa_device_count", "gjkepa_host_register", "gjkepa_host_unregister", "gjkepa_store_upload", "gjkepa_batch_resident_f64", "gjkepa_host_phase_ms", "gjkepa_f32_filter_stats",
 ]
 
 
@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
     L.gjkepa_create_multi.restype = C.c_int
     L.gjkepa_device_count.argtypes = [vp]
     L.gjkepa_device_count.restype = C.c_int32
+    L.gjkepa_f32_filter_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.gjkepa_f32_filter_stats.restype = C.c_int
     L.gjkepa_host_phase_ms.argtypes = [vp, dp]
     L.gjkepa_host_phase_ms.restype = C.c_int
     L.gjkepa_host_register.argtypes = [vp, C.c_int64]

@@ -46,6 +46,7 @@ struct BatchArgs {
     // optional visiting order of the thread-per-pair init kernel: entry q names pair (int32)order[q] (the low word of a sorted
     // 64-bit key).  Results are written at the pair's own index, so the order only decides which hulls are in L2 together.
     const unsigned long long *order;
+    const unsigned long long *order_count;      // with `order`: how many entries it has (device; null = n_pairs)
     // EPA work list (null when not wanted)
     int32_t *wl_pair;
     double  *wl_simplex;        // 12 doubles per entry, row-major rows 0..3

@@ -221,11 +221,11 @@ struct TileMeta {                        // raw loads only: the vertex counts ar
     __device__ __forceinline__ int nA() const { return (int)(ea - oa); }
     __device__ __forceinline__ int nB() const { return (int)(eb - ob); }
 };
-__device__ __forceinline__ TileIds load_tile_ids(const BatchArgs &a, int64_t tile, int64_t n_tiles, int lane)
+__device__ __forceinline__ TileIds load_tile_ids(const BatchArgs &a, int64_t tile, int64_t n_tiles, int64_t n_items, int lane)
 {
     TileIds m; m.ha = m.hb = 0;
     const int64_t q = tile * 32 + lane;
-    m.valid = tile < n_tiles && q < a.n_pairs;
+    m.valid = tile < n_tiles && q < n_items;
     m.p = q;
     if (m.valid) {
         if (a.order) m.p = (int64_t)(uint32_t)__ldg(a.order + q);      // visiting order (locality): one more link in a chain fetched two tiles ahead
@@ -253,13 +253,14 @@ gjk_init_kernel(TwoStageArgs ta)
     const unsigned FULL = 0xffffffffu;
     char *col = sm2 + (size_t)warp * ta.col_units * T2_PITCH + lane * 16;
     const Lanes<1> g;
-    const int64_t n_tiles = (a.n_pairs + 31) / 32;
+    const int64_t n_items = (a.order && a.order_count) ? (int64_t)(*a.order_count) : a.n_pairs;      // a filtered batch visits its survivors
+    const int64_t n_tiles = (n_items + 31) / 32;
     const int64_t n_warps = (int64_t)gridDim.x * (INIT_THREADS / 32);
 
     int64_t tile = (int64_t)blockIdx.x * (INIT_THREADS / 32) + warp;
-    TileMeta cur = load_tile_meta(a, load_tile_ids(a, tile, n_tiles, lane));
-    TileMeta nx = load_tile_meta(a, load_tile_ids(a, tile + n_warps, n_tiles, lane));
-    TileIds nid = load_tile_ids(a, tile + 2 * n_warps, n_tiles, lane);
+    TileMeta cur = load_tile_meta(a, load_tile_ids(a, tile, n_tiles, n_items, lane));
+    TileMeta nx = load_tile_meta(a, load_tile_ids(a, tile + n_warps, n_tiles, n_items, lane));
+    TileIds nid = load_tile_ids(a, tile + 2 * n_warps, n_tiles, n_items, lane);
     // issue the staging copies of a tile into this warp's columns (the previous tile must be done reading them)
     auto stage = [&](const TileMeta &t) {
         const int nA = t.nA(), nB = t.nB();
@@ -306,7 +307,7 @@ gjk_init_kernel(TwoStageArgs ta)
         __syncwarp();                                       // every lane is done with its column
         cur = nx;
         nx = load_tile_meta(a, nid);                        // the following tiles' index chain overlaps the write-out below
-        nid = load_tile_ids(a, tile + 3 * n_warps, n_tiles, lane);
+        nid = load_tile_ids(a, tile + 3 * n_warps, n_tiles, n_items, lane);
         stage(cur);                                         // next tile's copies in flight from here on (no-op past the last tile)
         // ---- write-out of tile t ----
         if (e > 0) {

@@ -84,7 +84,10 @@ struct gjkepa_ctx {
     bool ev_valid[3] = {false, false, false};      // K0, K1, K3 recorded by the last batch
     // envelope spheres computed ahead of the batch (resident store, or once per host batch that is run in chunks): K0 is skipped
     const gjk::Sphere *ext_sphere = nullptr;
-    const unsigned long long *ext_order = nullptr;      // visiting order of the next batch's pairs (host_batch.inl: locality sort), or null
+    const unsigned long long *ext_order = nullptr;      // visiting order of the next batch's pairs (host_batch.inl: locality sort, fp32 filter), or null
+    const unsigned long long *ext_order_count = nullptr;   // its length on the device (fp32 filter: the survivors), or null = n_pairs
+    int f32_filter = 0;                                  // GJKEPA_TUNE_F32_FILTER
+    int64_t filter_stats[2] = {0, 0};                    // pairs seen / pairs proven apart by the fp32 filter in the last fp32 batch
     int locality_sort = 2;                               // 0 off, 1 always, 2 automatic (GJKEPA_TUNE_LOCALITY_SORT)
     // resident world-space hull store (gjkepa_store_upload)
     double *d_store_verts = nullptr; int64_t *d_store_off = nullptr; gjk::Sphere *d_store_sphere = nullptr;
@@ -303,6 +306,7 @@ int gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value)
         return GJKEPA_OK;
     }
     if (key == GJKEPA_TUNE_EARLY_OUT) { ctx->early_out = value != 0; return GJKEPA_OK; }
+    if (key == GJKEPA_TUNE_F32_FILTER) { ctx->f32_filter = value != 0; return GJKEPA_OK; }
     if (key == GJKEPA_TUNE_LOCALITY_SORT) {
         if (value < 0 || value > 2) return GJKEPA_ERR_ARG;
         ctx->locality_sort = value;
@@ -436,6 +440,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
     a.ovf_list = ctx->d_ovf; a.ovf_count = ctx->d_counters + 2; a.col_doubles = 0;
     a.early_out = ctx->early_out;
     a.order = (use_tile && !ctx->single_kernel) ? ctx->ext_order : nullptr;
+    a.order_count = a.order ? ctx->ext_order_count : nullptr;
     a.ovf_status = (ctx->max_hull_hint != 0 && ctx->max_hull_hint <= ctx->tile_max_vertices) ? GJKEPA_ST_BAD_HINT : 0u;
     a.wl_pair = want_list ? ctx->d_wl_pair : nullptr;
     a.wl_simplex = want_list ? ctx->d_wl_simplex : nullptr;
@@ -1019,6 +1024,15 @@ int gjkepa_host_phase_ms(const gjkepa_ctx *ctx, double *ms)
 {
     if (!ctx || !ms) return GJKEPA_ERR_ARG;
     ms[0] = ctx->phase_ms[0]; ms[1] = ctx->phase_ms[1];
+    return GJKEPA_OK;
+}
+
+int gjkepa_f32_filter_stats(const gjkepa_ctx *ctx, int64_t *out)
+{
+    if (!ctx || !out) return GJKEPA_ERR_ARG;
+    out[0] = out[1] = 0;
+    if (ctx->multi) { for (gjkepa_ctx *k : multi_kids(ctx)) { out[0] += k->filter_stats[0]; out[1] += k->filter_stats[1]; } }
+    else { out[0] = ctx->filter_stats[0]; out[1] = ctx->filter_stats[1]; }
     return GJKEPA_OK;
 }
 

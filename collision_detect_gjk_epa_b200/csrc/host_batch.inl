@@ -102,7 +102,8 @@ struct HostPipe {
     void *d_acc = nullptr;   size_t cap_acc = 0;        // compact accumulators of the shard
     void *d_sel_tmp = nullptr; size_t cap_sel_tmp = 0;
     void *d_order = nullptr; size_t cap_order = 0;      // locality order of a chunk: keys in | keys out | cub scratch
-    int64_t *d_cnt = nullptr;                           // [0..MAX_CHUNKS) contacts per chunk, [MAX_CHUNKS] rows accumulated, [MAX_CHUNKS+1] bad hull numbers
+    int64_t *d_cnt = nullptr;                           // [0..MAX_CHUNKS) contacts per chunk, [MAX_CHUNKS] rows accumulated, [MAX_CHUNKS+1] bad hull numbers,
+                                                        // [MAX_CHUNKS+2 ..) survivors of the fp32 filter per chunk
     int64_t *h_cnt = nullptr;                           // pinned mirror
     // accumulator layout of the last shard (run_shard -> finish_shard)
     size_t a_idx = 0, a_dep = 0, a_nrm = 0, a_pt = 0, a_near = 0, a_type = 0, a_st = 0;
@@ -140,8 +141,8 @@ int pipe_get(gjkepa_ctx *ctx, HostPipe **out)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_store, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_cnt, (hostb::MAX_CHUNKS + 2) * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaHostAlloc((void **)&p->h_cnt, (hostb::MAX_CHUNKS + 2) * sizeof(int64_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_cnt, (2 * hostb::MAX_CHUNKS + 2) * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&p->h_cnt, (2 * hostb::MAX_CHUNKS + 2) * sizeof(int64_t), cudaHostAllocDefault);
     ctx->pipe = p;
     if (e != cudaSuccess) { pipe_free(ctx); return fail(ctx, GJKEPA_ERR_CUDA, "host pipeline streams/events", e); }
     *out = p;
@@ -272,7 +273,7 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         const size_t a_total = p.a_st + al256(r.compact && w_st ? (size_t)np * 4 : 0);
         if (int rc = grow_bytes(ctx, p.d_acc, p.cap_acc, a_total, "cudaMalloc contact accumulators")) return rc;
     }
-    CU(cudaMemsetAsync(p.d_cnt, 0, (hostb::MAX_CHUNKS + 2) * sizeof(int64_t), sc));
+    CU(cudaMemsetAsync(p.d_cnt, 0, (2 * hostb::MAX_CHUNKS + 2) * sizeof(int64_t), sc));
 
     // ---- the store the chunks run against ----
     const double *d_verts = nullptr; const int64_t *d_off = nullptr; int64_t nh_dev = 0;
@@ -352,13 +353,18 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         const int64_t nh_all = r.src == SRC_RESIDENT ? ctx->n_store_hulls : (r.src == SRC_POSED ? r.n_bodies : whole_nh);
         while (order_bits < 32 && ((int64_t)1 << order_bits) < nh_all) ++order_bits;
     }
+    // fp32 entry with GJKEPA_TUNE_F32_FILTER: the binary32 separation filter runs first and the init kernel visits its survivors
+    const bool use_filter = r.src == SRC_HOST_F32 && ctx->f32_filter && ctx->lanes == 0 && !ctx->single_kernel && cp > 256;
+    if (use_filter) use_order = false;
+    ctx->filter_stats[0] = ctx->filter_stats[1] = 0;
     size_t order_tmp = 0, o_keys1 = 0, o_otmp = 0;
+    if (use_filter) { if (int rc = grow_bytes(ctx, p.d_order, p.cap_order, al256((size_t)cp * 8), "cudaMalloc survivor list")) return rc; }
     if (use_order) {
         CU(cub::DeviceRadixSort::SortKeys(nullptr, order_tmp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)cp, 32, 32 + order_bits, sc));
         o_keys1 = al256((size_t)cp * 8); o_otmp = 2 * o_keys1;
         if (int rc = grow_bytes(ctx, p.d_order, p.cap_order, o_otmp + al256(order_tmp), "cudaMalloc locality order")) return rc;
     }
-    struct OrderBack { gjkepa_ctx *c; ~OrderBack() { c->ext_order = nullptr; } } order_back{ctx};
+    struct OrderBack { gjkepa_ctx *c; ~OrderBack() { c->ext_order = nullptr; c->ext_order_count = nullptr; } } order_back{ctx};
 
     // ---- the pipeline ----
     double acc_ms[3] = {0.0, 0.0, 0.0};
@@ -403,6 +409,16 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
             CU(cub::DeviceRadixSort::SortKeys((char *)p.d_order + o_otmp, tb, k0, k1, (int)n, 32, 32 + order_bits, sc));
             ctx->launches += 2;
             ctx->ext_order = k1;
+        }
+        if (use_filter) {
+            unsigned long long *cnt = (unsigned long long *)(p.d_cnt + hostb::MAX_CHUNKS + 2 + k);      // zeroed with the counter block
+            const float *v32 = ranged ? (const float *)(in + L.v32) : (const float *)p.d_whole;
+            const int64_t gb = (n + 255) / 256;
+            f32io::separation_filter_kernel<<<(unsigned)(gb < gm ? gb : gm), 256, 0, sc>>>(v32, ranged ? (const int64_t *)(in + L.off) : d_off,
+                (const int32_t *)(in + L.pa), (const int32_t *)(in + L.pb), n, need_flags ? (uint8_t *)(out + o_col) : nullptr,
+                w_st ? (uint32_t *)(out + o_st) : nullptr, (uint32_t)GJKEPA_EXIT_EARLY_OUT, (unsigned long long *)p.d_order, cnt);
+            ++ctx->launches;
+            ctx->ext_order = (const unsigned long long *)p.d_order; ctx->ext_order_count = cnt;
         }
         double *r64 = (double *)(out + o_r64);
         ctx->ext_sphere = ranged ? nullptr : sph;
@@ -463,10 +479,15 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         }
         CU(cudaEventRecord(p.ev_out[s], so));
     }
-    CU(cudaMemcpyAsync(p.h_cnt, p.d_cnt, (hostb::MAX_CHUNKS + 2) * sizeof(int64_t), cudaMemcpyDeviceToHost, sc));
+    CU(cudaMemcpyAsync(p.h_cnt, p.d_cnt, (2 * hostb::MAX_CHUNKS + 2) * sizeof(int64_t), cudaMemcpyDeviceToHost, sc));
     CU(cudaStreamSynchronize(sc));
     CU(cudaStreamSynchronize(so));
     CU(cudaStreamSynchronize(si));
+    if (use_filter) {
+        int64_t kept = 0;
+        for (int k = 0; k < nchunk; ++k) kept += p.h_cnt[hostb::MAX_CHUNKS + 2 + k];
+        ctx->filter_stats[0] = np; ctx->filter_stats[1] = np - kept;
+    }
     if (p.h_cnt[hostb::MAX_CHUNKS + 1] != 0) return fail(ctx, GJKEPA_ERR_ARG, "pair list names a hull outside the store (results of those pairs are meaningless)");
     if (want_cnt) {
         int64_t c = 0;

@@ -87,6 +87,7 @@ int  gjkepa_create(gjkepa_ctx **ctx, int32_t device);
  * need a single-device context (GJKEPA_ERR_ARG). */
 int  gjkepa_create_multi(gjkepa_ctx **ctx, const int32_t *devices, int32_t n_devices);
 int32_t gjkepa_device_count(const gjkepa_ctx *ctx);
+int  gjkepa_f32_filter_stats(const gjkepa_ctx *ctx, int64_t *out /*[2]*/);
 /* wall clock (ms) of the last HOST-buffer batch call: ms[0] = the shards (copy-in, kernels, per-pair results copied out;
  * devices side by side), ms[1] = the contact rows / contact_index copied to the caller's arrays at their row offsets */
 int  gjkepa_host_phase_ms(const gjkepa_ctx *ctx, double *ms /*[2]*/);
@@ -140,6 +141,13 @@ int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
  * automatic (default): when the store is larger than L2 and a sample of the pair list is not already ordered.  Results are
  * written at the pair's own index and do not depend on this. */
 #define GJKEPA_TUNE_LOCALITY_SORT  7
+/* F32_FILTER (gjkepa_batch_f32 only; default 0): binary32 ARITHMETIC as a filter in front of the binary64 kernels.  A kernel
+ * in float tests every pair for separation along the coordinate axes and the line of centroids with a margin above its own
+ * rounding error; a pair it proves apart gets flag 0 and exit path GJKEPA_EXIT_EARLY_OUT without a binary64 walk, every other
+ * pair runs the binary64 kernels as before.  The filter can only answer "separated" (by more than 1e-6: the argument of
+ * EARLY_OUT above), so flags are unchanged -- tests/test_gpu_f32_mode.py: 0 mismatches -- while status differs for the filtered
+ * pairs.  gjkepa_f32_filter_stats: out[0] = pairs of the last fp32 batch, out[1] = pairs the filter proved apart. */
+#define GJKEPA_TUNE_F32_FILTER     8
 #define GJKEPA_EXIT_EARLY_OUT      13
 int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);
 

@@ -50,3 +50,67 @@ def test_f32_small_batch_empty_and_gjk_only(W, engine):
     b = W.make_pairs("box8", 5000, 1.0, seed=3)
     g = engine.batch_host_f32(b.verts, b.hull_off, b.pair_a, b.pair_b, mode="gjk")
     assert set(g) == {"collision", "status"} and 0.3 < g["collision"].mean() < 0.8
+
+
+@pytest.mark.parametrize("maker,kw,mode", [
+    ("make_pairs", dict(kind="box8", n_pairs=200_000, sigma=1.0, seed=71), "gjk"),
+    ("make_pairs", dict(kind="hull", n_pairs=60_000, sigma=0.85, seed=72, n_vert=32), "epa"),
+    ("make_mixed", dict(n_pairs=60_000, sigma=0.6, seed=73), "full"),
+    ("make_shared_store", dict(n_bodies=20_000, n_pairs=200_000, n_vert=16, seed=74), "epa"),
+    ("make_touching_mix", dict(n_pairs=40_000, seed=75), "epa"),
+])
+def test_f32_arithmetic_filter_changes_no_flag(W, engine, multi_f32, maker, kw, mode):
+    """GJKEPA_TUNE_F32_FILTER: binary32 arithmetic proves pairs apart before the binary64 kernels run.  It may only answer
+    'separated': every flag, and every result of a pair it lets through, must be what the call without it returns (mismatch
+    rate 0, not 'small'); the filtered pairs are exactly the ones whose exit path reads EARLY_OUT; touching and nearly touching
+    pairs (gaps of 0 and 1e-7..1e-9, far below its margin) are never filtered."""
+    b = getattr(W, maker)(**kw)
+    v32 = b.verts.astype(np.float32)
+    for eng in (engine, multi_f32):
+        eng.set_max_hull_vertices(0)
+        eng.set_tuning(eng.TUNE_F32_FILTER, 0)
+        want = eng.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode=mode, want_contacts=True)
+        for chunks in (1, 3):
+            eng.set_tuning(eng.TUNE_HOST_CHUNKS, chunks)
+            eng.set_tuning(eng.TUNE_F32_FILTER, 1)
+            got = eng.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode=mode, want_contacts=True)
+            total, filtered = eng.f32_filter_stats()
+            assert total == b.n_pairs
+            assert np.array_equal(got["collision"], want["collision"]), "the filter changed a flag"
+            assert got["n_contacts"] == want["n_contacts"]
+            nc = got["n_contacts"]
+            assert np.array_equal(got["contact_index"][:nc], want["contact_index"][:nc])
+            out_path = (got["status"] & 0xff) == 13
+            assert int(out_path.sum()) == filtered and not np.any(got["collision"][out_path])
+            assert np.array_equal(got["status"][~out_path], want["status"][~out_path])
+            for k in ("depth", "normal", "colli_type", "nearest", "point"):
+                if k in want:
+                    assert np.array_equal(got[k], want[k]), k
+            if maker == "make_touching_mix":
+                near = (want["collision"] == 0) & (((want["status"] & 0xff) == 9) | ((want["status"] & 0xff) == 8))
+                assert near.any()
+            else:
+                assert filtered > 0.05 * b.n_pairs, (filtered, b.n_pairs)
+        eng.set_tuning(eng.TUNE_F32_FILTER, 0)
+        eng.set_tuning(eng.TUNE_HOST_CHUNKS, 0)
+
+
+@pytest.fixture(scope="module")
+def multi_f32():
+    import torch
+    from collision_detect_gjk_epa_b200 import Engine
+    n = torch.cuda.device_count()
+    eng = Engine(devices=list(range(n)) if n > 1 else [0, 0])
+    yield eng
+    eng.close()
+
+
+def test_f32_filter_keeps_non_finite_pairs_for_the_binary64_kernels(W, engine):
+    b = W.make_nonfinite("nan", 20000)
+    v32 = b.verts.astype(np.float32)
+    engine.set_tuning(engine.TUNE_F32_FILTER, 0)
+    want = engine.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode="gjk")
+    engine.set_tuning(engine.TUNE_F32_FILTER, 1)
+    got = engine.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode="gjk")
+    engine.set_tuning(engine.TUNE_F32_FILTER, 0)
+    assert np.array_equal(got["collision"], want["collision"])

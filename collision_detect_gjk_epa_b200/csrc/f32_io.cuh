@@ -50,12 +50,13 @@ narrow_kernel(const double *__restrict__ src, float *__restrict__ dst, int64_t n
 // Error bound: a 3-term binary32 dot product of |d| <= 1 with coordinates <= M is off by at most 3.5e-7 M, the difference of two
 // of them by 1e-6 M at most; the margin is 1e-5 (1 + M), so a pair that passes has a true gap above 1e-6.
 // Survivors are appended to the visiting order of the init kernel (low word of a 64-bit entry = pair number), one atomic per warp.
-// Eight lanes per pair (lane l takes vertices l, l + 8, ...; consecutive lanes read consecutive floats, so a warp's load touches
-// 4 x 32 B instead of 32 sectors -- one thread per pair was bound by L1 sector throughput: 0.18-0.6 ms per 1M pairs, more than the
-// filter saved), butterflies over the 8 lanes for the sums, boxes and projections.
-__device__ __forceinline__ float bfly8_add(float v) { for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 8); return v; }
-__device__ __forceinline__ float bfly8_min(float v) { for (int o = 4; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o, 8)); return v; }
-__device__ __forceinline__ float bfly8_max(float v) { for (int o = 4; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, 8)); return v; }
+// FLP lanes per pair (lane l takes vertices l, l + FLP, ...; consecutive lanes read consecutive floats, so a warp's load touches
+// 8 sectors instead of 32 -- one thread per pair was bound by L1 sector throughput: 0.18-0.6 ms per 1M pairs, more than the filter
+// saved; eight lanes per pair by shuffle throughput: 0.16-0.22 ms), butterflies over the group for the sums, boxes and projections.
+constexpr int FLP = 4;          // lanes per pair: 8 pairs per warp, two butterfly steps per reduction
+__device__ __forceinline__ float bfly8_add(float v) { for (int o = FLP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, FLP); return v; }
+__device__ __forceinline__ float bfly8_min(float v) { for (int o = FLP / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o, FLP)); return v; }
+__device__ __forceinline__ float bfly8_max(float v) { for (int o = FLP / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, FLP)); return v; }
 
 __global__ void __launch_bounds__(256)
 separation_filter_kernel(const float *__restrict__ v, const int64_t *__restrict__ hull_off, const int32_t *__restrict__ pair_a,
@@ -63,15 +64,21 @@ separation_filter_kernel(const float *__restrict__ v, const int64_t *__restrict_
                          uint32_t status_filtered, unsigned long long *__restrict__ order, unsigned long long *__restrict__ order_count)
 {
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, l = lane & 7, grp = lane >> 3;
+    constexpr int PPW = 32 / FLP;
+    const int lane = threadIdx.x & 31, l = lane & (FLP - 1), grp = lane / FLP;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t q = warp0 * 4; q < n_pairs; q += n_warps * 4) {
+    // the hull numbers of the NEXT round are loaded while this one is worked (the index chain pair -> hull -> offsets is three
+    // dependent round trips)
+    int nha = 0, nhb = 0;
+    { const int64_t p1 = warp0 * PPW + grp; if (p1 < n_pairs) { nha = pair_a[p1]; nhb = pair_b[p1]; } }
+    for (int64_t q = warp0 * PPW; q < n_pairs; q += n_warps * PPW) {
         const int64_t p = q + grp;
         const bool valid = p < n_pairs;
         int na = 0, nb = 0;
         const float *ax = v, *bx = v;
+        const int ha = nha, hb = nhb;
+        { const int64_t p1 = p + n_warps * PPW; if (p1 < n_pairs) { nha = pair_a[p1]; nhb = pair_b[p1]; } }
         if (valid) {
-            const int ha = pair_a[p], hb = pair_b[p];
             const int64_t oa = hull_off[ha], ob = hull_off[hb];
             na = (int)(hull_off[ha + 1] - oa); nb = (int)(hull_off[hb + 1] - ob);
             ax = v + 3 * oa; bx = v + 3 * ob;
@@ -80,12 +87,12 @@ separation_filter_kernel(const float *__restrict__ v, const int64_t *__restrict_
         float sa[3] = {0.f, 0.f, 0.f}, sb[3] = {0.f, 0.f, 0.f}, alo[3], ahi[3], blo[3], bhi[3], M = 0.f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) { alo[k] = blo[k] = 3.0e38f; ahi[k] = bhi[k] = -3.0e38f; }
-        for (int i = l; i < na; i += 8) {
+        for (int i = l; i < na; i += FLP) {
             const float c[3] = {ax[i], ay[i], az[i]};
 #pragma unroll
             for (int k = 0; k < 3; ++k) { sa[k] += c[k]; alo[k] = fminf(alo[k], c[k]); ahi[k] = fmaxf(ahi[k], c[k]); M = fmaxf(M, fabsf(c[k])); }
         }
-        for (int i = l; i < nb; i += 8) {
+        for (int i = l; i < nb; i += FLP) {
             const float c[3] = {bx[i], by[i], bz[i]};
 #pragma unroll
             for (int k = 0; k < 3; ++k) { sb[k] += c[k]; blo[k] = fminf(blo[k], c[k]); bhi[k] = fmaxf(bhi[k], c[k]); M = fmaxf(M, fabsf(c[k])); }
@@ -110,8 +117,8 @@ separation_filter_kernel(const float *__restrict__ v, const int64_t *__restrict_
             if (len > 1.0e-6f) { const float inv = 1.0f / len; d[0] *= inv; d[1] *= inv; d[2] *= inv; have_d = true; }
         }
         float hA = -3.0e38f, lB = 3.0e38f;
-        for (int i = l; i < na; i += 8) hA = fmaxf(hA, d[0] * ax[i] + d[1] * ay[i] + d[2] * az[i]);
-        for (int i = l; i < nb; i += 8) lB = fminf(lB, d[0] * bx[i] + d[1] * by[i] + d[2] * bz[i]);
+        for (int i = l; i < na; i += FLP) hA = fmaxf(hA, d[0] * ax[i] + d[1] * ay[i] + d[2] * az[i]);
+        for (int i = l; i < nb; i += FLP) lB = fminf(lB, d[0] * bx[i] + d[1] * by[i] + d[2] * bz[i]);
         hA = bfly8_max(hA); lB = bfly8_min(lB);
         if (have_d && (lB - hA) > margin) apart = true;
         const bool keep = valid && !apart;

@@ -413,7 +413,7 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         if (use_filter) {
             unsigned long long *cnt = (unsigned long long *)(p.d_cnt + hostb::MAX_CHUNKS + 2 + k);      // zeroed with the counter block
             const float *v32 = ranged ? (const float *)(in + L.v32) : (const float *)p.d_whole;
-            const int64_t gb = (n * 8 + 255) / 256;          // eight lanes per pair
+            const int64_t gb = (n * f32io::FLP + 255) / 256;         // FLP lanes per pair
             f32io::separation_filter_kernel<<<(unsigned)(gb < gm ? gb : gm), 256, 0, sc>>>(v32, ranged ? (const int64_t *)(in + L.off) : d_off,
                 (const int32_t *)(in + L.pa), (const int32_t *)(in + L.pb), n, need_flags ? (uint8_t *)(out + o_col) : nullptr,
                 w_st ? (uint32_t *)(out + o_st) : nullptr, (uint32_t)GJKEPA_EXIT_EARLY_OUT, (unsigned long long *)p.d_order, cnt);

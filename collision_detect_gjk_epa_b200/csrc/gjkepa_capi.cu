@@ -1,9 +1,11 @@
 // gjkepa_capi.cu -- C ABI (include/gjkepa.h) and host batch scheduler of libgjkepa_b200.so.
 //
 // Replaces, for batches, the call  CALL GJKEPA(version_, TOL_FF_, p1_, p2_, collision_, ...)
-// (reference src/GCLIB_GJKEPA.f90:39-52).  Pipeline per batch, all on one CUDA stream:
-//   K0 hull_prep  -> K1 gjk_kernel<L> (flags + EPA work list) -> K3 epa_kernel (depth, normal,
-//   contact epilogue) on the colliding pairs only.
+// (reference src/GCLIB_GJKEPA.f90:39-52).  gjkepa_batch_device_f64 is the device pipeline, all on one CUDA stream:
+//   K0 hull_prep (shared stores) -> K1 init + compacting walk kernels (flags + EPA work list) -> EPA routing by hull size ->
+//   linked-mesh / general EPA kernels on the colliding pairs only -> K4 contact epilogue.
+// The host-buffer entries (gjkepa_batch_f64 / _f32 / _posed_f64 / _resident_f64) sit on top of it in host_batch.inl: chunked
+// copy / compute / copy pipeline, device-side contact lists, one shard per device of a multi-device context.
 // There is no CPU compute path: without a usable device every entry point fails.
 #include "../../include/gjkepa.h"
 #include "gjk_kernels.cuh"

@@ -73,7 +73,7 @@ typedef struct gjkepa_ctx gjkepa_ctx;
  * Threading: a context owns its streams and its workspace and is used by ONE host thread at a time (several contexts on
  * one device may run from several threads).  gjkepa_pair_f64 is safe to call from any number of threads, OpenMP
  * threads included -- the reference is callable from an !$OMP PARALLEL DO (THREADPRIVATE scratch, F:55-60): concurrent
- * callers are coalesced into one small batch per round trip (see below).
+ * callers are coalesced into one small batch per round trip (see gjkepa_pair_f64).
  * Every entry point leaves the calling thread's current CUDA device as it found it. */
 int  gjkepa_create(gjkepa_ctx **ctx, int32_t device);
 /* One context over n_devices GPUs (devices == NULL or n_devices == 0: every visible GPU).  The reference's model is
@@ -152,7 +152,10 @@ int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
 int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);
 
 /* ---- replaces CALL GJKEPA(...) (F:39-52): one pair, every scalar by reference, HOST arrays ----
- * Uses a process-wide default context on device 0 (created on first call). */
+ * Uses a process-wide default context on device 0 (created on first call).  Safe to call from any number of threads at once:
+ * a caller that finds no batch in flight becomes the leader, takes every request queued so far (its own included), runs them as
+ * ONE small batch and hands each caller its results; callers arriving meanwhile queue up for the next leader.  Throughput is
+ * (calling threads) / (one GPU round trip, ~50-110 us), every result the bits the same pair gets in any batch call. */
 int gjkepa_pair_f64(const int32_t *version, const double *tol_ff,
                     const double *p1, const int32_t *n1, const double *p2, const int32_t *n2,
                     uint8_t *collision, int32_t *colli_type,

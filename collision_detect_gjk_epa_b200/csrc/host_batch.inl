@@ -216,11 +216,11 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
     double per_pair = 8.0 + (r.collision ? 1.0 : 0.0) + (r.status && !r.compact ? 4.0 : 0.0);
     if (!r.compact) per_pair += (r.f32 ? 0.5 : 1.0) * ((w_dep ? 8 : 0) + (w_nrm ? 24 : 0) + (w_pt ? 24 : 0) + (w_near ? 48 : 0)) + (w_type ? 4 : 0);
     if (private_store) per_pair += (r.f32 ? 12.0 : 24.0) * (double)(r.hull_off[r.n_hulls] - r.hull_off[0]) / (double)r.n_pairs;
-    const hostplan::Plan plan = hostplan::plan_shard(np, ctx->host_chunks, per_pair, private_store, r.n_hulls, r.hull_off, pa, pb);
+    hostplan::Plan plan = hostplan::plan_shard(np, ctx->host_chunks, per_pair, private_store, r.n_hulls, r.hull_off, pa, pb, /*lazy=*/true);
     if (plan.bad_index) return fail(ctx, GJKEPA_ERR_ARG, "pair list names a hull outside the store");
     const int nchunk = plan.nchunk;
     const int64_t cp = plan.cp;
-    const std::vector<Chunk> &ch = plan.ch;
+    std::vector<Chunk> &ch = plan.ch;
     const bool ranged = plan.ranged;
     const int64_t Hlo = plan.Hlo, Hhi = plan.Hhi;               // hull range uploaded whole when !ranged
     const int64_t whole_nh = Hhi - Hlo + 1;
@@ -241,9 +241,12 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
     };
     for (int k = 0; k < nchunk; ++k) {
         const int64_t n = ch[k].b - ch[k].a;
+        if (plan.lazy && k > 0) break;                   // lazy plan: sized by the first chunk here, re-checked per chunk below
+        if (plan.lazy && !hostplan::scan_chunk(plan, 0, r.n_hulls, pa, pb)) return fail(ctx, GJKEPA_ERR_ARG, "pair list names a hull outside the store");
         const InL L = ranged ? in_layout(r.hull_off[ch[k].hhi + 1] - r.hull_off[ch[k].hlo], ch[k].hhi - ch[k].hlo + 1, n) : in_layout(0, 0, n);
         need_in = L.total > need_in ? L.total : need_in;
     }
+    if (plan.lazy) need_in += need_in / 16;              // the other chunks of an ordered list are about this size
     // results of a chunk, dense: flags | type | status | reals (nearest, normal, point, depth back to back) | float copy of the reals | selected pairs
     const size_t n_real = (w_near ? 6 : 0) + (w_nrm ? 3 : 0) + (w_pt ? 3 : 0) + (w_dep ? 1 : 0);        // per pair
     const size_t o_col = 0, o_type = o_col + al256(need_flags ? (size_t)cp : 0), o_st = o_type + al256(w_type ? (size_t)cp * 4 : 0),
@@ -371,6 +374,15 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
     for (int k = 0; k < nchunk; ++k) {
         const int s = k & 1;
         const int64_t a = ch[k].a, n = ch[k].b - ch[k].a;
+        if (plan.lazy) {
+            // this chunk's exact hull range, scanned while the copies of the chunk before are on the bus
+            if (k > 0 && !hostplan::scan_chunk(plan, k, r.n_hulls, pa, pb)) return fail(ctx, GJKEPA_ERR_ARG, "pair list names a hull outside the store");
+            const InL Lk = in_layout(r.hull_off[ch[k].hhi + 1] - r.hull_off[ch[k].hlo], ch[k].hhi - ch[k].hlo + 1, n);
+            if (Lk.total > p.cap_in[s]) {                  // rare: a chunk that names a much wider range than the first one
+                CU(cudaStreamSynchronize(sc)); CU(cudaStreamSynchronize(si));
+                if (int rcg = grow_bytes(ctx, p.d_in[s], p.cap_in[s], Lk.total, "cudaMalloc input slot")) return rcg;
+            }
+        }
         char *in = (char *)p.d_in[s], *out = (char *)p.d_out[s];
         const int64_t hlo = ranged ? ch[k].hlo : Hlo;
         const int64_t nh = ranged ? ch[k].hhi - ch[k].hlo + 1 : 0;

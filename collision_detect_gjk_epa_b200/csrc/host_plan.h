@@ -31,14 +31,32 @@ inline int shards_for(int64_t n_pairs, int n_devices)
 
 struct Chunk { int64_t a, b; int64_t hlo, hhi; };      // pairs [a,b) of the shard (shard-relative), hulls [hlo,hhi] they name
 
+// lowest and highest value of v[0..n): the scan is serial host time in front of the first copy of a batch (8 MB of pair lists per
+// 1M pairs), so it is written for the vectoriser (independent accumulators, no branches) and cloned for AVX2 where the CPU has it
+#if defined(__GNUC__) && defined(__x86_64__) && !defined(__CUDACC__) && !defined(__clang__)
+#define HOSTPLAN_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define HOSTPLAN_CLONES
+#endif
+HOSTPLAN_CLONES inline void minmax_i32(const int32_t *v, int64_t n, int32_t &mn_out, int32_t &mx_out)
+{
+    int32_t mn[16], mx[16];
+    for (int k = 0; k < 16; ++k) { mn[k] = 0x7fffffff; mx[k] = -0x7fffffff - 1; }
+    int64_t i = 0;
+    for (; i + 16 <= n; i += 16)
+        for (int k = 0; k < 16; ++k) { const int32_t x = v[i + k]; mn[k] = x < mn[k] ? x : mn[k]; mx[k] = x > mx[k] ? x : mx[k]; }
+    for (; i < n; ++i) { const int32_t x = v[i]; mn[0] = x < mn[0] ? x : mn[0]; mx[0] = x > mx[0] ? x : mx[0]; }
+    for (int k = 1; k < 16; ++k) { mn[0] = mn[k] < mn[0] ? mn[k] : mn[0]; mx[0] = mx[k] > mx[0] ? mx[k] : mx[0]; }
+    mn_out = mn[0]; mx_out = mx[0];
+}
+
 // lowest and highest hull number named by pairs [a,b)
 inline void hull_range(const int32_t *pa, const int32_t *pb, int64_t a, int64_t b, int64_t &lo, int64_t &hi)
 {
-    int32_t mn = 0x7fffffff, mx = -1;
-    for (int64_t i = a; i < b; ++i) {
-        const int32_t x = pa[i], y = pb[i];
-        mn = x < mn ? x : mn; mn = y < mn ? y : mn;
-        mx = x > mx ? x : mx; mx = y > mx ? y : mx;
+    int32_t mn = 0x7fffffff, mx = -1, m0, m1;
+    if (b > a) {
+        minmax_i32(pa + a, b - a, m0, m1); mn = m0 < mn ? m0 : mn; mx = m1 > mx ? m1 : mx;
+        minmax_i32(pb + a, b - a, m0, m1); mn = m0 < mn ? m0 : mn; mx = m1 > mx ? m1 : mx;
     }
     lo = mn; hi = mx;
 }
@@ -63,15 +81,26 @@ inline void chunk_sizes(int64_t np, int forced, double bytes_per_pair, int &nchu
 struct Plan {
     int nchunk = 0; int64_t cp = 0;
     bool ranged = false;                 // every chunk brings its own hull range (pair-private stores)
+    bool lazy = false;                   // ranged, and the chunks' exact ranges are still to be scanned (scan_chunk, just in time)
     int64_t Hlo = 0, Hhi = -1;           // hull range uploaded whole when !ranged
     std::vector<Chunk> ch;
     bool bad_index = false;              // a pair names a hull outside [0, n_hulls)
 };
 
+// exact hull range of chunk k (lazy plans); false if a pair names a hull outside the store
+inline bool scan_chunk(Plan &P, int k, int64_t n_hulls, const int32_t *pa, const int32_t *pb)
+{
+    hull_range(pa, pb, P.ch[k].a, P.ch[k].b, P.ch[k].hlo, P.ch[k].hhi);
+    return P.ch[k].hlo >= 0 && P.ch[k].hhi < n_hulls;
+}
+
 // pa / pb: the SHARD's pair lists (np entries).  scan_store: the store is a host store that may be pair-private (about as
 // many hulls as pairs); otherwise it is shared or already on the device and no pair is looked at.
+// lazy (batches of several chunks): the pair lists are only SAMPLED here (one pair in 509) to tell an ordered list from a random
+// one; the exact range of a chunk is scanned just before its copy is queued, while the copy of the chunk before it is in flight --
+// the full scan (8 MB per 1M pairs, memory-bound) would otherwise be serial host time in front of the first byte on the bus.
 inline Plan plan_shard(int64_t np, int forced_chunks, double bytes_per_pair, bool scan_store, int64_t n_hulls, const int64_t *hull_off,
-                       const int32_t *pa, const int32_t *pb)
+                       const int32_t *pa, const int32_t *pb, bool lazy = false)
 {
     Plan P;
     chunk_sizes(np, forced_chunks, bytes_per_pair, P.nchunk, P.cp);
@@ -80,6 +109,23 @@ inline Plan plan_shard(int64_t np, int forced_chunks, double bytes_per_pair, boo
         P.ch[k].a = (int64_t)k * P.cp; P.ch[k].b = P.ch[k].a + P.cp < np ? P.ch[k].a + P.cp : np; P.ch[k].hlo = 0; P.ch[k].hhi = -1;
     }
     P.Hlo = 0; P.Hhi = n_hulls - 1;
+    if (scan_store && lazy && P.nchunk > 1) {
+        int64_t sum_v = 0, lo_all = n_hulls, hi_all = -1;
+        for (int k = 0; k < P.nchunk; ++k) {
+            int64_t lo = n_hulls, hi = -1;
+            for (int64_t i = P.ch[k].a; i < P.ch[k].b; i += 509) {
+                const int64_t x = pa[i], y = pb[i];
+                if (x < 0 || x >= n_hulls || y < 0 || y >= n_hulls) { P.bad_index = true; return P; }
+                lo = x < lo ? x : lo; lo = y < lo ? y : lo; hi = x > hi ? x : hi; hi = y > hi ? y : hi;
+            }
+            sum_v += hull_off[hi + 1] - hull_off[lo];
+            lo_all = lo < lo_all ? lo : lo_all; hi_all = hi > hi_all ? hi : hi_all;
+        }
+        const int64_t whole_v = hull_off[hi_all + 1] - hull_off[lo_all];
+        P.ranged = sum_v <= whole_v + whole_v / 4;
+        P.lazy = P.ranged;
+        if (P.ranged) return P;          // exact ranges: scan_chunk, chunk by chunk
+    }
     if (scan_store) {
         // look at what the chunks name: when pair i uses hulls near 2i every chunk needs a narrow range and the ranges
         // together are about the store; when pairs name hulls at random every chunk would need all of it

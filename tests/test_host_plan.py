@@ -70,6 +70,20 @@ def test_chunks_tile_a_shard_and_bring_the_hulls_their_pairs_name(plan, forced):
     assert P["Hlo"] == min(pa.min(), pb.min()) and P["Hhi"] == max(pa.max(), pb.max())
 
 
+def test_lazy_plan_decides_from_a_sample_and_scans_chunk_by_chunk(plan):
+    rng = np.random.default_rng(7)
+    n = 600_000
+    hull_off = (np.arange(2 * n + 1) * 8).astype(np.int64)
+    pa = (2 * np.arange(n)).astype(np.int32); pb = pa + 1
+    full = _plan(plan, n, 6, 400.0, 1, hull_off, pa, pb)
+    lazy = _plan(plan, n, 6, 400.0, 2, hull_off, pa, pb)
+    assert lazy["ranged"] and not lazy["bad"] and np.array_equal(lazy["chunks"], full["chunks"])
+    ra = rng.integers(0, 2 * n, size=n).astype(np.int32)              # random list over the same store: the sample sees it
+    assert not _plan(plan, n, 6, 400.0, 2, hull_off, ra, pb)["ranged"]
+    bad = pa.copy(); bad[123_457] = 2 * n                             # not on the sampling grid: found by the exact scan of its chunk
+    assert _plan(plan, n, 6, 400.0, 2, hull_off, bad, pb)["bad"]
+
+
 def test_shared_and_random_stores_go_up_whole(plan):
     rng = np.random.default_rng(1)
     n, nh = 400_000, 300_000

@@ -177,7 +177,8 @@ CONTAINS
         IF (PRESENT(ierr)) THEN
             ierr = INT(rc)
         ELSE IF (rc /= 0) THEN
-            WRITE(0, '(A,A,A,I0,A)') "GCLIB_GJKEPA: ", what, " failed with code ", rc, " (no CPU fallback; outputs left as no-collision)"
+            WRITE(0, '(A,A,A,I0,A)') "GCLIB_GJKEPA: ", what, " failed with code ", rc, &
+                                     " (no CPU fallback; outputs left as no-collision)"
         END IF
     END SUBROUTINE report
 
@@ -387,7 +388,8 @@ CONTAINS
         REAL(C_DOUBLE),     INTENT(OUT), TARGET, CONTIGUOUS :: penetration_depth_(:), collision_normal_(:,:)   ! (3,cap)
         INTEGER(C_INT64_T), INTENT(OUT) :: n_candidates, n_contacts
         INTEGER(C_INT) :: rc
-        rc = gjkepa_scene_posed_f64(ctx, version_, TOL_FF_, INT(SIZE(body_shape), C_INT64_T), C_LOC(body_shape), C_LOC(pose), mode, &
+        rc = gjkepa_scene_posed_f64(ctx, version_, TOL_FF_, INT(SIZE(body_shape), C_INT64_T), C_LOC(body_shape), &
+                                    C_LOC(pose), mode, &
                                     INT(MIN(SIZE(body_a), SIZE(body_b), SIZE(penetration_depth_)), C_INT64_T), C_LOC(body_a), &
                                     C_LOC(body_b), C_LOC(penetration_depth_), C_LOC(collision_normal_), C_NULL_PTR, C_NULL_PTR, &
                                     C_NULL_PTR, n_candidates, n_contacts)
@@ -401,7 +403,8 @@ CONTAINS
         REAL(C_DOUBLE),     INTENT(IN), TARGET, CONTIGUOUS :: verts(:)
         INTEGER(C_INT64_T), INTENT(IN), TARGET, CONTIGUOUS :: hull_off(:)
         INTEGER, INTENT(OUT), OPTIONAL :: ierr
-        CALL report(gjkepa_store_upload(ctx, INT(SIZE(hull_off) - 1, C_INT64_T), C_LOC(verts), C_LOC(hull_off)), ierr, "GJKEPA_STORE_UPLOAD")
+        CALL report(gjkepa_store_upload(ctx, INT(SIZE(hull_off) - 1, C_INT64_T), C_LOC(verts), C_LOC(hull_off)), &
+                    ierr, "GJKEPA_STORE_UPLOAD")
     END SUBROUTINE GJKEPA_STORE_UPLOAD
 
     ! GJKEPA_BATCH against the resident store: results at the pair's index, zero for non-colliding pairs (F:65-71).

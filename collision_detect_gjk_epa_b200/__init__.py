@@ -3,7 +3,7 @@
 Drop-in for the ``GJKEPA`` subroutine of xiejihong0306/collision-detect-GJK-EPA
 (src/GCLIB_GJKEPA.f90:39-52) behind a C ABI (include/gjkepa.h).  See DESIGN.md.
 """
-from .api import GJKEPA, Engine, GjkEpaError, EXIT_NAMES, MODE_GJK, MODE_EPA, MODE_FULL  # noqa: F401
+from .api import GJKEPA, Engine, guard_check, GjkEpaError, EXIT_NAMES, MODE_GJK, MODE_EPA, MODE_FULL  # noqa: F401
 from . import workloads  # noqa: F401
 
-__all__ = ["GJKEPA", "Engine", "GjkEpaError", "EXIT_NAMES", "MODE_GJK", "MODE_EPA", "MODE_FULL", "workloads"]
+__all__ = ["GJKEPA", "Engine", "guard_check", "GjkEpaError", "EXIT_NAMES", "MODE_GJK", "MODE_EPA", "MODE_FULL", "workloads"]

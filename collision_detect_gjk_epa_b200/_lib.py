@@ -25,6 +25,7 @@ SYMBOLS = [
     "gjkepa_launch_count", "gjkepa_set_lanes", "gjkepa_set_max_hull_vertices", "gjkepa_set_tuning", "gjkepa_set_profiling", "gjkepa_kernel_ms", "gjkepa_pair_f64", "gjkepa_batch_f64",
     "gjkepa_batch_device_f64", "gjkepa_sync", "gjkepa_debug_fp64", "gjkepa_shapes_upload", "gjkepa_batch_posed_f64", "gjkepa_broadphase_f64", "gjkepa_broadphase_posed_f64", "gjkepa_batch_f32", "gjkepa_scene_posed_f64",
     "gjkepa_create_multi", "gjkepa_device_count", "gjkepa_host_register", "gjkepa_host_unregister", "gjkepa_store_upload", "gjkepa_batch_resident_f64", "gjkepa_host_phase_ms", "gjkepa_f32_filter_stats",
+    "gjkepa_guard_check", "gjkepa_guard_selftest",
 ]
 
 
@@ -58,6 +59,10 @@ def lib() -> C.CDLL:
     vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
     L.gjkepa_create.argtypes = [C.POINTER(vp), C.c_int32]
     L.gjkepa_create.restype = C.c_int
+    L.gjkepa_guard_check.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.gjkepa_guard_check.restype = C.c_int
+    L.gjkepa_guard_selftest.argtypes = [C.c_int64]
+    L.gjkepa_guard_selftest.restype = C.c_int
     L.gjkepa_create_multi.argtypes = [C.POINTER(vp), ip, C.c_int32]
     L.gjkepa_create_multi.restype = C.c_int
     L.gjkepa_device_count.argtypes = [vp]

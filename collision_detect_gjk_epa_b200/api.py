@@ -329,6 +329,16 @@ class Engine:
         return out
 
 
+def guard_check():
+    """Checking mode (``GJKEPA_GUARD=1`` in the environment before the first call, include/gjkepa.h): returns
+    ``(live device allocations, guard bands that no longer hold their pattern)``; ``None`` outside checking mode."""
+    L = _lib.lib()
+    n, bad = C.c_int64(0), C.c_int64(0)
+    if L.gjkepa_guard_check(C.byref(n), C.byref(bad)) != _lib.OK:
+        return None
+    return int(n.value), int(bad.value)
+
+
 def GJKEPA(version_: int, TOL_FF_: float, p1_, p2_):
     """Drop-in for ``CALL GJKEPA(version_, TOL_FF_, p1_, p2_, collision_, colliType_,
     nearest_points_, collision_normal_, collision_point_, penetration_depth_)`` (F:39-52).

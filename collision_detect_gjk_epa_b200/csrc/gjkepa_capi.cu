@@ -37,6 +37,75 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
+// ---- checking mode (GJKEPA_GUARD=1 in the environment, read once) ----------------------------------------------------
+// compute-sanitizer is not available where this library is developed, so the library carries its own detector for the two
+// faults a workspace scheduler can hide: every device allocation it makes gets a 256-byte band on either side filled with
+// a pattern (a write past either end lands in a band; gjkepa_guard_check counts the bands that changed), and the payload is
+// filled with 0xFF bytes (NaN as a double, -1 as an index) instead of whatever cudaMalloc returns -- usually zeros, which
+// hides a kernel that reads workspace it never wrote.  tests/test_gpu_guard.py runs the whole pipeline in this mode.
+// Off (the default) the wrappers are the plain runtime calls.
+namespace guard {
+constexpr size_t BAND = 256;
+constexpr unsigned char FILL = 0xA5;
+struct Rec { char *base; size_t bytes; int dev; };
+static std::mutex g_mu;
+static std::vector<Rec> g_live;
+static std::atomic<long long> g_bad_at_free{0};
+static bool enabled()
+{
+    static const bool on = [] { const char *e = std::getenv("GJKEPA_GUARD"); return e && *e && *e != '0'; }();
+    return on;
+}
+static int bands_changed(const Rec &r)           // the caller has made r.dev current and idle
+{
+    unsigned char h[2 * BAND];
+    if (cudaMemcpy(h, r.base, BAND, cudaMemcpyDeviceToHost) != cudaSuccess) return 2;
+    if (cudaMemcpy(h + BAND, r.base + BAND + r.bytes, BAND, cudaMemcpyDeviceToHost) != cudaSuccess) return 2;
+    int bad = 0;
+    for (size_t k = 0; k < 2; ++k)
+        for (size_t i = 0; i < BAND; ++i) if (h[k * BAND + i] != FILL) { ++bad; break; }
+    return bad;
+}
+static cudaError_t gmalloc(void **p, size_t bytes)
+{
+    if (!enabled()) return ::cudaMalloc(p, bytes);
+    char *base = nullptr;
+    cudaError_t e = ::cudaMalloc((void **)&base, bytes + 2 * BAND);
+    if (e != cudaSuccess) { *p = nullptr; return e; }
+    e = cudaMemset(base, FILL, BAND);
+    if (e == cudaSuccess && bytes) e = cudaMemset(base + BAND, 0xFF, bytes);
+    if (e == cudaSuccess) e = cudaMemset(base + BAND + bytes, FILL, BAND);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { ::cudaFree(base); *p = nullptr; return e; }
+    Rec r{base, bytes, 0};
+    cudaGetDevice(&r.dev);
+    { std::lock_guard<std::mutex> lk(g_mu); g_live.push_back(r); }
+    *p = base + BAND;
+    return cudaSuccess;
+}
+static cudaError_t gfree(void *p)
+{
+    if (!enabled() || !p) return ::cudaFree(p);
+    Rec r{nullptr, 0, 0};
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (size_t i = 0; i < g_live.size(); ++i)
+            if (g_live[i].base + BAND == (char *)p) { r = g_live[i]; g_live[i] = g_live.back(); g_live.pop_back(); break; }
+    }
+    if (!r.base) return ::cudaFree(p);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(r.dev);
+    cudaDeviceSynchronize();
+    g_bad_at_free += bands_changed(r);
+    const cudaError_t e = ::cudaFree(r.base);
+    cudaSetDevice(cur);
+    return e;
+}
+}  // namespace guard
+#define cudaMalloc(p, n) guard::gmalloc((void **)(p), (n))
+#define cudaFree(p) guard::gfree((void *)(p))
+
 constexpr int hostb_max_chunks = 64;
 constexpr int N_COUNTERS = 64;           // device counter block of a context (work lists, queue heads, EPA routing)
 struct HostPipe;       // host_batch.inl: chunked copy/compute pipeline of the host-buffer entries
@@ -1368,6 +1437,40 @@ void run_pair_jobs(std::vector<PairJob *> &jobs)
 }
 }  // namespace
 extern "C" {
+
+int gjkepa_guard_check(int64_t *n_allocations, int64_t *n_bands_changed)
+{
+    if (n_allocations) *n_allocations = 0;
+    if (n_bands_changed) *n_bands_changed = 0;
+    if (!guard::enabled()) return GJKEPA_ERR_ARG;          // not a checking run: nothing to report
+    int cur = 0;
+    cudaGetDevice(&cur);
+    std::vector<guard::Rec> live;
+    { std::lock_guard<std::mutex> lk(guard::g_mu); live = guard::g_live; }
+    long long bad = guard::g_bad_at_free.load();
+    for (const guard::Rec &r : live) {
+        cudaSetDevice(r.dev);
+        cudaDeviceSynchronize();
+        bad += guard::bands_changed(r);
+    }
+    cudaSetDevice(cur);
+    if (n_allocations) *n_allocations = (int64_t)live.size();
+    if (n_bands_changed) *n_bands_changed = bad;
+    return GJKEPA_OK;
+}
+
+int gjkepa_guard_selftest(int64_t overrun_bytes)
+{
+    // plants a write of `overrun_bytes` past the end of a 1000-byte allocation made the way the library makes all of its own:
+    // a following gjkepa_guard_check must count it (the allocation stays live until the process ends)
+    if (!guard::enabled()) return GJKEPA_ERR_ARG;
+    char *p = nullptr;
+    if (cudaMalloc((void **)&p, 1000) != cudaSuccess) return GJKEPA_ERR_NOMEM;
+    if (overrun_bytes > 0 && cudaMemset(p + 1000, 0, (size_t)(overrun_bytes < 256 ? overrun_bytes : 256)) != cudaSuccess) return GJKEPA_ERR_CUDA;
+    if (overrun_bytes < -256) overrun_bytes = -256;
+    if (overrun_bytes < 0 && cudaMemset(p + overrun_bytes, 0, (size_t)(-overrun_bytes)) != cudaSuccess) return GJKEPA_ERR_CUDA;
+    return cudaDeviceSynchronize() == cudaSuccess ? GJKEPA_OK : GJKEPA_ERR_CUDA;
+}
 
 int gjkepa_pair_f64(const int32_t *version, const double *tol_ff,
                     const double *p1, const int32_t *n1, const double *p2, const int32_t *n2,

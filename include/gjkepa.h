@@ -91,6 +91,17 @@ int  gjkepa_f32_filter_stats(const gjkepa_ctx *ctx, int64_t *out /*[2]*/);
 /* wall clock (ms) of the last HOST-buffer batch call: ms[0] = the shards (copy-in, kernels, per-pair results copied out;
  * devices side by side), ms[1] = the contact rows / contact_index copied to the caller's arrays at their row offsets */
 int  gjkepa_host_phase_ms(const gjkepa_ctx *ctx, double *ms /*[2]*/);
+
+/* ---- checking mode: GJKEPA_GUARD=1 in the environment before the library's first call ----
+ * Every device allocation the library makes is then bracketed by two 256-byte bands holding a pattern and handed out filled
+ * with 0xFF bytes (NaN / -1) instead of the zeros a fresh cudaMalloc usually holds; gjkepa_guard_check idles the devices and
+ * reports the live allocations and how many bands no longer hold the pattern (bands found changed when an allocation was freed
+ * are included).  The reference has nothing like it (its scratch is ALLOCATE / DEALLOCATE per call, F:274-277): this is the
+ * library's own stand-in for a memory checker, used by tests/test_gpu_guard.py.  Outside checking mode both return
+ * GJKEPA_ERR_ARG.  gjkepa_guard_selftest plants a write of overrun_bytes past the end (negative: before the start) of a
+ * scratch allocation so that a test can see the detector fire. */
+int  gjkepa_guard_check(int64_t *n_allocations, int64_t *n_bands_changed);
+int  gjkepa_guard_selftest(int64_t overrun_bytes);
 int  gjkepa_destroy(gjkepa_ctx *ctx);
 /* Optional: page-lock an array the caller passes to the batch calls again and again (cudaHostRegister, portable).  The
  * arrays a Fortran host ALLOCATEs are pageable; copies from pageable memory go through the driver's staging buffer at a

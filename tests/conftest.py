@@ -51,3 +51,27 @@ def engine():
     eng = Engine(0)
     yield eng
     eng.close()
+
+
+_guard_checks = {"tests": 0, "allocations": 0}
+
+
+@pytest.fixture(autouse=True)
+def _guard_bands(request):
+    """Checking mode (GJKEPA_GUARD=1, tests/test_gpu_guard.py): after every GPU test no guard band of any device
+    allocation of the library may have changed."""
+    yield
+    if os.environ.get("GJKEPA_GUARD", "0") in ("", "0") or request.node.get_closest_marker("gpu") is None:
+        return
+    from collision_detect_gjk_epa_b200 import guard_check
+    got = guard_check()
+    assert got is not None, "GJKEPA_GUARD is set but the library is not in checking mode"
+    _guard_checks["tests"] += 1
+    _guard_checks["allocations"] = max(_guard_checks["allocations"], got[0])
+    assert got[1] == 0, f"{got[1]} guard band(s) overwritten (of {got[0]} live allocations) by the end of {request.node.nodeid}"
+
+
+def pytest_terminal_summary(terminalreporter):
+    if _guard_checks["tests"]:
+        terminalreporter.write_line(f"guard: checked the bands of up to {_guard_checks['allocations']} device allocations after "
+                                    f"{_guard_checks['tests']} tests, none overwritten")

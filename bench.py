@@ -684,6 +684,27 @@ def main():
             "flag_mismatch_rate_vs_f64": float(np.mean(f_out["collision"] != flags64)),
             "note": "opt-in: binary32 separation test (3 axes + line of centroids, margin 1e-5 (1 + max|coordinate|)) before the binary64 "
                     "kernels; the exit path of a filtered pair reads EARLY_OUT"}
+        # ... and with the GJK walk itself in binary32 ARITHMETIC (GJKEPA_TUNE_F32_ARITH): the float store is walked
+        # as it arrived, no widening and no binary64 kernel in GJK mode.  Flags are not promised equal: the rate is reported.
+        eng.set_tuning(eng.TUNE_F32_ARITH, 1)
+        for _ in range(2):
+            eng.batch_host_f32(*f_in, mode="gjk", out=f_out)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(kf):
+            eng.batch_host_f32(*f_in, mode="gjk", out=f_out)
+        torch.cuda.synchronize()
+        dtfa = (time.perf_counter() - t0) / kf
+        eng.set_tuning(eng.TUNE_F32_ARITH, 0)
+        fa = f_out["collision"]
+        line["extra"]["e2e_f32_mode"]["with_f32_arithmetic"] = {
+            "value": batch.n_pairs / dtfa, "unit": UNIT, "ms_per_step": dtfa * 1e3,
+            "flag_mismatch_rate_vs_f64_kernels_on_the_same_floats": float(np.mean(fa != flags_nofilter)),
+            "flags_extra": int(((fa > 0) & (flags_nofilter == 0)).sum()), "flags_missing": int(((fa == 0) & (flags_nofilter > 0)).sum()),
+            "flag_mismatch_rate_vs_f64": float(np.mean(fa != flags64)),
+            "note": "opt-in: the reference's flag path compiled with float operands from the source text of the binary64 kernels "
+                    "(csrc/gjk_core_body.inc), thresholds scaled to binary32 (1e-8 -> 1e-5, 1e-12 -> 1e-7); differing pairs touch to "
+                    "within that band (tests/test_gpu_f32_mode.py checks each with Qhull)"}
         eng.set_max_hull_vertices(0)
     if not args.no_extra and args.workload == "cfg2" and world == 1:
         # upstream of the path: candidate pairs built on the device (gjkepa_broadphase_posed_f64) for 1M posed bodies

@@ -83,10 +83,12 @@ class Engine:
         self._check(self._L.gjkepa_set_max_hull_vertices(self._h, int(n)), "gjkepa_set_max_hull_vertices")
 
     TUNE_WALK_REFILL, TUNE_SINGLE_KERNEL, TUNE_EPA_GENERAL, TUNE_TILE_MAX_VERTICES, TUNE_EARLY_OUT, TUNE_HOST_CHUNKS = 1, 2, 3, 4, 5, 6
-    TUNE_LOCALITY_SORT, TUNE_F32_FILTER = 7, 8
+    TUNE_LOCALITY_SORT, TUNE_F32_FILTER, TUNE_F32_ARITH = 7, 8, 9
+    ST_F32_DECIDED = 32 << 16
 
     def f32_filter_stats(self):
-        """(pairs of the last fp32 batch, pairs its binary32 separation filter proved apart) -- GJKEPA_TUNE_F32_FILTER."""
+        """(pairs of the last fp32 batch, pairs its binary32 separation filter proved apart -- GJKEPA_TUNE_F32_FILTER -- or its
+        binary32 walk called separated -- GJKEPA_TUNE_F32_ARITH)."""
         out = (C.c_int64 * 2)()
         self._check(self._L.gjkepa_f32_filter_stats(self._h, out), "gjkepa_f32_filter_stats")
         return int(out[0]), int(out[1])

@@ -17,6 +17,7 @@
 #include "pose_kernel.cuh"
 #include "broadphase.cuh"
 #include "f32_io.cuh"
+#include "gjk_f32.cuh"
 #include "scene.cuh"
 
 #include <cub/device/device_scan.cuh>
@@ -158,6 +159,7 @@ struct gjkepa_ctx {
     const unsigned long long *ext_order = nullptr;      // visiting order of the next batch's pairs (host_batch.inl: locality sort, fp32 filter), or null
     const unsigned long long *ext_order_count = nullptr;   // its length on the device (fp32 filter: the survivors), or null = n_pairs
     int f32_filter = 0;                                  // GJKEPA_TUNE_F32_FILTER
+    int f32_arith = 0;                                   // GJKEPA_TUNE_F32_ARITH: the GJK walk of the fp32 entry in binary32 arithmetic
     int64_t filter_stats[2] = {0, 0};                    // pairs seen / pairs proven apart by the fp32 filter in the last fp32 batch
     int locality_sort = 2;                               // 0 off, 1 always, 2 automatic (GJKEPA_TUNE_LOCALITY_SORT)
     // resident world-space hull store (gjkepa_store_upload)
@@ -378,6 +380,7 @@ int gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value)
     }
     if (key == GJKEPA_TUNE_EARLY_OUT) { ctx->early_out = value != 0; return GJKEPA_OK; }
     if (key == GJKEPA_TUNE_F32_FILTER) { ctx->f32_filter = value != 0; return GJKEPA_OK; }
+    if (key == GJKEPA_TUNE_F32_ARITH) { ctx->f32_arith = value != 0; return GJKEPA_OK; }
     if (key == GJKEPA_TUNE_LOCALITY_SORT) {
         if (value < 0 || value > 2) return GJKEPA_ERR_ARG;
         ctx->locality_sort = value;

@@ -21,6 +21,7 @@
 namespace hostb {
 
 constexpr int MAX_CHUNKS = hostplan::MAX_CHUNKS;
+constexpr int N_CNT = 3 * MAX_CHUNKS + 2;      // HostPipe::d_cnt
 
 // Pair list and hull offsets of a chunk made relative to the first hull / first vertex of the range it brought along, and
 // every hull number checked against the store the kernels will index (n_hulls entries): a number outside it is replaced by 0
@@ -103,7 +104,8 @@ struct HostPipe {
     void *d_sel_tmp = nullptr; size_t cap_sel_tmp = 0;
     void *d_order = nullptr; size_t cap_order = 0;      // locality order of a chunk: keys in | keys out | cub scratch
     int64_t *d_cnt = nullptr;                           // [0..MAX_CHUNKS) contacts per chunk, [MAX_CHUNKS] rows accumulated, [MAX_CHUNKS+1] bad hull numbers,
-                                                        // [MAX_CHUNKS+2 ..) survivors of the fp32 filter per chunk
+                                                        // [MAX_CHUNKS+2 ..) survivors of the fp32 filter / binary32 walk per chunk,
+                                                        // [2*MAX_CHUNKS+2 ..) pairs the binary32 thread-per-pair kernel left to its group kernel
     int64_t *h_cnt = nullptr;                           // pinned mirror
     // accumulator layout of the last shard (run_shard -> finish_shard)
     size_t a_idx = 0, a_dep = 0, a_nrm = 0, a_pt = 0, a_near = 0, a_type = 0, a_st = 0;
@@ -141,8 +143,8 @@ int pipe_get(gjkepa_ctx *ctx, HostPipe **out)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_store, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_cnt, (2 * hostb::MAX_CHUNKS + 2) * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaHostAlloc((void **)&p->h_cnt, (2 * hostb::MAX_CHUNKS + 2) * sizeof(int64_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p->d_cnt, hostb::N_CNT * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaHostAlloc((void **)&p->h_cnt, hostb::N_CNT * sizeof(int64_t), cudaHostAllocDefault);
     ctx->pipe = p;
     if (e != cudaSuccess) { pipe_free(ctx); return fail(ctx, GJKEPA_ERR_CUDA, "host pipeline streams/events", e); }
     *out = p;
@@ -220,6 +222,10 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
     if (plan.bad_index) return fail(ctx, GJKEPA_ERR_ARG, "pair list names a hull outside the store");
     const int nchunk = plan.nchunk;
     const int64_t cp = plan.cp;
+    // fp32 entry with GJKEPA_TUNE_F32_ARITH: the GJK walk itself runs in binary32 (gjk_f32.cuh); the binary64 kernels only see the
+    // pairs it calls colliding, and in GJK mode not even those
+    const bool use_arith = r.src == SRC_HOST_F32 && ctx->f32_arith && ctx->lanes == 0 && !ctx->single_kernel && cp > 256;
+    const bool arith_only = use_arith && !epa;
     std::vector<Chunk> &ch = plan.ch;
     const bool ranged = plan.ranged;
     const int64_t Hlo = plan.Hlo, Hhi = plan.Hhi;               // hull range uploaded whole when !ranged
@@ -276,7 +282,7 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         const size_t a_total = p.a_st + al256(r.compact && w_st ? (size_t)np * 4 : 0);
         if (int rc = grow_bytes(ctx, p.d_acc, p.cap_acc, a_total, "cudaMalloc contact accumulators")) return rc;
     }
-    CU(cudaMemsetAsync(p.d_cnt, 0, (2 * hostb::MAX_CHUNKS + 2) * sizeof(int64_t), sc));
+    CU(cudaMemsetAsync(p.d_cnt, 0, hostb::N_CNT * sizeof(int64_t), sc));
 
     // ---- the store the chunks run against ----
     const double *d_verts = nullptr; const int64_t *d_off = nullptr; int64_t nh_dev = 0;
@@ -316,7 +322,7 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         CU(cudaMemcpyAsync(b + o_off, r.hull_off + Hlo, (size_t)(whole_nh + 1) * 8, cudaMemcpyHostToDevice, si));
         CU(cudaEventRecord(p.ev_store, si));
         CU(cudaStreamWaitEvent(sc, p.ev_store, 0));
-        if (r.f32) {
+        if (r.f32 && !arith_only) {
             const int64_t ne = whole_nv * 3;
             int64_t gb = (ne / 4 + 256) / 256; const int64_t gm = (int64_t)ctx->sm_count * 16;
             f32io::widen_kernel<<<(unsigned)(gb < gm ? gb : gm), 256, 0, sc>>>((const float *)b, (double *)(b + o_v64), ne);
@@ -328,7 +334,7 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
                 nullptr, nullptr, 0, 0, 0, (int64_t *)(b + o_off), whole_nh + 1, whole_v0, nullptr);
             ++ctx->launches;
         }
-        if (nchunk > 1 && !e1_skips_spheres) {
+        if (nchunk > 1 && !e1_skips_spheres && !arith_only) {
             if (int rc = ensure(ctx, ctx->d_sphere, ctx->cap_sphere, nh_dev)) return rc;
             if (int rc = spheres_for(ctx, d_verts, d_off, nh_dev, ctx->d_sphere, sc)) return rc;
             sph = ctx->d_sphere;
@@ -357,11 +363,12 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         while (order_bits < 32 && ((int64_t)1 << order_bits) < nh_all) ++order_bits;
     }
     // fp32 entry with GJKEPA_TUNE_F32_FILTER: the binary32 separation filter runs first and the init kernel visits its survivors
-    const bool use_filter = r.src == SRC_HOST_F32 && ctx->f32_filter && ctx->lanes == 0 && !ctx->single_kernel && cp > 256;
-    if (use_filter) use_order = false;
+    const bool use_filter = !use_arith && r.src == SRC_HOST_F32 && ctx->f32_filter && ctx->lanes == 0 && !ctx->single_kernel && cp > 256;
+    if (use_filter || use_arith) use_order = false;
     ctx->filter_stats[0] = ctx->filter_stats[1] = 0;
     size_t order_tmp = 0, o_keys1 = 0, o_otmp = 0;
     if (use_filter) { if (int rc = grow_bytes(ctx, p.d_order, p.cap_order, al256((size_t)cp * 8), "cudaMalloc survivor list")) return rc; }
+    if (use_arith) { if (int rc = grow_bytes(ctx, p.d_order, p.cap_order, al256((size_t)cp * 8) + al256((size_t)cp * 4), "cudaMalloc survivor list")) return rc; }
     if (use_order) {
         CU(cub::DeviceRadixSort::SortKeys(nullptr, order_tmp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)cp, 32, 32 + order_bits, sc));
         o_keys1 = al256((size_t)cp * 8); o_otmp = 2 * o_keys1;
@@ -402,7 +409,7 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         CU(cudaStreamWaitEvent(sc, p.ev_in[s], 0));
         if (k >= 2) CU(cudaStreamWaitEvent(sc, p.ev_out[s], 0));
         const int64_t gm = (int64_t)ctx->sm_count * 16;
-        if (ranged && r.f32) {
+        if (ranged && r.f32 && !arith_only) {
             const int64_t ne = nv * 3; const int64_t gb = (ne / 4 + 256) / 256;
             f32io::widen_kernel<<<(unsigned)(gb < gm ? gb : gm), 256, 0, sc>>>((const float *)(in + L.v32), (double *)(in + L.v64), ne);
             ++ctx->launches;
@@ -432,16 +439,45 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
             ++ctx->launches;
             ctx->ext_order = (const unsigned long long *)p.d_order; ctx->ext_order_count = cnt;
         }
+        if (use_arith) {
+            gjk32::F32Args fa;
+            fa.verts = ranged ? (const float *)(in + L.v32) : (const float *)p.d_whole;
+            fa.hull_off = ranged ? (const int64_t *)(in + L.off) : d_off;
+            fa.pair_a = (const int32_t *)(in + L.pa); fa.pair_b = (const int32_t *)(in + L.pb); fa.n_pairs = n;
+            fa.collision = need_flags ? (uint8_t *)(out + o_col) : nullptr;
+            fa.status = w_st ? (uint32_t *)(out + o_st) : nullptr;
+            fa.mark = GJKEPA_ST_F32_DECIDED; fa.final_flags = arith_only ? 1 : 0;
+            fa.order = (unsigned long long *)p.d_order;
+            fa.order_count = (unsigned long long *)(p.d_cnt + hostb::MAX_CHUNKS + 2 + k);
+            fa.ovf_list = (int32_t *)((char *)p.d_order + al256((size_t)cp * 8));
+            fa.ovf_count = (unsigned long long *)(p.d_cnt + 2 * hostb::MAX_CHUNKS + 2 + k);
+            fa.pair_list = fa.ovf_list; fa.pair_list_count = fa.ovf_count;
+            const int hint = ctx->max_hull_hint;
+            fa.cap = (hint > 0 && hint < 16) ? hint : 16;
+            fa.early_out = ctx->early_out;
+            const size_t smem_f = (size_t)gjk32::F32_WARPS * 6 * fa.cap * 32 * sizeof(float);
+            int per_sm = 1;
+            CU(cudaFuncSetAttribute(gjk32::gjk_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk32::gjk_f32_kernel, gjk32::F32_WARPS * 32, smem_f));
+            const int64_t want = (n + gjk32::F32_WARPS * 32 - 1) / (gjk32::F32_WARPS * 32), res = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+            gjk32::gjk_f32_kernel<<<(unsigned)(want < res ? want : res), gjk32::F32_WARPS * 32, smem_f, sc>>>(fa);
+            if (hint == 0 || hint > 16) {
+                gjk32::gjk_f32_group_kernel<<<(unsigned)(ctx->sm_count * 8), 128, 0, sc>>>(fa);
+                ++ctx->launches;
+            }
+            ++ctx->launches;
+            ctx->ext_order = (const unsigned long long *)p.d_order; ctx->ext_order_count = fa.order_count;
+        }
         double *r64 = (double *)(out + o_r64);
         ctx->ext_sphere = ranged ? nullptr : sph;
-        int rc = gjkepa_batch_device_f64(ctx, r.version, r.tol_ff, ranged ? nh : nh_dev,
+        int rc = arith_only ? GJKEPA_OK : gjkepa_batch_device_f64(ctx, r.version, r.tol_ff, ranged ? nh : nh_dev,
             ranged ? (const double *)(in + L.v64) : d_verts, ranged ? (const int64_t *)(in + L.off) : d_off, n,
             (const int32_t *)(in + L.pa), (const int32_t *)(in + L.pb), r.mode,
             need_flags ? (uint8_t *)(out + o_col) : nullptr, w_type ? (int32_t *)(out + o_type) : nullptr,
             w_near ? r64 + r_near * cp : nullptr, w_nrm ? r64 + r_nrm * cp : nullptr, w_pt ? r64 + r_pt * cp : nullptr, w_dep ? r64 + r_dep * cp : nullptr,
             w_st ? (uint32_t *)(out + o_st) : nullptr, nullptr, nullptr);
         if (rc) return rc;
-        if (ctx->profiling) {    // a profiled run gives up the overlap: per-kernel durations summed over the chunks
+        if (ctx->profiling && !arith_only) {    // a profiled run gives up the overlap: per-kernel durations summed over the chunks
             double t[3];
             if (int rq = gjkepa_kernel_ms(ctx, t)) return rq;
             for (int q = 0; q < 3; ++q) acc_ms[q] += t[q];
@@ -491,11 +527,11 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
         }
         CU(cudaEventRecord(p.ev_out[s], so));
     }
-    CU(cudaMemcpyAsync(p.h_cnt, p.d_cnt, (2 * hostb::MAX_CHUNKS + 2) * sizeof(int64_t), cudaMemcpyDeviceToHost, sc));
+    CU(cudaMemcpyAsync(p.h_cnt, p.d_cnt, hostb::N_CNT * sizeof(int64_t), cudaMemcpyDeviceToHost, sc));
     CU(cudaStreamSynchronize(sc));
     CU(cudaStreamSynchronize(so));
     CU(cudaStreamSynchronize(si));
-    if (use_filter) {
+    if (use_filter || use_arith) {
         int64_t kept = 0;
         for (int k = 0; k < nchunk; ++k) kept += p.h_cnt[hostb::MAX_CHUNKS + 2 + k];
         ctx->filter_stats[0] = np; ctx->filter_stats[1] = np - kept;

@@ -159,6 +159,20 @@ int  gjkepa_set_max_hull_vertices(gjkepa_ctx *ctx, int32_t n);
  * EARLY_OUT above), so flags are unchanged -- tests/test_gpu_f32_mode.py: 0 mismatches -- while status differs for the filtered
  * pairs.  gjkepa_f32_filter_stats: out[0] = pairs of the last fp32 batch, out[1] = pairs the filter proved apart. */
 #define GJKEPA_TUNE_F32_FILTER     8
+/* F32_ARITH (gjkepa_batch_f32 only; default 0; takes precedence over F32_FILTER): the GJK walk itself in BINARY32 ARITHMETIC --
+ * the reference's flag path (F:76-236) compiled with float operands from the same source text as the binary64 kernels
+ * (csrc/gjk_core_body.inc), reading the float store as it arrived, no widening.  A pair that walk calls separated gets flag 0
+ * and the walk's exit path and iteration count, marked GJKEPA_ST_F32_DECIDED.  GJKEPA_MODE_GJK: the pairs it calls colliding get
+ * flag 1 the same way and no binary64 kernel runs at all.  GJKEPA_MODE_EPA / _FULL: those pairs are handed to the binary64
+ * kernels, which confirm the flag in binary64 and produce depth, normal and the contact epilogue as for any batch.
+ * The reference's absolute thresholds (1e-8 bands, 1e-12 / 1e-15 degeneracy tests) lie below binary32's rounding noise, so
+ * this build scales them to its precision (1e-5, 1e-7, 1e-9; csrc/gjk_core_f32.cuh says why).  Flags can then differ from the
+ * binary64 answer only for pairs that touch to within ~1e-5 of the hull scale: tests/test_host_sim.py (CPU) and
+ * tests/test_gpu_f32_mode.py bound the rate at 1e-4 (measured: 0 of 1.1M random pairs) and check every differing pair's gap
+ * with Qhull; bench.py reports rate and timing. */
+#define GJKEPA_TUNE_F32_ARITH      9
+#define GJKEPA_ST_F32_DECIDED  (32u << 16) /* status of a pair decided by the binary32 walk: 32 in the EPA-iterations field,
+                                            * which is otherwise 0 for every pair without an EPA run */
 #define GJKEPA_EXIT_EARLY_OUT      13
 int  gjkepa_set_tuning(gjkepa_ctx *ctx, int32_t key, int32_t value);
 

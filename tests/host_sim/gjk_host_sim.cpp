@@ -3,6 +3,7 @@
 // Test-only: the shipped library never runs this path.
 #define GJK_SHADOW_HISTORY 1
 #include "../../collision_detect_gjk_epa_b200/csrc/gjk_core.cuh"
+#include "../../collision_detect_gjk_epa_b200/csrc/gjk_core_f32.cuh"
 #include <cstring>
 
 static void gjk_batch_impl(const double *verts, const int64_t *hull_off, int64_t n_pairs,
@@ -60,4 +61,25 @@ extern "C" int hostsim_stall(const double *last1, const double *last2, int have2
 extern "C" void hostsim_shadow_counts(long long *checks, long long *mismatch)
 {
     *checks = gjk::g_shadow_checks; *mismatch = gjk::g_shadow_mismatch;
+}
+
+// The binary32 instantiation of the same text (csrc/gjk_core_f32.cuh, GJKEPA_TUNE_F32_ARITH): float vertices in, flags and the
+// walk's exit path / iteration count out.
+extern "C" void hostsim_gjk32_batch(const float *verts, const int64_t *hull_off, int64_t n_pairs,
+                                    const int32_t *pa, const int32_t *pb, uint8_t *collision, uint32_t *status)
+{
+    using namespace gjk32;
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        HullView A, B;
+        int64_t oa = hull_off[pa[i]], ob = hull_off[pb[i]];
+        A.n = (int)(hull_off[pa[i] + 1] - oa); A.x = verts + 3 * oa; A.y = A.x + A.n; A.z = A.y + A.n;
+        B.n = (int)(hull_off[pb[i] + 1] - ob); B.x = verts + 3 * ob; B.y = B.x + B.n; B.z = B.y + B.n;
+        Sphere sa = hull_sphere(A), sb = hull_sphere(B);
+        Lanes<1> g;
+        Vec3 S[4];
+        GjkOut o = gjk_pair(g, A, B, sa, sb, S, false);
+        collision[i] = exit_is_collision(o.exit_path) ? 1 : 0;
+        status[i] = (uint32_t)o.exit_path | ((uint32_t)o.iters << 8) | (o.stop_flag ? (1u << 25) : 0u);
+    }
 }

@@ -114,3 +114,73 @@ def test_f32_filter_keeps_non_finite_pairs_for_the_binary64_kernels(W, engine):
     got = engine.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode="gjk")
     engine.set_tuning(engine.TUNE_F32_FILTER, 0)
     assert np.array_equal(got["collision"], want["collision"])
+
+
+def _origin_depth(b, i):
+    """Qhull on the Minkowski difference of pair i (binary64, float-rounded vertices): > 0 = overlap depth, < 0 = minus a lower
+    bound of the gap."""
+    from scipy.spatial import ConvexHull
+    p1 = b.hull(int(b.pair_a[i])).astype(np.float32).astype(np.float64)
+    p2 = b.hull(int(b.pair_b[i])).astype(np.float32).astype(np.float64)
+    md = (p1[:, None, :] - p2[None, :, :]).reshape(-1, 3)
+    return float((-ConvexHull(md).equations[:, 3]).min())
+
+
+@pytest.mark.parametrize("maker,kw", [
+    ("make_pairs", dict(kind="box8", n_pairs=300_000, sigma=1.0, seed=81)),
+    ("make_pairs", dict(kind="hull", n_pairs=60_000, sigma=0.85, seed=82, n_vert=32)),
+    ("make_mixed", dict(n_pairs=60_000, sigma=0.6, seed=83)),
+    ("make_shared_store", dict(n_bodies=20_000, n_pairs=300_000, n_vert=16, seed=84)),
+])
+def test_binary32_arithmetic_walk(W, engine, multi_f32, maker, kw):
+    """GJKEPA_TUNE_F32_ARITH (SURVEY.md 8(f)2 as written): the GJK walk in binary32 arithmetic, same source text as the binary64
+    kernels.  Flags are NOT guaranteed equal to the binary64 answer; what is asserted:
+      * GJK mode: the mismatch rate against the binary64 kernels (same float-rounded vertices) is below 1e-4, and EVERY
+        differing pair has a gap or overlap below 1e-4 (Qhull on its Minkowski difference) -- only nearly touching pairs flip;
+      * EPA mode: the binary64 kernels confirm what the binary32 walk calls colliding, so no pair is flagged that the binary64
+        call does not flag, and every contact both report has the binary64 call's depth and normal, bit for bit;
+      * pairs decided by the binary32 walk say so in their status word; chunks and devices do not change a bit."""
+    b = getattr(W, maker)(**kw)
+    v32 = b.verts.astype(np.float32)
+    engine.set_max_hull_vertices(0)
+    engine.set_tuning(engine.TUNE_F32_ARITH, 0)
+    want = engine.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode="epa", want_contacts=True)
+    first = None
+    for eng in (engine, multi_f32):
+        for chunks in (1, 3):
+            eng.set_max_hull_vertices(0)
+            eng.set_tuning(eng.TUNE_HOST_CHUNKS, chunks)
+            eng.set_tuning(eng.TUNE_F32_ARITH, 1)
+            g = eng.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode="gjk", want_contacts=True)
+            total, decided = eng.f32_filter_stats()
+            e = eng.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode="epa", want_contacts=True)
+            eng.set_tuning(eng.TUNE_F32_ARITH, 0)
+            eng.set_tuning(eng.TUNE_HOST_CHUNKS, 0)
+            assert total == b.n_pairs and decided == int((g["collision"] == 0).sum())
+            assert np.all((g["status"] >> 16) & 0xff == 32)                       # every pair was decided in binary32
+            assert g["n_contacts"] == int(g["collision"].sum())
+            assert np.array_equal(g["contact_index"][:g["n_contacts"]], np.nonzero(g["collision"])[0].astype(np.int32))
+            if first is None:
+                first = (g, e)
+                diff = np.nonzero(g["collision"] != want["collision"])[0]
+                rate = len(diff) / b.n_pairs
+                print(f"binary32 walk vs binary64 kernels on {maker}: {len(diff)} of {b.n_pairs} flags differ ({rate:.2e})")
+                assert rate <= 1e-4, rate
+                for i in diff:
+                    d0 = _origin_depth(b, i)
+                    assert abs(d0) < 1e-4, (int(i), d0, int(g["collision"][i]), int(want["collision"][i]))
+                assert 0.05 < g["collision"].mean() < 0.98
+            else:
+                for k in ("collision", "status"):
+                    assert np.array_equal(g[k], first[0][k]), k
+                for k in ("collision", "status", "depth", "normal"):
+                    assert np.array_equal(e[k], first[1][k]), k
+            # EPA mode: binary64 has the last word on every contact
+            assert not np.any((e["collision"] > 0) & (want["collision"] == 0))
+            both = (e["collision"] > 0) & (want["collision"] > 0)
+            assert both.sum() >= 0.999 * (want["collision"] > 0).sum()
+            for k in ("depth", "normal", "status"):
+                assert np.array_equal(e[k][both], want[k][both]), k
+            sep32 = (e["collision"] == 0) & (((e["status"] >> 16) & 0xff) == 32)
+            assert sep32.sum() >= 0.99 * (e["collision"] == 0).sum()              # the rest: survivors binary64 called separated
+            assert np.all(e["depth"][e["collision"] == 0] == 0.0)

@@ -142,3 +142,31 @@ def test_core_follows_the_oracle_on_nonfinite_and_extreme_inputs(orc, W, host_si
     assert np.array_equal(st & 0xffff, o["status"] & 0xffff)
     assert np.array_equal(ns, o["n_support"])
 
+
+
+@pytest.mark.parametrize("maker,kw", [
+    ("make_pairs", dict(kind="box8", n_pairs=200000, sigma=1.0, seed=91)),
+    ("make_pairs", dict(kind="hull", n_pairs=60000, sigma=0.85, n_vert=32, seed=92)),
+    ("make_mixed", dict(n_pairs=40000, sigma=0.6, seed=93)),
+    ("make_shared_store", dict(n_bodies=20000, n_pairs=200000, n_vert=16, seed=94)),
+])
+def test_binary32_instantiation_of_the_core(orc, W, host_sim, maker, kw):
+    """csrc/gjk_core_f32.cuh (GJKEPA_TUNE_F32_ARITH): the same source text compiled with float operands, against
+    the oracle on the same float-rounded vertices.  Flags are not promised equal; the mismatch rate is measured and bounded at
+    1e-4, every walk terminates on one of the reference's exit paths, and separated pairs stay within the iteration cap."""
+    b = getattr(W, maker)(**kw)
+    v32 = b.verts.astype(np.float32)
+    n = b.n_pairs
+    col = np.zeros(n, np.uint8); st = np.zeros(n, np.uint32)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    host_sim.hostsim_gjk32_batch(P(v32, C.c_float), P(b.hull_off, C.c_int64), C.c_int64(n), P(b.pair_a, C.c_int32), P(b.pair_b, C.c_int32),
+                                 P(col, C.c_uint8), P(st, C.c_uint32))
+    o = orc.batch(v32.astype(np.float64), b.hull_off, b.pair_a, b.pair_b, mode=orc.MODE_GJK)
+    rate = float(np.mean(col != o["collision"]))
+    print(f"binary32 core vs oracle on {maker}: mismatch rate {rate:.2e}; "
+          f"mean walk iterations {((st >> 8) & 0xff).mean():.2f} (binary64: {((o['status'] >> 8) & 0xff).mean():.2f})")
+    assert rate <= 1e-4, rate
+    path = st & 0xff
+    assert path.min() >= 1 and path.max() <= 12
+    assert np.array_equal(col > 0, np.isin(path, (4, 6, 10)))
+    assert ((st >> 8) & 0xff).max() <= 50

@@ -131,6 +131,7 @@ def _origin_depth(b, i):
     ("make_pairs", dict(kind="hull", n_pairs=60_000, sigma=0.85, seed=82, n_vert=32)),
     ("make_mixed", dict(n_pairs=60_000, sigma=0.6, seed=83)),
     ("make_shared_store", dict(n_bodies=20_000, n_pairs=300_000, n_vert=16, seed=84)),
+    ("make_touching_mix", dict(n_pairs=40_000, seed=85)),      # planted gaps of 0, 5e-9 and 1e-6: inside binary32's band by construction
 ])
 def test_binary32_arithmetic_walk(W, engine, multi_f32, maker, kw):
     """GJKEPA_TUNE_F32_ARITH (SURVEY.md 8(f)2 as written): the GJK walk in binary32 arithmetic, same source text as the binary64
@@ -165,7 +166,7 @@ def test_binary32_arithmetic_walk(W, engine, multi_f32, maker, kw):
                 diff = np.nonzero(g["collision"] != want["collision"])[0]
                 rate = len(diff) / b.n_pairs
                 print(f"binary32 walk vs binary64 kernels on {maker}: {len(diff)} of {b.n_pairs} flags differ ({rate:.2e})")
-                assert rate <= 1e-4, rate
+                assert rate <= (1e-4 if maker != "make_touching_mix" else 1e-2), rate
                 for i in diff:
                     d0 = _origin_depth(b, i)
                     assert abs(d0) < 1e-4, (int(i), d0, int(g["collision"][i]), int(want["collision"][i]))
@@ -184,3 +185,34 @@ def test_binary32_arithmetic_walk(W, engine, multi_f32, maker, kw):
             sep32 = (e["collision"] == 0) & (((e["status"] >> 16) & 0xff) == 32)
             assert sep32.sum() >= 0.99 * (e["collision"] == 0).sum()              # the rest: survivors binary64 called separated
             assert np.all(e["depth"][e["collision"] == 0] == 0.0)
+
+
+def test_binary32_walk_on_degenerate_and_non_finite_hulls(W, engine):
+    """The binary32 walk on what a hull library would reject: 1-5 vertex 'hulls' (the initial-tetrahedron exits F:86, 123, 157),
+    duplicated vertices, planar polygons, and hulls holding NaN / Inf.  It must terminate on one of the reference's exit paths
+    for every pair, take the binary64 kernels' exits on non-finite hulls (NaN: always FALSE), and on the degenerate families disagree with
+    them only marginally (their outcomes sit ON the thresholds, which the two precisions place differently)."""
+    engine.set_max_hull_vertices(0)
+    for b, bound in ((W.make_mixed(40000, 0.5, seed=3, n_lo=1, n_hi=5), 1e-3), (W.make_nonfinite("nan", 20000), 0.0), (W.make_nonfinite("inf", 20000), 0.0)):
+        v32 = b.verts.astype(np.float32)
+        engine.set_tuning(engine.TUNE_F32_ARITH, 0)
+        want = engine.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode="gjk")
+        engine.set_tuning(engine.TUNE_F32_ARITH, 1)
+        got = engine.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode="gjk")
+        engine.set_tuning(engine.TUNE_F32_ARITH, 0)
+        path = got["status"] & 0xff
+        assert path.min() >= 1 and path.max() <= 12
+        assert np.array_equal(got["collision"] > 0, np.isin(path, (4, 6, 10)))
+        bad = ~np.isfinite(v32)
+        if bad.any():                                  # NaN: the sphere test fails (F:1185) in both; Inf: the same exits in both
+            hull_bad = np.add.reduceat(bad.astype(np.int64), 3 * b.hull_off[:-1]) > 0
+            pair_bad = hull_bad[b.pair_a] | hull_bad[b.pair_b]
+            assert pair_bad.sum() > 1000
+            assert np.array_equal(got["collision"], want["collision"])
+            assert np.array_equal(path[pair_bad], (want["status"] & 0xff)[pair_bad])
+            if np.isnan(v32).any():
+                assert not got["collision"][pair_bad].any()
+        else:
+            rate = float(np.mean(got["collision"] != want["collision"]))
+            print(f"binary32 walk on 1-5 vertex hulls: {rate:.2e} of the flags differ from the binary64 kernels'")
+            assert rate <= bound, rate

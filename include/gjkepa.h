@@ -217,9 +217,10 @@ int gjkepa_batch_resident_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
 
 /* ---- fp32 mode: binary32 at the boundary (north_star: "1e-5 if an fp32 mode is offered") ----
  * Same call with the hull store, the tolerance and the real-valued results as float: half the bytes over PCIe, which
- * bounds the host-buffer step.  The device widens the store once (exact) and runs the SAME binary64 kernels, because
- * the reference's decision thresholds (1e-8 bands F:157,203,1248; 1e-12 degeneracy tests F:1349,1388) lie below
- * binary32's epsilon and a binary32 walk could not evaluate them.  Hence: flags, colli_type and status are exactly
+ * bounds the host-buffer step.  By default the device widens the store once (exact) and runs the SAME binary64 kernels,
+ * because the reference's decision thresholds (1e-8 bands F:157,203,1248; 1e-12 degeneracy tests F:1349,1388) lie below
+ * binary32's epsilon and a binary32 walk cannot evaluate them as written (GJKEPA_TUNE_F32_ARITH above is the opt-in walk in
+ * binary32 arithmetic, with thresholds scaled to it).  Hence, by default: flags, colli_type and status are exactly
  * what gjkepa_batch_f64 returns for the float-rounded vertices; depth / normal / nearest / point are that call's
  * doubles rounded once to float.  Against the unrounded binary64 hulls: depth and normal within 1e-5 (relative to
  * the hull scale), flags equal except for pairs whose gap or overlap is below the rounding of the vertices. */

@@ -26,10 +26,13 @@ MODULE GCLIB_GJKEPA
     PUBLIC :: GJKEPA, GJKEPA_BATCH, GJKEPA_CTX_CREATE, GJKEPA_CTX_DESTROY, GJKEPA_SHAPES_UPLOAD, GJKEPA_BATCH_POSED, &
               GJKEPA_BROADPHASE, GJKEPA_BROADPHASE_POSED, GJKEPA_BATCH_R4, GJKEPA_SCENE_POSED, &
               GJKEPA_CTX_CREATE_MULTI, GJKEPA_STORE_UPLOAD, GJKEPA_BATCH_RESIDENT, GJKEPA_CONTACTS_RESIDENT, &
-              GJKEPA_PIN, GJKEPA_UNPIN, GJKEPA_LAST_STATUS
+              GJKEPA_PIN, GJKEPA_UNPIN, GJKEPA_LAST_STATUS, GJKEPA_SET_TUNING, GJKEPA_SET_MAX_HULL_VERTICES
 
     INTEGER(C_INT32_T), PARAMETER, PUBLIC :: GJKEPA_MODE_GJK = 0, GJKEPA_MODE_EPA = 1, GJKEPA_MODE_FULL = 2
     INTEGER(C_INT32_T), PARAMETER, PUBLIC :: GJKEPA_MODE_COMPACT = 16       ! OR-ed into mode: one row per contact
+    ! keys of GJKEPA_SET_TUNING (include/gjkepa.h GJKEPA_TUNE_*): none changes a result except as gjkepa.h states
+    INTEGER(C_INT32_T), PARAMETER, PUBLIC :: GJKEPA_TUNE_EARLY_OUT = 5, GJKEPA_TUNE_HOST_CHUNKS = 6, &
+                                             GJKEPA_TUNE_LOCALITY_SORT = 7, GJKEPA_TUNE_F32_FILTER = 8, GJKEPA_TUNE_F32_ARITH = 9
 
     INTEGER(C_INT), SAVE :: last_status = 0
     !$OMP THREADPRIVATE(last_status)
@@ -61,6 +64,18 @@ MODULE GCLIB_GJKEPA
             INTEGER(C_INT32_T), VALUE :: n_devices
             INTEGER(C_INT) :: rc
         END FUNCTION gjkepa_create_multi
+        FUNCTION gjkepa_set_tuning(ctx, key, val) BIND(C, NAME="gjkepa_set_tuning") RESULT(rc)
+            IMPORT :: C_PTR, C_INT, C_INT32_T
+            TYPE(C_PTR), VALUE :: ctx
+            INTEGER(C_INT32_T), VALUE :: key, val
+            INTEGER(C_INT) :: rc
+        END FUNCTION
+        FUNCTION gjkepa_set_max_hull_vertices(ctx, n) BIND(C, NAME="gjkepa_set_max_hull_vertices") RESULT(rc)
+            IMPORT :: C_PTR, C_INT, C_INT32_T
+            TYPE(C_PTR), VALUE :: ctx
+            INTEGER(C_INT32_T), VALUE :: n
+            INTEGER(C_INT) :: rc
+        END FUNCTION
         FUNCTION gjkepa_store_upload(ctx, n_hulls, verts, hull_off) BIND(C, NAME="gjkepa_store_upload") RESULT(rc)
             IMPORT :: C_PTR, C_INT, C_INT64_T
             TYPE(C_PTR), VALUE :: ctx, verts, hull_off
@@ -219,6 +234,24 @@ CONTAINS
         INTEGER, INTENT(OUT), OPTIONAL :: ierr
         CALL report(gjkepa_create(ctx, INT(device, C_INT32_T)), ierr, "GJKEPA_CTX_CREATE")
     END SUBROUTINE GJKEPA_CTX_CREATE
+
+    ! Knobs of a context (keys GJKEPA_TUNE_* above): kernel selection, host pipeline, the opt-in shortcut E1, the fp32 entry's
+    ! binary32 filter / binary32 walk.  A multi-device context passes them on to every device.
+    SUBROUTINE GJKEPA_SET_TUNING(ctx, key, val, ierr)
+        TYPE(C_PTR), INTENT(IN) :: ctx
+        INTEGER*4, INTENT(IN) :: key, val
+        INTEGER, INTENT(OUT), OPTIONAL :: ierr
+        CALL report(gjkepa_set_tuning(ctx, INT(key, C_INT32_T), INT(val, C_INT32_T)), ierr, "GJKEPA_SET_TUNING")
+    END SUBROUTINE GJKEPA_SET_TUNING
+
+    ! The caller's bound on vertices per hull (0 = unknown): sizes the shared-memory columns.  A pair that violates it is
+    ! reported in its status word (GJKEPA_ST_BAD_HINT, flag .FALSE.), never processed silently.
+    SUBROUTINE GJKEPA_SET_MAX_HULL_VERTICES(ctx, n, ierr)
+        TYPE(C_PTR), INTENT(IN) :: ctx
+        INTEGER*4, INTENT(IN) :: n
+        INTEGER, INTENT(OUT), OPTIONAL :: ierr
+        CALL report(gjkepa_set_max_hull_vertices(ctx, INT(n, C_INT32_T)), ierr, "GJKEPA_SET_MAX_HULL_VERTICES")
+    END SUBROUTINE GJKEPA_SET_MAX_HULL_VERTICES
 
     ! One context over several GPUs of the box (devices absent: every visible GPU).  The batch routines below then split
     ! the pair list into one contiguous range per GPU inside the library and every GPU copies its results straight into

@@ -52,3 +52,34 @@ def test_product_does_not_touch_the_oracle():
         assert not imp.search(p.read_text()), p
     out = __import__("subprocess").run(["ldd", str(pkg / "libgjkepa_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def c_arg_counts():
+    """name -> number of parameters of every function include/gjkepa.h declares."""
+    txt = (ROOT / "include" / "gjkepa.h").read_text()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(gjkepa_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_fortran_shim_binds_only_declared_functions_with_matching_argument_counts():
+    """No Fortran compiler exists here, so the ISO_C_BINDING shim is at least checked as text: every BIND(C, NAME=...) names
+    a function of include/gjkepa.h, its dummy list has that function's number of parameters, no line exceeds the free-form
+    limit of 132 columns, and every PUBLIC procedure is defined."""
+    src = (ROOT / "fortran" / "gclib_gjkepa.f90").read_text()
+    assert max(len(l) for l in src.splitlines()) <= 132
+    counts = c_arg_counts()
+    joined = re.sub(r"&\s*\n\s*&?", " ", src)                  # continuation lines
+    binds = re.findall(r"FUNCTION\s+(\w+)\s*\(([^)]*)\)\s*BIND\(C,\s*NAME=\"(\w+)\"\)", joined)
+    assert len(binds) >= 15
+    for fname, dummies, cname in binds:
+        assert fname == cname, (fname, cname)
+        assert cname in counts, f"{cname} is not declared in include/gjkepa.h"
+        n = len([d for d in dummies.split(",") if d.strip()])
+        assert n == counts[cname], f"{cname}: {n} dummies in the shim, {counts[cname]} parameters in the header"
+    pub = re.search(r"PUBLIC\s*::(.*?)\n\s*\n", joined, flags=re.S).group(1)
+    for name in re.findall(r"\b(GJKEPA\w*)\b", pub):
+        assert re.search(rf"(SUBROUTINE|FUNCTION)\s+{name}\b", src), f"PUBLIC {name} has no definition"

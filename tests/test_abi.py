@@ -83,3 +83,12 @@ def test_fortran_shim_binds_only_declared_functions_with_matching_argument_count
     pub = re.search(r"PUBLIC\s*::(.*?)\n\s*\n", joined, flags=re.S).group(1)
     for name in re.findall(r"\b(GJKEPA\w*)\b", pub):
         assert re.search(rf"(SUBROUTINE|FUNCTION)\s+{name}\b", src), f"PUBLIC {name} has no definition"
+
+
+def test_header_and_example_are_plain_c99(tmp_path):
+    """The boundary is a C ABI: include/gjkepa.h and the example that uses it must compile as C99, pedantically, without the
+    C++ front end."""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"), "-c",
+                        str(ROOT / "examples" / "gjkepa_example.c"), "-o", str(tmp_path / "ex.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]

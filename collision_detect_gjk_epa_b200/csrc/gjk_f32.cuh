@@ -9,6 +9,10 @@
 //                              for hulls of at most `cap` (<= 16) vertices; other pairs go to the overflow list.
 //   K1fg gjk_f32_group_kernel  the overflow list by sub-warps of 4 lanes over global memory (a lane scans vertices
 //                              l, l+4, ...: a group's load touches one 16-byte run).
+// K1f is the one-kernel form on purpose: split into an init kernel and a walk kernel with re-packed warps, as the binary64
+// path is, it was SLOWER (cfg2 0.19 + 0.29 ms against 0.38 ms, cfg5 0.35 + 0.49 against 0.62 ms, same bits;
+// profiles/r2_ab_f32_two_stage.txt): a float walk round is cheap, and re-staging a lane's hulls at every re-pack costs more
+// than the idle lanes it removes.
 //
 // What leaves the kernels: flag 0 and the binary32 walk's exit path / iteration count (marked GJKEPA_ST_F32_DECIDED) for a
 // pair the walk calls separated -- final; a pair it calls colliding is appended to the survivor list.  In GJK mode the
@@ -46,7 +50,8 @@ struct HullViewCol {
 
 __device__ __forceinline__ uint32_t pack_status(const GjkOut &o, uint32_t mark)
 {
-    return (uint32_t)o.exit_path | ((uint32_t)o.iters << 8) | (o.stop_flag ? (1u << 25) : 0u) | mark;
+    return (uint32_t)o.exit_path | ((uint32_t)o.iters << 8) | (o.stop_flag ? (1u << 25) : 0u)
+         | (o.exit_path == EXIT_TRI_ORIGIN ? (1u << 28) : 0u) | mark;
 }
 
 // flag / status of one decided pair and the warp-aggregated append of the survivors

@@ -236,6 +236,27 @@ void multi_free(gjkepa_ctx *ctx);
 static const std::vector<gjkepa_ctx *> &multi_kids(const gjkepa_ctx *ctx);
 static gjkepa_ctx *first_kid(const gjkepa_ctx *ctx);
 
+// seed queue between the two GJK stages (gjk_two_stage.cuh; the binary32 walk of gjk_f32.cuh reuses the same arrays)
+static int ensure_seed_queue(gjkepa_ctx *ctx, int64_t n_pairs)
+{
+    if (n_pairs <= ctx->cap_seed) return GJKEPA_OK;
+    if (ctx->d_seed_f64) cudaFree(ctx->d_seed_f64);
+    if (ctx->d_seed_pair) cudaFree(ctx->d_seed_pair);
+    if (ctx->d_seed_fl) cudaFree(ctx->d_seed_fl);
+    if (ctx->d_seed_off) cudaFree(ctx->d_seed_off);
+    if (ctx->d_seed_idx) cudaFree(ctx->d_seed_idx);
+    ctx->d_seed_f64 = nullptr; ctx->d_seed_pair = nullptr; ctx->d_seed_fl = nullptr; ctx->d_seed_off = nullptr; ctx->d_seed_idx = nullptr; ctx->cap_seed = 0;
+    const int64_t ncap = ((n_pairs + n_pairs / 8 + 1024) + 31) & ~(int64_t)31;
+    cudaError_t e = cudaMalloc((void **)&ctx->d_seed_f64, (size_t)ncap * gjk::SEED_F64 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_pair, (size_t)ncap * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_fl, (size_t)ncap * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_off, (size_t)ncap * 2 * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_idx, (size_t)ncap * sizeof(uint2));
+    if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc seed queue", e);
+    ctx->cap_seed = ncap;
+    return GJKEPA_OK;
+}
+
 extern "C" {
 
 int gjkepa_create(gjkepa_ctx **out, int32_t device)
@@ -528,22 +549,7 @@ int gjkepa_batch_device_f64(gjkepa_ctx *ctx, int32_t version, double tol_ff,
         ta.b = a;
         ta.col_units = 2 * 3 * ((cap_vertices + 1) / 2);
         ta.refill = ctx->walk_refill;
-        if (n_pairs > ctx->cap_seed) {
-            if (ctx->d_seed_f64) cudaFree(ctx->d_seed_f64);
-            if (ctx->d_seed_pair) cudaFree(ctx->d_seed_pair);
-            if (ctx->d_seed_fl) cudaFree(ctx->d_seed_fl);
-            if (ctx->d_seed_off) cudaFree(ctx->d_seed_off);
-            if (ctx->d_seed_idx) cudaFree(ctx->d_seed_idx);
-            ctx->d_seed_f64 = nullptr; ctx->d_seed_pair = nullptr; ctx->d_seed_fl = nullptr; ctx->d_seed_off = nullptr; ctx->d_seed_idx = nullptr; ctx->cap_seed = 0;
-            const int64_t ncap = ((n_pairs + n_pairs / 8 + 1024) + 31) & ~(int64_t)31;
-            cudaError_t e = cudaMalloc((void **)&ctx->d_seed_f64, (size_t)ncap * gjk::SEED_F64 * sizeof(double));
-            if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_pair, (size_t)ncap * sizeof(int32_t));
-            if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_fl, (size_t)ncap * sizeof(uint32_t));
-            if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_off, (size_t)ncap * 2 * sizeof(int64_t));
-            if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_seed_idx, (size_t)ncap * sizeof(uint2));
-            if (e != cudaSuccess) return fail(ctx, GJKEPA_ERR_NOMEM, "cudaMalloc seed queue", e);
-            ctx->cap_seed = ncap;
-        }
+        rc = ensure_seed_queue(ctx, n_pairs); if (rc) return rc;
         ta.q.f64 = ctx->d_seed_f64; ta.q.pair = ctx->d_seed_pair; ta.q.fln = ctx->d_seed_fl; ta.q.idx = ctx->d_seed_idx;
         ta.q.oa = ctx->d_seed_off; ta.q.ob = ctx->d_seed_off + ctx->cap_seed;
         ta.q.count = ctx->d_counters + 6; ta.q.head = ctx->d_counters + 7; ta.q.cap = ctx->cap_seed;

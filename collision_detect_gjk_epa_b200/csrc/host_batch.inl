@@ -456,16 +456,21 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
             fa.cap = (hint > 0 && hint < 16) ? hint : 16;
             fa.early_out = ctx->early_out;
             const size_t smem_f = (size_t)gjk32::F32_WARPS * 6 * fa.cap * 32 * sizeof(float);
-            int per_sm = 1;
-            CU(cudaFuncSetAttribute(gjk32::gjk_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk32::gjk_f32_kernel, gjk32::F32_WARPS * 32, smem_f));
-            const int64_t want = (n + gjk32::F32_WARPS * 32 - 1) / (gjk32::F32_WARPS * 32), res = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
-            gjk32::gjk_f32_kernel<<<(unsigned)(want < res ? want : res), gjk32::F32_WARPS * 32, smem_f, sc>>>(fa);
+            const int64_t want = (n + gjk32::F32_WARPS * 32 - 1) / (gjk32::F32_WARPS * 32);
+            auto launch_f = [&](void (*kernel)(gjk32::F32Args), bool persistent) -> int {
+                int per_sm = 1;
+                CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, gjk32::F32_WARPS * 32, smem_f));
+                const int64_t res = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 1);
+                kernel<<<(unsigned)(persistent || res < want ? res : want), gjk32::F32_WARPS * 32, smem_f, sc>>>(fa);
+                ++ctx->launches;
+                return GJKEPA_OK;
+            };
+            if (int rcl = launch_f(gjk32::gjk_f32_kernel, false)) return rcl;
             if (hint == 0 || hint > 16) {
                 gjk32::gjk_f32_group_kernel<<<(unsigned)(ctx->sm_count * 8), 128, 0, sc>>>(fa);
                 ++ctx->launches;
             }
-            ++ctx->launches;
             ctx->ext_order = (const unsigned long long *)p.d_order; ctx->ext_order_count = fa.order_count;
         }
         double *r64 = (double *)(out + o_r64);

@@ -467,10 +467,9 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
                 return GJKEPA_OK;
             };
             if (int rcl = launch_f(gjk32::gjk_f32_kernel, false)) return rcl;
-            if (hint == 0 || hint > 16) {
-                gjk32::gjk_f32_group_kernel<<<(unsigned)(ctx->sm_count * 8), 128, 0, sc>>>(fa);
-                ++ctx->launches;
-            }
+            // always: a hull above the caller's bound must still get its answer (the bound only sizes K1f's columns here)
+            gjk32::gjk_f32_group_kernel<<<(unsigned)(ctx->sm_count * 8), 128, 0, sc>>>(fa);
+            ++ctx->launches;
             ctx->ext_order = (const unsigned long long *)p.d_order; ctx->ext_order_count = fa.order_count;
         }
         double *r64 = (double *)(out + o_r64);

@@ -216,3 +216,19 @@ def test_binary32_walk_on_degenerate_and_non_finite_hulls(W, engine):
             rate = float(np.mean(got["collision"] != want["collision"]))
             print(f"binary32 walk on 1-5 vertex hulls: {rate:.2e} of the flags differ from the binary64 kernels'")
             assert rate <= bound, rate
+
+
+def test_binary32_walk_ignores_a_bound_the_data_violates(W, engine):
+    """gjkepa_set_max_hull_vertices only sizes the binary32 kernel's columns: hulls above it take the 4-lane kernel, and every
+    pair gets the answer it gets without the bound."""
+    b = W.make_mixed(30000, 0.5, seed=31, n_lo=4, n_hi=40)
+    v32 = b.verts.astype(np.float32)
+    engine.set_tuning(engine.TUNE_F32_ARITH, 1)
+    engine.set_max_hull_vertices(0)
+    want = engine.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode="gjk")
+    for hint in (8, 12, 16, 40):
+        engine.set_max_hull_vertices(hint)
+        got = engine.batch_host_f32(v32, b.hull_off, b.pair_a, b.pair_b, mode="gjk")
+        assert np.array_equal(got["collision"], want["collision"]) and np.array_equal(got["status"], want["status"]), hint
+    engine.set_max_hull_vertices(0)
+    engine.set_tuning(engine.TUNE_F32_ARITH, 0)

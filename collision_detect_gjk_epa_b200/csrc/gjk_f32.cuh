@@ -7,8 +7,8 @@
 //   K1f  gjk_f32_kernel        one thread per pair; the two hulls of the 32 pairs of a warp staged once in shared memory,
 //                              element e of lane l's pair at col[e * 32 + l] (a lane reads its own bank: conflict free),
 //                              for hulls of at most `cap` (<= 16) vertices; other pairs go to the overflow list.
-//   K1fg gjk_f32_group_kernel  the overflow list by sub-warps of 4 lanes over global memory (a lane scans vertices
-//                              l, l+4, ...: a group's load touches one 16-byte run).
+//   K1fg gjk_f32_group_kernel  the overflow list by sub-warps of 4 lanes: the pair's blocks copied verbatim into a shared-memory
+//                              slot (nA + nB <= 128; larger pairs are walked over global memory), a lane scans vertices l, l+4, ...
 // K1f is the one-kernel form on purpose: split into an init kernel and a walk kernel with re-packed warps, as the binary64
 // path is, it was SLOWER (cfg2 0.19 + 0.29 ms against 0.38 ms, cfg5 0.35 + 0.49 against 0.62 ms, same bits;
 // profiles/r2_ab_f32_two_stage.txt): a float walk round is cheap, and re-staging a lane's hulls at every re-pack costs more
@@ -125,12 +125,34 @@ gjk_f32_kernel(F32Args a)
     }
 }
 
+// the pair's two blocks [x(n) | y(n) | z(n)] copied verbatim into a shared-memory slot
+struct HullViewSlot {
+    const float *x, *y, *z;
+    int n;
+    __device__ __forceinline__ Vec3 get(int i) const { return v3(x[i], y[i], z[i]); }
+};
+
+constexpr int F32_SLOT_VERTS = 128;                        // nA + nB a slot holds
+constexpr int F32_SLOT_FLOATS = 3 * F32_SLOT_VERTS + 4;    // +4: the 8 slots of a warp start 4 banks apart, a group's 4 lanes read 4 banks
+
+template <class HV>
+__device__ __forceinline__ GjkOut group_walk(const Lanes<4> &g, const HV &A, const HV &B, bool early)
+{
+    Sphere sa, sb;
+    if (early) { sa.cx = sa.cy = sa.cz = sa.r = 0.0f; sb = sa; }
+    else { sa = hull_sphere(A); sb = hull_sphere(B); }
+    Vec3 S[4];
+    return gjk_pair(g, A, B, sa, sb, S, early);
+}
+
 __global__ void __launch_bounds__(128)
 gjk_f32_group_kernel(F32Args a)
 {
+    extern __shared__ __align__(16) float smf[];
     constexpr int L = 4, GPW = 32 / L;
     const Lanes<L> g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane / L;
+    float *slot = smf + (size_t)(warp * GPW + grp) * F32_SLOT_FLOATS;
     const int64_t n_items = (int64_t)(*a.pair_list_count);
     const int64_t n_tiles = (n_items + GPW - 1) / GPW;
     const int64_t n_warps = (int64_t)gridDim.x * 4;
@@ -148,13 +170,21 @@ gjk_f32_group_kernel(F32Args a)
             A.x = a.verts + 3 * oa; A.y = A.x + A.n; A.z = A.y + A.n;
             B.x = a.verts + 3 * ob; B.y = B.x + B.n; B.z = B.y + B.n;
         }
+        const bool fits = valid && A.n + B.n <= F32_SLOT_VERTS;
+        __syncwarp();                                  // the previous tile's slots are no longer read
+        if (fits) {                                    // a group's lanes copy 16-byte runs of its pair's blocks
+            for (int e = g.lane; e < 3 * A.n; e += L) slot[e] = __ldg(A.x + e);
+            for (int e = g.lane; e < 3 * B.n; e += L) slot[3 * A.n + e] = __ldg(B.x + e);
+        }
+        __syncwarp();
         GjkOut o; o.exit_path = 0; o.iters = 0; o.n_support = 0; o.stop_flag = false; o.cold = 0; o.band = 0;
-        if (valid) {                                   // the group's four lanes take this branch together
-            Sphere sa, sb;
-            if (a.early_out) { sa.cx = sa.cy = sa.cz = sa.r = 0.0f; sb = sa; }
-            else { sa = hull_sphere(A); sb = hull_sphere(B); }
-            Vec3 S[4];
-            o = gjk_pair(g, A, B, sa, sb, S, a.early_out != 0);
+        if (fits) {                                    // the group's four lanes take this branch together
+            HullViewSlot SA, SB;
+            SA.x = slot; SA.y = slot + A.n; SA.z = slot + 2 * A.n; SA.n = A.n;
+            SB.x = slot + 3 * A.n; SB.y = SB.x + B.n; SB.z = SB.y + B.n; SB.n = B.n;
+            o = group_walk(g, SA, SB, a.early_out != 0);
+        } else if (valid) {                            // larger than a slot: over global memory
+            o = group_walk(g, A, B, a.early_out != 0);
         }
         __syncwarp();
         emit(a, valid, g.lane == 0, p, o);

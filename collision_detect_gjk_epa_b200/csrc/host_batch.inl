@@ -468,8 +468,14 @@ int run_shard(gjkepa_ctx *ctx, const Req &r, int64_t P0, int64_t P1, int64_t *co
             };
             if (int rcl = launch_f(gjk32::gjk_f32_kernel, false)) return rcl;
             // always: a hull above the caller's bound must still get its answer (the bound only sizes K1f's columns here)
-            gjk32::gjk_f32_group_kernel<<<(unsigned)(ctx->sm_count * 8), 128, 0, sc>>>(fa);
-            ++ctx->launches;
+            {
+                const size_t smem_g = (size_t)4 * 8 * gjk32::F32_SLOT_FLOATS * sizeof(float);
+                int per_sm = 1;
+                CU(cudaFuncSetAttribute(gjk32::gjk_f32_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+                CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gjk32::gjk_f32_group_kernel, 128, smem_g));
+                gjk32::gjk_f32_group_kernel<<<(unsigned)(ctx->sm_count * (per_sm > 0 ? per_sm : 1)), 128, smem_g, sc>>>(fa);
+                ++ctx->launches;
+            }
             ctx->ext_order = (const unsigned long long *)p.d_order; ctx->ext_order_count = fa.order_count;
         }
         double *r64 = (double *)(out + o_r64);
